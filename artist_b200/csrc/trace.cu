@@ -1,0 +1,670 @@
+// Fused heliostat ray tracer: forward (flux bitmaps + factors) and backward (gradients to the
+// aligned surface points / normals).  One CTA per heliostat-sample (or per chunk of its surface
+// points when there are few samples), thread <-> surface point, loop over the R rays of the point
+// in registers.  See DESIGN.md "Kernels" for the data layout and the roofline of each kernel.
+//
+// Flux accumulation: a window of the U x E bitmap around the heliostat's focal spot lives in
+// shared memory as a 32-bit FIXED-POINT histogram updated with native integer atomics
+// (ATOMS.ADD; fp32 shared atomics are a CAS loop on sm_100a - measured 3.4x slower, see
+// profiles/r01_atomics_microbench.txt).  Integer adds are order independent, so the bitmap is
+// bit-reproducible run to run.  Rays that fall outside the window use integer REDG atomics on
+// the (pre-zeroed) output row itself, which is converted to fp32 in place afterwards.
+#include <cstdarg>
+#include <cstring>
+#include "trace_device.cuh"
+
+namespace ab200 {
+
+static thread_local char g_error_detail[512] = "";
+
+void set_error_detail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error_detail, sizeof(g_error_detail), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    int dev = 0, n = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+struct TraceParams {
+    ab200_trace_args a;
+    int split;          // CTAs per heliostat-sample
+    int pts_per_chunk;  // surface points per CTA
+    int win_cap;        // shared-memory window capacity (32-bit cells)
+    float fx_scale;     // fixed-point scale (counts per unit of flux)
+    float fx_inv;       // 1 / fx_scale (signed)
+    float sigma;        // scatter sigma used for the window margin
+};
+
+// Window of the bitmap held in shared memory, in (iu, ie) index space.
+struct Window {
+    int e0, u0, ww, wh;
+};
+
+constexpr int kWindowSampleStride = 4;
+
+// ---------------------------------------------------------------------------------------------
+// window placement: bounding box of the undistorted reflections of a subset of the CTA's points,
+// grown by ~4 sigma of the sun shape projected onto the target.  Correctness never depends on
+// the window (misses take the global path); it only decides how many rays take the fast path.
+// ---------------------------------------------------------------------------------------------
+template <int THREADS>
+__device__ void place_window(Window& win_out, const TraceParams& prm, const TargetCtx& T, int h, int p_begin, int p_end,
+                             float i0, float i1, float i2, float* red /* [6*32] */, Window* win_sh) {
+    const int tid = threadIdx.x;
+    const int P = prm.a.n_points;
+    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float inf = __int_as_float(0x7f800000);
+    float emin = inf, emax = -inf, umin = inf, umax = -inf, tmax = 0.f, cmin = inf;
+    for (int p = p_begin + tid * kWindowSampleStride; p < p_end; p += THREADS * kWindowSampleStride) {
+        PointCtx pc;
+        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        float be, bu, t, cosi;
+        const bool ok = T.planar ? centre_planar(T, pc, be, bu, t, cosi) : centre_cylinder(T, pc, be, bu, t, cosi);
+        if (ok && be == be && bu == bu && fabsf(be) < 1e6f && fabsf(bu) < 1e6f) {
+            emin = fminf(emin, be); emax = fmaxf(emax, be);
+            umin = fminf(umin, bu); umax = fmaxf(umax, bu);
+            tmax = fmaxf(tmax, t);  cmin = fminf(cmin, cosi);
+        }
+    }
+    emin = warp_min(emin); emax = warp_max(emax); umin = warp_min(umin); umax = warp_max(umax);
+    tmax = warp_max(tmax); cmin = warp_min(cmin);
+    const int warp = tid >> 5, lane = tid & 31;
+    if (lane == 0) {
+        red[warp] = emin; red[32 + warp] = emax; red[64 + warp] = umin; red[96 + warp] = umax;
+        red[128 + warp] = tmax; red[160 + warp] = cmin;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = THREADS / 32;
+        emin = lane < nw ? red[lane] : inf;         emax = lane < nw ? red[32 + lane] : -inf;
+        umin = lane < nw ? red[64 + lane] : inf;    umax = lane < nw ? red[96 + lane] : -inf;
+        tmax = lane < nw ? red[128 + lane] : 0.f;   cmin = lane < nw ? red[160 + lane] : inf;
+        emin = warp_min(emin); emax = warp_max(emax); umin = warp_min(umin); umax = warp_max(umax);
+        tmax = warp_max(tmax); cmin = warp_min(cmin);
+        if (lane == 0) {
+            Window w;
+            const int E = prm.a.res_e, U = prm.a.res_u;
+            if (!(emin <= emax) || prm.win_cap < 4) {
+                w.e0 = 1 << 28; w.u0 = 1 << 28; w.ww = 0; w.wh = 0;  // nothing takes the fast path
+            } else {
+                const float m = 4.0f * prm.sigma * tmax / fmaxf(cmin, 0.1f);
+                const float me = m * T.px_per_m_e + 2.0f, mu = m * T.px_per_m_u + 2.0f;
+                int e_lo = max(0, (int)floorf(emin - me)), e_hi = min(E - 1, (int)ceilf(emax + me) + 1);
+                int u_lo = max(0, (int)floorf(umin - mu)), u_hi = min(U - 1, (int)ceilf(umax + mu) + 1);
+                int ww = max(0, e_hi - e_lo + 1), wh = max(0, u_hi - u_lo + 1);
+                if ((long long)ww * wh > prm.win_cap) {
+                    // keep the aspect ratio, centre on the bounding box
+                    const float sc = sqrtf((float)prm.win_cap / ((float)ww * (float)wh));
+                    int nww = max(2, (int)(ww * sc)), nwh = max(2, (int)(wh * sc));
+                    while ((long long)nww * nwh > prm.win_cap) { if (nww > nwh) --nww; else --nwh; }
+                    e_lo += (ww - nww) / 2; u_lo += (wh - nwh) / 2;
+                    ww = nww; wh = nwh;
+                }
+                if (ww < 2 || wh < 2) { w.e0 = 1 << 28; w.u0 = 1 << 28; w.ww = 0; w.wh = 0; }
+                else { w.e0 = e_lo; w.u0 = u_lo; w.ww = ww; w.wh = wh; }
+            }
+            *win_sh = w;
+        }
+    }
+    __syncthreads();
+    win_out = *win_sh;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 1024 ? 1 : 2))
+trace_fwd_kernel(const TraceParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* win_u = reinterpret_cast<unsigned*>(smem_raw);
+    float* win_f = reinterpret_cast<float*>(smem_raw);
+    __shared__ TargetCtx T_sh;
+    __shared__ Window win_sh;
+    __shared__ float red[6 * 32];
+    __shared__ int cnt_sh[2];
+    __shared__ int fallback_sh;
+
+    const int tid = threadIdx.x;
+    const int li = blockIdx.x / prm.split;
+    const int chunk = blockIdx.x - li * prm.split;
+    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const int p_begin = chunk * prm.pts_per_chunk;
+    const int p_end = min(P, p_begin + prm.pts_per_chunk);
+
+    if (tid == 0) {
+        load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
+        cnt_sh[0] = 0; cnt_sh[1] = 0; fallback_sh = 0;
+    }
+    __syncthreads();
+    const TargetCtx T = T_sh;
+    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
+                i2 = __ldg(prm.a.incident + 4 * h + 2);
+
+    Window W;
+    place_window<THREADS>(W, prm, T, h, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    const int wcells = W.ww * W.wh;
+    for (int i = tid; i < wcells; i += THREADS) win_u[i] = 0u;
+    __syncthreads();
+
+    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    float* out_f = prm.a.flux + (size_t)h * U * E;
+    unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
+    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
+    const float fxs = prm.fx_scale;
+
+    int cnt_lam = 0, cnt_int = 0;
+    bool fell_back = false;
+
+    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+        PointCtx pc;
+        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        const float2* dp = dist + p;
+        float2 d_next = __ldcs(dp);
+        for (int r = 0; r < R; ++r) {
+            const float2 d = d_next;
+            if (r + 1 < R) d_next = __ldcs(dp + (size_t)(r + 1) * P);
+            Scatter s;
+            ray_trig<TRIG>(d.x, d.y, trig, (size_t)r * P + p, s.cu, s.su, s.ce, s.se);
+            scatter(s, pc);
+            Hit hit;
+            if (T.planar) hit_planar(hit, T, pc, s, mag); else hit_cylinder(hit, T, pc, s, mag);
+            // intensities = lambert * (1 - blocked) * (1 - extinction) * reflectivity   (:482-487)
+            const float inten = smul(smul(smul(hit.lam, 1.0f), ome), refl);
+            if (DBG) {
+                const size_t q = ((size_t)h * R + r) * P + p;
+                if (prm.a.dbg_be) prm.a.dbg_be[q] = hit.be;
+                if (prm.a.dbg_bu) prm.a.dbg_bu[q] = hit.bu;
+                if (prm.a.dbg_t) prm.a.dbg_t[q] = hit.t;
+                if (prm.a.dbg_lambert) prm.a.dbg_lambert[q] = hit.lam;
+            }
+            cnt_lam += (hit.lam > 0.0f);
+            cnt_int += (inten > 0.0f);
+            if (!hit.valid) continue;
+            Splat sp;
+            splat_weights(sp, hit.be, hit.bu, E, U);
+            if (!sp.on) continue;
+            const int ce = sp.ie - W.e0, cu = sp.iu - W.u0;
+            const bool fast = (ce >= 0) && (ce + 1 < W.ww) && (cu >= 0) && (cu + 1 < W.wh);
+            if (FP32ACC) {
+                const float v1 = smul(smul(sp.wle, sp.whu), inten), v2 = smul(smul(sp.whe, sp.whu), inten);
+                const float v3 = smul(smul(sp.whe, sp.wlu), inten), v4 = smul(smul(sp.wle, sp.wlu), inten);
+                if (fast) {
+                    const int b = cu * W.ww + ce;
+                    atomicAdd(win_f + b + W.ww, v1); atomicAdd(win_f + b + W.ww + 1, v2);
+                    atomicAdd(win_f + b + 1, v3);    atomicAdd(win_f + b, v4);
+                } else {
+                    float* row_hi = out_f + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
+                    float* row_lo = out_f + (size_t)(U - 1 - sp.iu) * E + sp.ie;
+                    atomicAdd(row_hi, v1); atomicAdd(row_hi + 1, v2); atomicAdd(row_lo + 1, v3); atomicAdd(row_lo, v4);
+                }
+            } else {
+                const float ahi = fabsf(sp.whu * inten) * fxs, alo = fabsf(sp.wlu * inten) * fxs;
+                const unsigned q1 = __float2uint_rn(sp.wle * ahi), q2 = __float2uint_rn(sp.whe * ahi);
+                const unsigned q3 = __float2uint_rn(sp.whe * alo), q4 = __float2uint_rn(sp.wle * alo);
+                if (fast) {
+                    const int b = cu * W.ww + ce;
+                    atomicAdd(win_u + b + W.ww, q1); atomicAdd(win_u + b + W.ww + 1, q2);
+                    atomicAdd(win_u + b + 1, q3);    atomicAdd(win_u + b, q4);
+                } else {
+                    // per-tap routing: a tap inside the window region must go to shared memory so that
+                    // window pixels are owned by shared memory only
+                    fell_back = true;
+                    const bool e_in0 = (ce >= 0) && (ce < W.ww), e_in1 = (ce + 1 >= 0) && (ce + 1 < W.ww);
+                    const bool u_in0 = (cu >= 0) && (cu < W.wh), u_in1 = (cu + 1 >= 0) && (cu + 1 < W.wh);
+                    unsigned* g_hi = out_u + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
+                    unsigned* g_lo = out_u + (size_t)(U - 1 - sp.iu) * E + sp.ie;
+                    const int b = cu * W.ww + ce;
+                    if (u_in1 && e_in0) atomicAdd(win_u + b + W.ww, q1); else atomicAdd(g_hi, q1);
+                    if (u_in1 && e_in1) atomicAdd(win_u + b + W.ww + 1, q2); else atomicAdd(g_hi + 1, q2);
+                    if (u_in0 && e_in1) atomicAdd(win_u + b + 1, q3); else atomicAdd(g_lo + 1, q3);
+                    if (u_in0 && e_in0) atomicAdd(win_u + b, q4); else atomicAdd(g_lo, q4);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: counters, window flush -----------------------------------------------------
+    cnt_lam = warp_sum(cnt_lam);
+    cnt_int = warp_sum(cnt_int);
+    if ((tid & 31) == 0) {
+        if (cnt_lam) atomicAdd(&cnt_sh[0], cnt_lam);
+        if (cnt_int) atomicAdd(&cnt_sh[1], cnt_int);
+    }
+    if (!FP32ACC && fell_back) fallback_sh = 1;
+    if (!FP32ACC) __threadfence();  // integer REDs of this thread are performed before the barrier
+    __syncthreads();
+
+    const bool single = (prm.split == 1);
+    if (tid == 0) {
+        if (single) {
+            const float rp = (float)(R * P);
+            prm.a.on_target[h] = sdiv((float)cnt_sh[0], rp);
+            prm.a.intercept[h] = sdiv((float)cnt_sh[1], rp);
+            prm.a.blocking[h] = 1.0f;  // (blocked < 1e-3).sum() / (R*P) with blocked == 0
+        } else {
+            atomicAdd(reinterpret_cast<int*>(prm.a.on_target) + h, cnt_sh[0]);
+            atomicAdd(reinterpret_cast<int*>(prm.a.intercept) + h, cnt_sh[1]);
+        }
+    }
+
+    const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
+    if (FP32ACC) {
+        for (int r = warp; r < W.wh; r += nwarps) {
+            float* orow = out_f + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
+            for (int c = lane; c < W.ww; c += 32) {
+                const float v = win_f[r * W.ww + c];
+                if (v != 0.0f) atomicAdd(orow + c, v);
+            }
+        }
+        return;
+    }
+    if (single) {
+        const float inv = prm.fx_inv;
+        const bool any_fb = fallback_sh != 0;
+        for (int r = warp; r < W.wh; r += nwarps) {
+            float* orow = out_f + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
+            for (int c = lane; c < W.ww; c += 32) orow[c] = __uint2float_rn(win_u[r * W.ww + c]) * inv;
+        }
+        if (any_fb) {
+            // rare: convert the integer taps that landed outside the window, in place
+            for (int row = warp; row < U; row += nwarps) {
+                const int iu = U - 1 - row;
+                const bool row_in = (iu >= W.u0) && (iu < W.u0 + W.wh);
+                for (int c = lane; c < E; c += 32) {
+                    if (row_in && c >= W.e0 && c < W.e0 + W.ww) continue;
+                    const unsigned q = __ldcg(out_u + (size_t)row * E + c);
+                    if (q) out_f[(size_t)row * E + c] = __uint2float_rn(q) * inv;
+                }
+            }
+        }
+    } else {
+        for (int r = warp; r < W.wh; r += nwarps) {
+            unsigned* orow = out_u + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
+            for (int c = lane; c < W.ww; c += 32) {
+                const unsigned q = win_u[r * W.ww + c];
+                if (q) atomicAdd(orow + c, q);
+            }
+        }
+    }
+}
+
+// split mode only: integer bitmap / counters -> fp32, in place
+__global__ void finalize_split_kernel(const TraceParams prm) {
+    const int li = blockIdx.y;
+    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
+    const int UE = prm.a.res_u * prm.a.res_e;
+    float* out_f = prm.a.flux + (size_t)h * UE;
+    unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < UE; i += gridDim.x * blockDim.x) {
+        const unsigned q = out_u[i];
+        if (q) out_f[i] = __uint2float_rn(q) * prm.fx_inv;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const float rp = (float)(prm.a.n_rays * prm.a.n_points);
+        const int c0 = reinterpret_cast<int*>(prm.a.on_target)[h];
+        const int c1 = reinterpret_cast<int*>(prm.a.intercept)[h];
+        prm.a.on_target[h] = sdiv((float)c0, rp);
+        prm.a.intercept[h] = sdiv((float)c1, rp);
+        prm.a.blocking[h] = 1.0f;
+    }
+}
+
+__global__ void finalize_split_fp32_kernel(const TraceParams prm) {
+    const int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li >= prm.a.n_local) return;
+    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
+    const float rp = (float)(prm.a.n_rays * prm.a.n_points);
+    const int c0 = reinterpret_cast<int*>(prm.a.on_target)[h];
+    const int c1 = reinterpret_cast<int*>(prm.a.intercept)[h];
+    prm.a.on_target[h] = sdiv((float)c0, rp);
+    prm.a.intercept[h] = sdiv((float)c1, rp);
+    prm.a.blocking[h] = 1.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+template <int THREADS, int TRIG>
+__global__ void __launch_bounds__(THREADS, (THREADS >= 1024 ? 1 : 2))
+trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, float* __restrict__ grad_points,
+                 float* __restrict__ grad_normals) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* win_g = reinterpret_cast<float*>(smem_raw);
+    __shared__ TargetCtx T_sh;
+    __shared__ Window win_sh;
+    __shared__ float red[6 * 32];
+
+    const int tid = threadIdx.x;
+    const int li = blockIdx.x / prm.split;
+    const int chunk = blockIdx.x - li * prm.split;
+    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const int p_begin = chunk * prm.pts_per_chunk;
+    const int p_end = min(P, p_begin + prm.pts_per_chunk);
+
+    if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
+    __syncthreads();
+    const TargetCtx T = T_sh;
+    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
+                i2 = __ldg(prm.a.incident + 4 * h + 2);
+
+    Window W;
+    place_window<THREADS>(W, prm, T, h, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    const float* gf = grad_flux + (size_t)h * U * E;
+    {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
+        const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
+        for (int r = warp; r < W.wh; r += nwarps) {
+            const float* grow = gf + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
+            for (int c = lane; c < W.ww; c += 32) win_g[r * W.ww + c] = __ldg(grow + c);
+        }
+    }
+    __syncthreads();
+
+    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
+    const float k_int = mag * ome * refl;          // d intensity / d lambert-cosine
+    const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
+
+    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+        const float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+        PointCtx pc;
+        make_point(pc, T, i0, i1, i2, o4, n4);
+        float go0 = 0.f, go1 = 0.f, go2 = 0.f;   // planar: grad origin (world); cylindrical: grad origin (cylinder frame)
+        float gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;   // grad preferred reflection direction
+        const float2* dp = dist + p;
+        float2 d_next = __ldcs(dp);
+        for (int r = 0; r < R; ++r) {
+            const float2 d = d_next;
+            if (r + 1 < R) d_next = __ldcs(dp + (size_t)(r + 1) * P);
+            Scatter s;
+            ray_trig<TRIG>(d.x, d.y, trig, (size_t)r * P + p, s.cu, s.su, s.ce, s.se);
+            scatter(s, pc);
+            Hit hit;
+            if (T.planar) hit_planar(hit, T, pc, s, mag); else hit_cylinder(hit, T, pc, s, mag);
+            if (!hit.valid) continue;
+            Splat sp;
+            splat_weights(sp, hit.be, hit.bu, E, U);
+            if (!sp.on) continue;
+            // gather the four gradient taps
+            float g1, g2, g3, g4;
+            const int ce = sp.ie - W.e0, cu = sp.iu - W.u0;
+            if ((ce >= 0) && (ce + 1 < W.ww) && (cu >= 0) && (cu + 1 < W.wh)) {
+                const int b = cu * W.ww + ce;
+                g1 = win_g[b + W.ww]; g2 = win_g[b + W.ww + 1]; g3 = win_g[b + 1]; g4 = win_g[b];
+            } else {
+                const float* row_hi = gf + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
+                const float* row_lo = gf + (size_t)(U - 1 - sp.iu) * E + sp.ie;
+                g1 = __ldg(row_hi); g2 = __ldg(row_hi + 1); g3 = __ldg(row_lo + 1); g4 = __ldg(row_lo);
+            }
+            const float inten = hit.lam * ome * refl;
+            const float g_int = sp.whu * (sp.wle * g1 + sp.whe * g2) + sp.wlu * (sp.whe * g3 + sp.wle * g4);
+            const float g_be = inten * (sp.whu * (g2 - g1) + sp.wlu * (g3 - g4));
+            const float g_bu = inten * (sp.wle * (g1 - g4) + sp.whe * (g2 - g3));
+            float gdx, gdy, gdz;
+            if (T.planar) {
+                const float g_a0 = -g_int * k_int;                 // lam = mag * (-a)
+                const float gX = -g_be * k_e, gZ = g_bu * k_u;     // be = (E-1) - te/w*(E-1)
+                go0 += gX; go2 += gZ;
+                const float gt = gX * s.dx + gZ * s.dz;
+                const float gnum = gt / hit.a;                     // t = num / a
+                const float g_a = g_a0 - gnum * hit.t;
+                go0 -= gnum * T.n0; go1 -= gnum * T.n1; go2 -= gnum * T.n2;
+                gdx = gX * hit.t + g_a * T.n0;
+                gdy = g_a * T.n1;
+                gdz = gZ * hit.t + g_a * T.n2;
+            } else {
+                const float g_ang = g_be * (T.em1 / T.opn), g_z = g_bu * k_u;
+                const float inv_n = 1.0f / hit.nrm, inv_n2 = inv_n * inv_n;
+                const float sdot = hit.dlx * hit.x + hit.dly * hit.y;    // lam = -sdot / nrm  (if positive)
+                const float g_lam = (sdot < 0.0f) ? g_int * k_int : 0.0f;
+                const float gs = -g_lam * inv_n, gn = g_lam * sdot * inv_n2;
+                float gx = gs * hit.dlx + gn * hit.x * inv_n - g_ang * hit.y * inv_n2;
+                float gy = gs * hit.dly + gn * hit.y * inv_n + g_ang * hit.x * inv_n2;
+                float gdlx = gs * hit.x + gx * hit.t;
+                float gdly = gs * hit.y + gy * hit.t;
+                float gdlz = g_z * hit.t;
+                const float gt = gx * hit.dlx + gy * hit.dly + g_z * hit.dlz;
+                const float inv_2a = 0.5f / hit.qa;
+                float gqb = -gt * inv_2a;
+                const float gsq = (hit.near_root ? -gt : gt) * inv_2a;
+                float gqa = -gt * hit.t / hit.qa;
+                const float gdisc = gsq * 0.5f / hit.sq;
+                gqb += 2.0f * hit.qb * gdisc;
+                gqa -= 4.0f * pc.cc * gdisc;
+                const float gcc = -4.0f * hit.qa * gdisc;
+                go0 += gx + 2.0f * pc.ox * gcc + 2.0f * hit.dlx * gqb;
+                go1 += gy + 2.0f * pc.oy * gcc + 2.0f * hit.dly * gqb;
+                go2 += g_z;
+                gdlx += 2.0f * pc.ox * gqb + 2.0f * hit.dlx * gqa;
+                gdly += 2.0f * pc.oy * gqb + 2.0f * hit.dly * gqa;
+                gdx = T.ux * gdlx + T.n0 * gdly + T.ax0 * gdlz;
+                gdy = T.uy * gdlx + T.n1 * gdly + T.ax1 * gdlz;
+                gdz = T.uz * gdlx + T.n2 * gdly + T.ax2 * gdlz;
+            }
+            // d = M r  ->  grad r += M^T grad d
+            gr0 += s.cu * gdx + s.m10 * gdy + s.m20 * gdz;
+            gr1 += -s.su * gdx + s.m11 * gdy + s.m21 * gdz;
+            gr2 += -s.se * gdy + s.ce * gdz;
+        }
+        float gp0, gp1, gp2;
+        if (T.planar) { gp0 = go0; gp1 = go1; gp2 = go2; }
+        else {  // origin_local = Rot (o - c)
+            gp0 = T.ux * go0 + T.n0 * go1 + T.ax0 * go2;
+            gp1 = T.uy * go0 + T.n1 * go1 + T.ax1 * go2;
+            gp2 = T.uz * go0 + T.n2 * go1 + T.ax2 * go2;
+        }
+        // r = i - 2 (i.n) n   ->   grad n = -2 [ (i.n) grad r + (grad r . n) i ]
+        const float grn = gr0 * n4.x + gr1 * n4.y + gr2 * n4.z;
+        const float gn0 = -2.0f * (pc.dot * gr0 + grn * i0);
+        const float gn1 = -2.0f * (pc.dot * gr1 + grn * i1);
+        const float gn2 = -2.0f * (pc.dot * gr2 + grn * i2);
+        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = make_float4(gp0, gp1, gp2, 0.f);
+        reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = make_float4(gn0, gn1, gn2, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int32_t validate(const ab200_trace_args* a) {
+    AB200_REQUIRE(a != nullptr, AB200_EINVAL, "args is NULL");
+    AB200_REQUIRE(a->abi_version == AB200_ABI_VERSION, AB200_EINVAL, "abi_version %d != %d", a->abi_version, AB200_ABI_VERSION);
+    AB200_REQUIRE(a->n_samples >= 0 && a->n_points > 0 && a->n_rays > 0, AB200_EINVAL, "bad sizes N=%d P=%d R=%d",
+                  a->n_samples, a->n_points, a->n_rays);
+    AB200_REQUIRE(a->res_e >= 2 && a->res_u >= 2, AB200_EINVAL, "bitmap resolution must be >= 2x2 (got %dx%d)", a->res_e, a->res_u);
+    AB200_REQUIRE(a->n_local >= 0 && a->n_local <= a->n_samples, AB200_EINVAL, "n_local %d out of range", a->n_local);
+    AB200_REQUIRE((long long)a->n_points * a->n_rays < (1ll << 30), AB200_ELIMIT, "P*R too large");
+    AB200_REQUIRE(a->points && a->normals && a->incident && a->distortions && a->target_idx, AB200_EINVAL, "NULL input pointer");
+    AB200_REQUIRE(a->trig_mode != AB200_TRIG_TABLE || a->trig, AB200_EINVAL, "trig_mode TABLE needs args->trig");
+    AB200_REQUIRE(a->trig_mode >= 0 && a->trig_mode <= 2, AB200_EINVAL, "bad trig_mode %d", a->trig_mode);
+    AB200_REQUIRE(a->targets.n_planar + a->targets.n_cyl > 0, AB200_EINVAL, "no target areas");
+    AB200_REQUIRE(a->blockers.n_blockers == 0, AB200_EINVAL, "blocking is not supported by this build");
+    return AB200_OK;
+}
+
+struct LaunchPlan {
+    int threads, split, pts_per_chunk, smem_bytes;
+};
+
+static LaunchPlan make_plan(int n_local, int n_points, int max_threads_large) {
+    LaunchPlan pl;
+    const int sms = sm_count();
+    if (n_local >= 2 * sms) {
+        pl.threads = max_threads_large; pl.split = 1; pl.smem_bytes = 200 * 1024;
+    } else {
+        pl.threads = 512;
+        const int want = (4 * sms + (n_local > 0 ? n_local : 1) - 1) / (n_local > 0 ? n_local : 1);
+        const int max_split = (n_points + pl.threads - 1) / pl.threads;
+        pl.split = want < 1 ? 1 : (want > max_split ? max_split : want);
+        pl.smem_bytes = 100 * 1024;
+    }
+    pl.pts_per_chunk = (n_points + pl.split - 1) / pl.split;
+    return pl;
+}
+
+static void fill_params(TraceParams& prm, const ab200_trace_args* a, const LaunchPlan& pl) {
+    prm.a = *a;
+    prm.split = pl.split;
+    prm.pts_per_chunk = pl.pts_per_chunk;
+    prm.win_cap = pl.smem_bytes / 4;
+    const double k = (double)a->ray_magnitude * (double)a->one_minus_extinction * (double)a->reflectivity;
+    const double imax = (k < 0 ? -k : k) * 1.01;   // |lambert cosine| <= 1 for unit vectors (+1% slack)
+    const double rays = (double)a->n_points * (double)a->n_rays;
+    if (imax > 0.0) {
+        const double s = (4294967295.0 - 2.0 * rays) / (rays * imax) * (1.0 - 1e-6);
+        prm.fx_scale = (float)s;
+        prm.fx_inv = (float)((k < 0 ? -1.0 : 1.0) / (double)prm.fx_scale);
+    } else {
+        prm.fx_scale = 0.f;
+        prm.fx_inv = 0.f;
+    }
+    prm.sigma = a->scatter_sigma > 0.f ? a->scatter_sigma : 2.5e-3f;
+}
+
+template <int THREADS, int TRIG>
+static cudaError_t launch_fwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, bool dbg, bool fp32acc) {
+    const int grid = prm.a.n_local * pl.split;
+#define AB200_LAUNCH_FWD(DBG, ACC)                                                                           \
+    do {                                                                                                     \
+        auto kern = trace_fwd_kernel<THREADS, TRIG, DBG, ACC>;                                               \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes); \
+        if (e != cudaSuccess) return e;                                                                      \
+        kern<<<grid, THREADS, pl.smem_bytes, st>>>(prm);                                                     \
+    } while (0)
+    if (dbg) { if (fp32acc) AB200_LAUNCH_FWD(true, true); else AB200_LAUNCH_FWD(true, false); }
+    else     { if (fp32acc) AB200_LAUNCH_FWD(false, true); else AB200_LAUNCH_FWD(false, false); }
+#undef AB200_LAUNCH_FWD
+    return cudaGetLastError();
+}
+
+template <int THREADS>
+static cudaError_t launch_fwd_trig(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, bool dbg, bool fp32acc) {
+    switch (prm.a.trig_mode) {
+        case AB200_TRIG_TABLE: return launch_fwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, dbg, fp32acc);
+        case AB200_TRIG_POLY: return launch_fwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, dbg, fp32acc);
+        default: return launch_fwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, dbg, fp32acc);
+    }
+}
+
+template <int THREADS, int TRIG>
+static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
+                              float* gpts, float* gnrm) {
+    auto kern = trace_bwd_kernel<THREADS, TRIG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gpts, gnrm);
+    return cudaGetLastError();
+}
+
+template <int THREADS>
+static cudaError_t launch_bwd_trig(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
+                                   float* gpts, float* gnrm) {
+    switch (prm.a.trig_mode) {
+        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gpts, gnrm);
+        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gpts, gnrm);
+        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gpts, gnrm);
+    }
+}
+
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
+    int32_t rc = validate(a);
+    if (rc != AB200_OK) return rc;
+    AB200_REQUIRE(a->flux && a->intercept && a->on_target && a->blocking, AB200_EINVAL, "NULL output pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t ue = (size_t)a->res_u * a->res_e;
+    // rows not traced by this rank stay zero; traced rows are accumulated into / overwritten
+    AB200_CUDA_TRY(cudaMemsetAsync(a->flux, 0, (size_t)a->n_samples * ue * sizeof(float), st));
+    AB200_CUDA_TRY(cudaMemsetAsync(a->intercept, 0, (size_t)a->n_samples * sizeof(float), st));
+    AB200_CUDA_TRY(cudaMemsetAsync(a->on_target, 0, (size_t)a->n_samples * sizeof(float), st));
+    AB200_CUDA_TRY(cudaMemsetAsync(a->blocking, 0, (size_t)a->n_samples * sizeof(float), st));
+    if (a->n_local == 0 || a->n_samples == 0) return AB200_OK;
+    const LaunchPlan pl = make_plan(a->n_local, a->n_points, 1024);
+    TraceParams prm;
+    fill_params(prm, a, pl);
+    const bool dbg = a->dbg_be || a->dbg_bu || a->dbg_t || a->dbg_lambert;
+    const bool fp32acc = (a->flags & AB200_FLAG_FP32_ACCUM) != 0;
+    cudaError_t e = (pl.threads == 1024) ? launch_fwd_trig<1024>(prm, pl, st, dbg, fp32acc)
+                                         : launch_fwd_trig<512>(prm, pl, st, dbg, fp32acc);
+    AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_fwd launch failed: %s", cudaGetErrorString(e));
+    if (pl.split > 1) {
+        if (!fp32acc) {
+            dim3 grid((unsigned)((ue + 1023) / 1024 < 64 ? (ue + 1023) / 1024 : 64), (unsigned)a->n_local);
+            finalize_split_kernel<<<grid, 256, 0, st>>>(prm);
+        } else {
+            finalize_split_fp32_kernel<<<(a->n_local + 127) / 128, 128, 0, st>>>(prm);
+        }
+        AB200_CUDA_TRY(cudaGetLastError());
+    }
+    return AB200_OK;
+}
+
+extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) {
+    AB200_REQUIRE(b != nullptr, AB200_EINVAL, "args is NULL");
+    const ab200_trace_args* a = &b->fwd;
+    int32_t rc = validate(a);
+    if (rc != AB200_OK) return rc;
+    AB200_REQUIRE(b->grad_flux && b->grad_points && b->grad_normals, AB200_EINVAL, "NULL gradient pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t np4 = (size_t)a->n_samples * a->n_points * 4;
+    if (a->n_local < a->n_samples) {
+        AB200_CUDA_TRY(cudaMemsetAsync(b->grad_points, 0, np4 * sizeof(float), st));
+        AB200_CUDA_TRY(cudaMemsetAsync(b->grad_normals, 0, np4 * sizeof(float), st));
+    }
+    if (a->n_local == 0 || a->n_samples == 0) return AB200_OK;
+    const LaunchPlan pl = make_plan(a->n_local, a->n_points, 512);
+    TraceParams prm;
+    fill_params(prm, a, pl);
+    cudaError_t e = launch_bwd_trig<512>(prm, pl, st, b->grad_flux, b->grad_points, b->grad_normals);
+    AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_bwd launch failed: %s", cudaGetErrorString(e));
+    return AB200_OK;
+}
+
+extern "C" int32_t ab200_abi_version(void) { return AB200_ABI_VERSION; }
+
+extern "C" const char* ab200_error_string(int32_t code) {
+    switch (code) {
+        case AB200_OK: return "ok";
+        case AB200_EINVAL: return "invalid argument";
+        case AB200_ECUDA: return "CUDA failure";
+        case AB200_ELIMIT: return "size limit exceeded";
+        default: return "unknown error";
+    }
+}
+
+extern "C" const char* ab200_last_error_detail(void) { return ab200::g_error_detail; }
+
+namespace ab200 {
+__global__ void debug_trig_kernel(const float* x, int n, int mode, float* s, float* c) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ss, cc;
+    if (mode == AB200_TRIG_POLY) sincos_poly(x[i], &ss, &cc); else sincosf(x[i], &ss, &cc);
+    s[i] = ss; c[i] = cc;
+}
+}  // namespace ab200
+
+extern "C" int32_t ab200_debug_trig(const float* angles, int32_t n, int32_t mode, float* out_sin, float* out_cos, void* stream) {
+    AB200_REQUIRE(angles && out_sin && out_cos && n >= 0, AB200_EINVAL, "bad arguments");
+    if (n == 0) return AB200_OK;
+    debug_trig_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(angles, n, mode, out_sin, out_cos);
+    AB200_CUDA_TRY(cudaGetLastError());
+    return AB200_OK;
+}

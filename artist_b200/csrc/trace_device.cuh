@@ -1,0 +1,228 @@
+// Per-ray device math shared by the forward and backward trace kernels.
+//
+// Everything that decides WHICH pixel a ray lands in (reflect -> scatter -> intersection ->
+// bitmap coordinates) is written with the strict one-rounding-per-op helpers of common.cuh in
+// the evaluation order of the reference's eager ops (verified bit-equal
+// against the reference on CPU by tests/golden).  Gradient math (backward only) is free to use
+// FMAs.
+#pragma once
+#include "common.cuh"
+
+namespace ab200 {
+
+// Per-CTA target constants (one heliostat-sample aims at one target area).
+struct TargetCtx {
+    int planar;
+    float em1, um1;  // (E-1), (U-1) as float
+    // planar: artist/raytracing/geometry.py:100-204
+    float n0, n1, n2, c0, c1, c2, w, h, half_w, half_h;
+    // cylindrical: artist/raytracing/geometry.py:287-445 (local frame rows u = n x axis, n, axis)
+    float ux, uy, uz, ax0, ax1, ax2, rad2, opn, ang0;
+    // pixel-per-metre scale used only for sizing the shared-memory window
+    float px_per_m_e, px_per_m_u;
+};
+
+__device__ inline void load_target(TargetCtx& T, const ab200_targets& tg, int tidx, int res_e, int res_u) {
+    T.em1 = (float)(res_e - 1);
+    T.um1 = (float)(res_u - 1);
+    if (tidx < tg.n_planar) {
+        T.planar = 1;
+        const float* n = tg.planar_normals + 4 * tidx;
+        const float* c = tg.planar_centers + 4 * tidx;
+        T.n0 = n[0]; T.n1 = n[1]; T.n2 = n[2];
+        T.c0 = c[0]; T.c1 = c[1]; T.c2 = c[2];
+        T.w = tg.planar_dims[2 * tidx];
+        T.h = tg.planar_dims[2 * tidx + 1];
+        T.half_w = sdiv(T.w, 2.0f);
+        T.half_h = sdiv(T.h, 2.0f);
+        T.px_per_m_e = T.em1 / T.w;
+        T.px_per_m_u = T.um1 / T.h;
+    } else {
+        const int k = tidx - tg.n_planar;
+        T.planar = 0;
+        const float* n = tg.cyl_normals + 4 * k;
+        const float* a = tg.cyl_axes + 4 * k;
+        const float* c = tg.cyl_centers + 4 * k;
+        T.n0 = n[0]; T.n1 = n[1]; T.n2 = n[2];
+        T.ax0 = a[0]; T.ax1 = a[1]; T.ax2 = a[2];
+        T.c0 = c[0]; T.c1 = c[1]; T.c2 = c[2];
+        // u = cross(normal, axis)  (torch.cross: each product rounded, then subtracted)
+        T.ux = ssub(smul(T.n1, T.ax2), smul(T.n2, T.ax1));
+        T.uy = ssub(smul(T.n2, T.ax0), smul(T.n0, T.ax2));
+        T.uz = ssub(smul(T.n0, T.ax1), smul(T.n1, T.ax0));
+        const float rad = tg.cyl_radii[k];
+        T.rad2 = smul(rad, rad);
+        T.h = tg.cyl_heights[k];
+        T.half_h = sdiv(T.h, 2.0f);
+        T.opn = tg.cyl_opening[k];
+        T.w = T.opn;  // "width" of the unwrapped sector is the opening angle
+        T.half_w = 0.f;
+        T.ang0 = ssub(atan2f(T.n1, T.n0), sdiv(T.opn, 2.0f));
+        T.px_per_m_e = T.em1 / fmaxf(rad * T.opn, 1e-6f);
+        T.px_per_m_u = T.um1 / T.h;
+    }
+}
+
+// Per-point context: origin, preferred reflection direction and the ray-independent terms.
+struct PointCtx {
+    float o0, o1, o2;   // ray origin (aligned surface point)
+    float r0, r1, r2;   // preferred reflection direction (geometry.py:32-41)
+    float dot;          // incident . normal (needed by the backward of reflect)
+    float num;          // planar: (c - o) . n_t      (geometry.py:126-128)
+    float ox, oy, oz;   // cylindrical: origin in the cylinder frame
+    float cc;           // cylindrical: ox^2 + oy^2 - r^2
+};
+
+__device__ __forceinline__ void make_point(PointCtx& pc, const TargetCtx& T, float i0, float i1, float i2,
+                                           const float4 o, const float4 n) {
+    pc.o0 = o.x; pc.o1 = o.y; pc.o2 = o.z;
+    // dot over the 4 homogeneous components; incident.w * normal.w = 0 contributes +0
+    const float dot = sadd(sadd(smul(i0, n.x), smul(i1, n.y)), smul(i2, n.z));
+    pc.dot = dot;
+    const float two_dot = smul(2.0f, dot);
+    pc.r0 = ssub(i0, smul(two_dot, n.x));
+    pc.r1 = ssub(i1, smul(two_dot, n.y));
+    pc.r2 = ssub(i2, smul(two_dot, n.z));
+    if (T.planar) {
+        pc.num = sadd(sadd(smul(ssub(T.c0, o.x), T.n0), smul(ssub(T.c1, o.y), T.n1)), smul(ssub(T.c2, o.z), T.n2));
+    } else {
+        const float q0 = ssub(o.x, T.c0), q1 = ssub(o.y, T.c1), q2 = ssub(o.z, T.c2);
+        // [P,3] @ [3,3]: the CPU GEMM accumulates as an FMA chain over k (measured)
+        pc.ox = fmaf(q2, T.uz, fmaf(q1, T.uy, smul(q0, T.ux)));
+        pc.oy = fmaf(q2, T.n2, fmaf(q1, T.n1, smul(q0, T.n0)));
+        pc.oz = fmaf(q2, T.ax2, fmaf(q1, T.ax1, smul(q0, T.ax0)));
+        pc.cc = ssub(sadd(smul(pc.ox, pc.ox), smul(pc.oy, pc.oy)), T.rad2);
+    }
+}
+
+// Scatter: d = M(e,u) * r   (geometry/transforms.py:67-74, heliostat_ray_tracer.py:547-552)
+struct Scatter {
+    float cu, su, ce, se;
+    float m10, m11, m20, m21;
+    float dx, dy, dz;
+};
+
+__device__ __forceinline__ void scatter(Scatter& s, const PointCtx& pc) {
+    s.m10 = smul(s.ce, s.su);
+    s.m11 = smul(s.ce, s.cu);
+    s.m20 = smul(s.se, s.su);
+    s.m21 = smul(s.se, s.cu);
+    s.dx = sadd(smul(s.cu, pc.r0), smul(-s.su, pc.r1));
+    s.dy = sadd(sadd(smul(s.m10, pc.r0), smul(s.m11, pc.r1)), smul(-s.se, pc.r2));
+    s.dz = sadd(sadd(smul(s.m20, pc.r0), smul(s.m21, pc.r1)), smul(s.ce, pc.r2));
+}
+
+// Result of one ray / target intersection in bitmap coordinates.
+struct Hit {
+    float be, bu;    // continuous bitmap coordinates (be already flipped for planar targets)
+    float t;         // intersection distance
+    float lam;       // ray_magnitude * Lambert cosine (0 if invalid)
+    bool valid;
+    // planar intermediates for the backward
+    float a;
+    // cylindrical intermediates for the backward
+    float dlx, dly, dlz, x, y, qa, qb, sq, nrm;
+    int near_root;
+};
+
+__device__ __forceinline__ void hit_planar(Hit& h, const TargetCtx& T, const PointCtx& pc, const Scatter& s, float mag) {
+    const float a = sadd(sadd(smul(s.dx, T.n0), smul(s.dy, T.n1)), smul(s.dz, T.n2));
+    const bool ff = a < 0.0f;
+    const float t = ff ? sdiv(pc.num, a) : 0.0f;
+    const float X = sadd(pc.o0, smul(s.dx, t));
+    const float Z = sadd(pc.o2, smul(s.dz, t));
+    const float te = ssub(sadd(X, T.half_w), T.c0);
+    const float tu = ssub(sadd(Z, T.half_h), T.c2);
+    const float be0 = smul(sdiv(te, T.w), T.em1);
+    const float bu0 = smul(sdiv(tu, T.h), T.um1);
+    const bool valid = ff && (0.0f <= be0) && (be0 <= T.em1) && (0.0f <= bu0) && (bu0 <= T.um1);
+    h.a = a;
+    h.valid = valid;
+    h.t = valid ? t : 0.0f;
+    h.be = ssub(T.em1, valid ? be0 : 0.0f);
+    h.bu = valid ? bu0 : 0.0f;
+    h.lam = valid ? smul(mag, -a) : 0.0f;
+}
+
+// raw (unmasked) planar coordinates of the undistorted ray, used only to place the smem window
+__device__ __forceinline__ bool centre_planar(const TargetCtx& T, const PointCtx& pc, float& be, float& bu, float& t,
+                                              float& cosi) {
+    const float a = pc.r0 * T.n0 + pc.r1 * T.n1 + pc.r2 * T.n2;
+    if (!(a < 0.0f)) return false;
+    t = pc.num / a;
+    be = T.em1 - ((pc.o0 + pc.r0 * t) + T.half_w - T.c0) / T.w * T.em1;
+    bu = ((pc.o2 + pc.r2 * t) + T.half_h - T.c2) / T.h * T.um1;
+    cosi = -a;
+    return true;
+}
+
+__device__ __forceinline__ void hit_cylinder(Hit& h, const TargetCtx& T, const PointCtx& pc, const Scatter& s, float mag) {
+    // directions @ rot^T (FMA chain over k, as the CPU GEMM does)
+    const float dlx = fmaf(s.dz, T.uz, fmaf(s.dy, T.uy, smul(s.dx, T.ux)));
+    const float dly = fmaf(s.dz, T.n2, fmaf(s.dy, T.n1, smul(s.dx, T.n0)));
+    const float dlz = fmaf(s.dz, T.ax2, fmaf(s.dy, T.ax1, smul(s.dx, T.ax0)));
+    const float qa = sadd(smul(dlx, dlx), smul(dly, dly));
+    const float qb = smul(2.0f, sadd(smul(pc.ox, dlx), smul(pc.oy, dly)));
+    const float disc = ssub(smul(qb, qb), smul(smul(4.0f, qa), pc.cc));
+    const bool hits = (disc >= 0.0f) && (fabsf(qa) > 1e-8f);
+    const float sq = sqrtf(sadd(hits ? disc : smul(disc, 0.0f), 1e-12f));
+    const float two_a = smul(2.0f, qa);
+    float t1 = sdiv(ssub(-qb, sq), two_a);
+    float t2 = sdiv(sadd(-qb, sq), two_a);
+    const float inf = __int_as_float(0x7f800000);
+    t1 = (t1 > 0.0f) ? t1 : inf;
+    t2 = (t2 > 0.0f) ? t2 : inf;
+    float t = fminf(t1, t2);
+    const int near_root = (t1 <= t2);
+    const bool vd = hits && (t < inf) && (t == t);
+    t = vd ? t : 0.0f;
+    const float x = sadd(pc.ox, smul(t, dlx));
+    const float y = sadd(pc.oy, smul(t, dly));
+    float z = sadd(pc.oz, smul(t, dlz));
+    const float nrm = sqrtf(sadd(smul(x, x), smul(y, y)));
+    const float nlx = sdiv(x, nrm), nly = sdiv(y, nrm);
+    float lam = sadd(smul(-dlx, nlx), smul(-dly, nly));
+    lam = fmaxf(lam, 0.0f);
+    z = sadd(z, T.half_h);
+    const float ang = ssub(atan2f(y, x), T.ang0);
+    const bool on = (z >= 0.0f) && (z <= T.h) && (ang >= 0.0f) && (ang <= T.opn);
+    const bool valid = on && vd;
+    h.valid = valid;
+    h.bu = valid ? smul(sdiv(z, T.h), T.um1) : 0.0f;
+    h.be = valid ? smul(sdiv(ang, T.opn), T.em1) : 0.0f;
+    h.t = valid ? t : 0.0f;
+    h.lam = valid ? smul(mag, lam) : 0.0f;
+    h.dlx = dlx; h.dly = dly; h.dlz = dlz; h.x = x; h.y = y; h.qa = qa; h.qb = qb; h.sq = sq; h.nrm = nrm;
+    h.near_root = near_root;
+    h.a = 0.f;
+}
+
+__device__ __forceinline__ bool centre_cylinder(const TargetCtx& T, const PointCtx& pc, float& be, float& bu, float& t,
+                                                float& cosi) {
+    Scatter s;
+    s.dx = pc.r0; s.dy = pc.r1; s.dz = pc.r2;
+    Hit h;
+    hit_cylinder(h, T, pc, s, 1.0f);
+    if (!h.valid) return false;
+    be = h.be; bu = h.bu; t = h.t; cosi = fmaxf(h.lam, 0.05f);
+    return true;
+}
+
+// Bilinear splat weights (heliostat_ray_tracer.py:674-728)
+struct Splat {
+    int ie, iu;
+    bool on;
+    float wle, whe, wlu, whu;
+};
+
+__device__ __forceinline__ void splat_weights(Splat& sp, float be, float bu, int res_e, int res_u) {
+    sp.ie = (int)be;  // trunc toward zero == tensor.long() for the valid range
+    sp.iu = (int)bu;
+    sp.on = (0 <= sp.ie) && (sp.ie + 1 < res_e) && (0 <= sp.iu) && (sp.iu + 1 < res_u);
+    sp.wle = ssub((float)(sp.ie + 1), be);
+    sp.wlu = ssub((float)(sp.iu + 1), bu);
+    sp.whe = ssub(be, (float)sp.ie);
+    sp.whu = ssub(bu, (float)sp.iu);
+}
+
+}  // namespace ab200

@@ -1,0 +1,99 @@
+from __future__ import annotations
+
+import torch
+
+from ..util.env import get_device
+from .kinematics_rigid_body import Kinematics
+
+
+class HeliostatGroup:
+    """SoA of heliostats sharing one kinematics/actuator type (``artist/field/heliostat_group.py:10-315``)."""
+
+    def __init__(self, names: list[str], positions: torch.Tensor, surface_points: torch.Tensor,
+                 surface_normals: torch.Tensor, canting: torch.Tensor, facet_translations: torch.Tensor,
+                 initial_orientations: torch.Tensor, nurbs_control_points: torch.Tensor, nurbs_degrees: torch.Tensor,
+                 device: torch.device | None = None) -> None:
+        device = get_device(device)
+        self.number_of_heliostats = len(names)
+        self.number_of_facets_per_heliostat = nurbs_control_points.shape[1]
+        self.names = names
+        self.positions = positions
+        self.surface_points = surface_points
+        self.surface_normals = surface_normals
+        self.canting = canting
+        self.facet_translations = facet_translations
+        self.initial_orientations = initial_orientations
+        self.nurbs_control_points = nurbs_control_points
+        self.nurbs_degrees = nurbs_degrees
+        self.kinematics = Kinematics()
+        self.number_of_active_heliostats = 0
+        self.active_heliostats_mask = torch.zeros(self.number_of_heliostats, device=device)
+        self.active_surface_points = surface_points
+        self.active_surface_normals = surface_normals
+        self.active_canting = canting
+        self.active_facet_translations = facet_translations
+        self.active_nurbs_control_points = nurbs_control_points
+        self._reflection_inputs = None
+        self._active_rows = None
+
+    # The reference materialises ``preferred_reflection_directions`` ([N,P,4]) inside trace_rays; the fused
+    # kernel never needs it in memory, so it is evaluated only if somebody reads the attribute.
+    @property
+    def preferred_reflection_directions(self) -> torch.Tensor:
+        if self._reflection_inputs is None:
+            return torch.empty(self.number_of_heliostats, 4, device=self.positions.device)
+        incident, normals = self._reflection_inputs
+        incident = incident.unsqueeze(1)
+        return incident - 2 * torch.sum(incident * normals, dim=-1, keepdim=True) * normals
+
+    @preferred_reflection_directions.setter
+    def preferred_reflection_directions(self, value) -> None:
+        self._reflection_inputs = None
+        self.__dict__["_explicit_reflection"] = value
+
+    def align_surfaces_with_incident_ray_directions(self, aim_points, incident_ray_directions, active_heliostats_mask,
+                                                    device=None) -> None:
+        raise NotImplementedError("Must be overridden!")
+
+    def align_surfaces_with_motor_positions(self, motor_positions, active_heliostats_mask, device=None) -> None:
+        raise NotImplementedError("Must be overridden!")
+
+    def activate_heliostats(self, active_heliostats_mask: torch.Tensor | None = None,
+                            device: torch.device | None = None) -> None:
+        """Select (and replicate: mask values > 1) heliostats (``:225-315``).  With an all-ones mask the
+        ``active_*`` tensors alias the group's tensors (no copies); otherwise rows are gathered once."""
+        device = get_device(device) if device is not None else self.positions.device
+        if active_heliostats_mask is None:
+            active_heliostats_mask = torch.ones(self.number_of_heliostats, dtype=torch.int32, device=device)
+        self.number_of_active_heliostats = int(active_heliostats_mask.sum().item())
+        self.active_heliostats_mask = active_heliostats_mask
+        identity = self.number_of_active_heliostats == self.number_of_heliostats and bool(
+            (active_heliostats_mask == 1).all().item())
+        kin = self.kinematics
+        act = getattr(kin, "actuators", None)
+        if identity:
+            self._active_rows = None
+            pick = lambda t: t
+        else:
+            rows = torch.repeat_interleave(torch.arange(self.number_of_heliostats, device=active_heliostats_mask.device),
+                                           active_heliostats_mask.long())
+            self._active_rows = rows
+            pick = lambda t: t.index_select(0, rows.to(t.device))
+        self.active_surface_points = pick(self.surface_points)
+        self.active_surface_normals = pick(self.surface_normals)
+        self.active_canting = pick(self.canting)
+        self.active_facet_translations = pick(self.facet_translations)
+        self.active_nurbs_control_points = pick(self.nurbs_control_points)
+        kin.number_of_active_heliostats = self.number_of_active_heliostats
+        if hasattr(kin, "heliostat_positions"):
+            kin.active_heliostat_positions = pick(kin.heliostat_positions)
+            kin.active_initial_orientations = pick(kin.initial_orientations)
+            kin.active_translation_deviation_parameters = pick(kin.translation_deviation_parameters)
+            kin.active_rotation_deviation_parameters = pick(kin.rotation_deviation_parameters)
+            kin.active_motor_positions = pick(kin.motor_positions)
+        if act is not None:
+            act.active_non_optimizable_parameters = pick(act.non_optimizable_parameters)
+            if act.optimizable_parameters.numel() > 0:
+                act.active_optimizable_parameters = pick(act.optimizable_parameters)
+            else:
+                act.active_optimizable_parameters = torch.tensor([], requires_grad=True)

@@ -1,0 +1,400 @@
+"""Thin torch layer over the C ABI: tensors in, ``data_ptr()`` + current CUDA stream out, with
+explicit ``autograd.Function`` backwards that call the hand-written backward kernels.
+
+Nothing here computes on the CPU; every function raises if its tensors are not CUDA tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import ABI_VERSION
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.Ab200Error(f"{name} must be a CUDA tensor (artist_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _i32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.Ab200Error(f"{name} must be a CUDA tensor (artist_b200 has no CPU path)")
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
+def _p(t: torch.Tensor | None):
+    return None if t is None else t.data_ptr()
+
+
+@dataclass
+class TargetTensors:
+    """Device-resident target-area SoA (``artist/field/tower_target_areas_*.py``)."""
+
+    planar_centers: torch.Tensor
+    planar_normals: torch.Tensor
+    planar_dims: torch.Tensor
+    cyl_centers: torch.Tensor
+    cyl_normals: torch.Tensor
+    cyl_axes: torch.Tensor
+    cyl_radii: torch.Tensor
+    cyl_heights: torch.Tensor
+    cyl_opening: torch.Tensor
+
+    @property
+    def n_planar(self) -> int:
+        return int(self.planar_centers.shape[0])
+
+    @property
+    def n_cyl(self) -> int:
+        return int(self.cyl_centers.shape[0])
+
+    def struct(self) -> _lib.Targets:
+        return _lib.Targets(self.n_planar, self.n_cyl, _p(self.planar_centers), _p(self.planar_normals),
+                            _p(self.planar_dims), _p(self.cyl_centers), _p(self.cyl_normals), _p(self.cyl_axes),
+                            _p(self.cyl_radii), _p(self.cyl_heights), _p(self.cyl_opening))
+
+    @classmethod
+    def from_solar_tower(cls, solar_tower, device) -> "TargetTensors":
+        planar, cyl = solar_tower.target_areas[0], solar_tower.target_areas[1]
+
+        def g(x, shape):
+            x = torch.as_tensor(x, dtype=torch.float32, device=device).reshape(shape)
+            return x.contiguous()
+
+        return cls(g(planar.centers, (-1, 4)), g(planar.normals, (-1, 4)), g(planar.dimensions, (-1, 2)),
+                   g(cyl.centers, (-1, 4)), g(cyl.normals, (-1, 4)), g(cyl.axes, (-1, 4)), g(cyl.radii, (-1,)),
+                   g(cyl.heights, (-1,)), g(cyl.opening_angles, (-1,)))
+
+
+@dataclass
+class TraceOptions:
+    res_e: int = 256
+    res_u: int = 256
+    ray_magnitude: float = 1.0
+    ray_extinction_factor: float = 0.0
+    mirror_reflectivity: float = 0.935
+    scatter_sigma: float = 0.0
+    trig_mode: int = _lib.TRIG_SINCOSF
+    fp32_accumulate: bool = False
+
+
+def pack_distortions(distortions_u: torch.Tensor, distortions_e: torch.Tensor) -> torch.Tensor:
+    """Return the interleaved ``[N,R,P,2]`` (u,e) buffer the kernels stream.
+
+    ``Sun.get_distortions`` returns two permuted views of exactly such a buffer
+    (``artist/scene/sun.py:227-233``); in that case no copy is made.
+    """
+    n, r, p = distortions_u.shape
+    if (distortions_u.dtype == torch.float32 and distortions_e.dtype == torch.float32
+            and distortions_u.stride() == (r * p * 2, p * 2, 2) and distortions_e.stride() == (r * p * 2, p * 2, 2)
+            and distortions_e.data_ptr() == distortions_u.data_ptr() + 4
+            and distortions_u.storage_offset() % 2 == 0):
+        return torch.as_strided(distortions_u, (n, r, p, 2), (r * p * 2, p * 2, 2, 1))
+    return torch.stack([distortions_u.float(), distortions_e.float()], dim=-1).contiguous()
+
+
+def _trace_args(points, normals, incident, distortions, trig, target_idx, targets: TargetTensors, opt: TraceOptions,
+                local_rows, flux, intercept, on_target, blocking, dbg=None) -> _lib.TraceArgs:
+    n, p, _ = points.shape
+    r = distortions.shape[1]
+    a = _lib.TraceArgs()
+    a.abi_version = ABI_VERSION
+    a.n_samples, a.n_points, a.n_rays = n, p, r
+    a.res_e, a.res_u = opt.res_e, opt.res_u
+    a.n_local = n if local_rows is None else int(local_rows.numel())
+    a.local_rows = _p(local_rows)
+    a.points, a.normals, a.incident = _p(points), _p(normals), _p(incident)
+    a.distortions, a.trig, a.target_idx = _p(distortions), _p(trig), _p(target_idx)
+    a.targets = targets.struct()
+    a.blockers = _lib.Blockers(0, None, None, None, None, 1000.0, 1e-12)
+    a.ray_magnitude = float(opt.ray_magnitude)
+    a.one_minus_extinction = float(1 - opt.ray_extinction_factor)
+    a.reflectivity = float(opt.mirror_reflectivity)
+    a.scatter_sigma = float(opt.scatter_sigma)
+    a.trig_mode = int(opt.trig_mode)
+    a.flags = _lib.FLAG_FP32_ACCUM if opt.fp32_accumulate else 0
+    a.flux, a.intercept, a.on_target, a.blocking = _p(flux), _p(intercept), _p(on_target), _p(blocking)
+    if dbg is not None:
+        a.dbg_be, a.dbg_bu, a.dbg_t, a.dbg_lambert = (_p(d) for d in dbg)
+    return a
+
+
+class _TraceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt):
+        points, normals, incident = _f32(points, "points"), _f32(normals, "normals"), _f32(incident, "incident")
+        distortions = _f32(distortions, "distortions")
+        target_idx = _i32(target_idx, "target_area_indices")
+        n = points.shape[0]
+        dev = points.device
+        flux = torch.empty(n, opt.res_u, opt.res_e, device=dev)
+        intercept = torch.empty(n, device=dev)
+        on_target = torch.empty(n, device=dev)
+        blocking = torch.empty(n, device=dev)
+        args = _trace_args(points, normals, incident, distortions, trig, target_idx, targets, opt, local_rows,
+                           flux, intercept, on_target, blocking)
+        _lib.call("ab200_trace_fwd", C.byref(args), _stream())
+        ctx.save_for_backward(points, normals, incident, distortions, trig, target_idx, local_rows)
+        ctx.targets, ctx.opt = targets, opt
+        ctx.mark_non_differentiable(intercept, on_target, blocking)
+        return flux, intercept, on_target, blocking
+
+    @staticmethod
+    def backward(ctx, g_flux, _gi, _go, _gb):
+        points, normals, incident, distortions, trig, target_idx, local_rows = ctx.saved_tensors
+        g_flux = _f32(g_flux, "grad_flux")
+        g_points = torch.empty_like(points)
+        g_normals = torch.empty_like(normals)
+        b = _lib.TraceBwdArgs()
+        b.fwd = _trace_args(points, normals, incident, distortions, trig, target_idx, ctx.targets, ctx.opt, local_rows,
+                            None, None, None, None)
+        b.grad_flux, b.grad_points, b.grad_normals = _p(g_flux), _p(g_points), _p(g_normals)
+        _lib.call("ab200_trace_bwd", C.byref(b), _stream())
+        return g_points, g_normals, None, None, None, None, None, None, None
+
+
+def trace(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,
+          local_rows: torch.Tensor | None = None, trig: torch.Tensor | None = None):
+    """Fused forward trace -> ``(flux[N,U,E], intercept[N], on_target[N], blocking[N])``; differentiable
+    w.r.t. ``points`` and ``normals``."""
+    if trig is not None:
+        trig = _f32(trig, "trig")
+    if local_rows is not None:
+        local_rows = _i32(local_rows, "local_rows")
+    return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt)
+
+
+def trace_debug(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,
+                trig: torch.Tensor | None = None):
+    """Forward trace that also returns the per-ray ``(be, bu, t, lambert)`` ``[N,R,P]`` parity probes."""
+    points, normals, incident = _f32(points, "points"), _f32(normals, "normals"), _f32(incident, "incident")
+    distortions = _f32(distortions, "distortions")
+    target_idx = _i32(target_idx, "target_area_indices")
+    n, p, _ = points.shape
+    r = distortions.shape[1]
+    dev = points.device
+    flux = torch.empty(n, opt.res_u, opt.res_e, device=dev)
+    fac = [torch.empty(n, device=dev) for _ in range(3)]
+    dbg = [torch.zeros(n, r, p, device=dev) for _ in range(4)]
+    args = _trace_args(points, normals, incident, distortions, trig, target_idx, targets, opt, None, flux, *fac, dbg=dbg)
+    _lib.call("ab200_trace_fwd", C.byref(args), _stream())
+    return (flux, *fac), tuple(dbg)
+
+
+# --------------------------------------------------------------------------------------------
+# per-target reduction
+# --------------------------------------------------------------------------------------------
+class _PerTargetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bitmaps, target_idx, n_targets):
+        bitmaps = _f32(bitmaps, "bitmaps_per_heliostat")
+        target_idx = _i32(target_idx, "target_area_indices")
+        n, u, e = bitmaps.shape
+        out = torch.empty(n_targets, u, e, device=bitmaps.device)
+        _lib.call("ab200_bitmaps_per_target", _p(bitmaps), _p(target_idx), n, n_targets, u, e, _p(out), _stream())
+        ctx.save_for_backward(target_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (target_idx,) = ctx.saved_tensors
+        return g.index_select(0, target_idx.long()), None, None
+
+
+def bitmaps_per_target(bitmaps, target_idx, n_targets: int):
+    return _PerTargetFn.apply(bitmaps, target_idx, n_targets)
+
+
+# --------------------------------------------------------------------------------------------
+# NURBS
+# --------------------------------------------------------------------------------------------
+def _nurbs_args(cp, eval_points, knots_u, knots_v, degree_u, degree_v, canting, translations, points, normals):
+    n, f, cu, cv, _ = cp.shape
+    a = _lib.NurbsArgs()
+    a.abi_version = ABI_VERSION
+    a.n_surfaces, a.n_facets = n, f
+    a.n_ctrl_u, a.n_ctrl_v, a.degree_u, a.degree_v = cu, cv, degree_u, degree_v
+    a.control_points = _p(cp)
+    # evaluation points [N,F,K,2] possibly an expanded view of a shared [K,2] grid
+    a.n_eval = eval_points.shape[2]
+    st = eval_points.stride()
+    if st[2] != 2 or st[3] != 1:
+        raise _lib.Ab200Error("evaluation_points must be (u,v)-interleaved along the last two dims")
+    a.eval_points = eval_points.data_ptr()
+    a.eval_stride_n = st[0] if eval_points.shape[0] > 1 else 0
+    a.eval_stride_f = st[1] if eval_points.shape[1] > 1 else 0
+    a.knots_u, a.knots_v = _p(knots_u), _p(knots_v)
+    a.canting, a.facet_translations = _p(canting), _p(translations)
+    a.points, a.normals = _p(points), _p(normals)
+    return a
+
+
+class _NurbsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cp, eval_points, knots_u, knots_v, degree_u, degree_v, canting, translations):
+        cp = _f32(cp, "control_points")
+        if eval_points.dtype != torch.float32 or not eval_points.is_cuda:
+            raise _lib.Ab200Error("evaluation_points must be a CUDA float32 tensor")
+        if eval_points.stride()[-1] != 1 or eval_points.stride()[-2] != 2:
+            eval_points = eval_points.contiguous()
+        n, f = cp.shape[:2]
+        k = eval_points.shape[2]
+        points = torch.empty(n, f, k, 4, device=cp.device)
+        normals = torch.empty(n, f, k, 4, device=cp.device)
+        canting = None if canting is None else _f32(canting, "canting")
+        translations = None if translations is None else _f32(translations, "facet_translations")
+        args = _nurbs_args(cp, eval_points, knots_u, knots_v, degree_u, degree_v, canting, translations, points, normals)
+        _lib.call("ab200_nurbs_fwd", C.byref(args), _stream())
+        ctx.save_for_backward(cp, eval_points, knots_u, knots_v, canting, translations)
+        ctx.deg = (degree_u, degree_v)
+        return points, normals
+
+    @staticmethod
+    def backward(ctx, g_points, g_normals):
+        cp, eval_points, knots_u, knots_v, canting, translations = ctx.saved_tensors
+        g_points = _f32(g_points, "grad_points")
+        g_normals = _f32(g_normals, "grad_normals")
+        g_cp = torch.empty_like(cp)
+        b = _lib.NurbsBwdArgs()
+        b.fwd = _nurbs_args(cp, eval_points, knots_u, knots_v, ctx.deg[0], ctx.deg[1], canting, translations, None, None)
+        b.grad_points, b.grad_normals, b.grad_control_points = _p(g_points), _p(g_normals), _p(g_cp)
+        _lib.call("ab200_nurbs_bwd", C.byref(b), _stream())
+        return g_cp, None, None, None, None, None, None, None
+
+
+def nurbs_points_and_normals(control_points, evaluation_points, knots_u, knots_v, degree_u: int, degree_v: int,
+                             canting=None, facet_translations=None):
+    return _NurbsFn.apply(control_points, evaluation_points, knots_u, knots_v, degree_u, degree_v, canting,
+                          facet_translations)
+
+
+# --------------------------------------------------------------------------------------------
+# kinematics
+# --------------------------------------------------------------------------------------------
+def _kin_args(positions, trans_dev, rot_dev, act_non_opt, act_opt, offset, linear: bool):
+    k = _lib.KinematicsArgs()
+    k.abi_version = ABI_VERSION
+    k.n = positions.shape[0]
+    k.linear_actuators = 1 if linear else 0
+    k.positions, k.translation_dev, k.rotation_dev = _p(positions), _p(trans_dev), _p(rot_dev)
+    k.actuator_non_opt, k.actuator_opt, k.orientation_offset = _p(act_non_opt), _p(act_opt), _p(offset)
+    return k
+
+
+class _KinematicsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, motor, rot_dev, trans_dev, act_opt, positions, act_non_opt, offset, linear):
+        motor, rot_dev, trans_dev = _f32(motor, "motor_positions"), _f32(rot_dev, "rotation_deviation"), _f32(trans_dev, "translation_deviation")
+        positions, act_non_opt, offset = _f32(positions, "positions"), _f32(act_non_opt, "actuator params"), _f32(offset, "offset")
+        has_opt = act_opt is not None and act_opt.numel() > 0
+        act_opt_c = _f32(act_opt, "actuator_opt") if has_opt else None
+        if linear and not has_opt:
+            raise _lib.Ab200Error("linear actuators need optimizable parameters [N,2,2]")
+        out = torch.empty(motor.shape[0], 4, 4, device=motor.device)
+        k = _kin_args(positions, trans_dev, rot_dev, act_non_opt, act_opt_c, offset, linear)
+        _lib.call("ab200_kinematics_fwd", C.byref(k), _p(motor), _p(out), _stream())
+        ctx.save_for_backward(motor, rot_dev, trans_dev, act_opt_c, positions, act_non_opt, offset)
+        ctx.linear = linear
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        motor, rot_dev, trans_dev, act_opt, positions, act_non_opt, offset = ctx.saved_tensors
+        g_out = _f32(g_out, "grad_orientations")
+        need = ctx.needs_input_grad
+        g_motor = torch.empty_like(motor) if need[0] else None
+        g_rot = torch.empty_like(rot_dev) if need[1] else None
+        g_trans = torch.empty_like(trans_dev) if need[2] else None
+        g_act = torch.empty_like(act_opt) if (need[3] and act_opt is not None) else None
+        g_pos = torch.empty_like(positions) if need[4] else None
+        k = _kin_args(positions, trans_dev, rot_dev, act_non_opt, act_opt, offset, ctx.linear)
+        _lib.call("ab200_kinematics_bwd", C.byref(k), _p(motor), _p(g_out), _p(g_motor), _p(g_rot), _p(g_trans),
+                  _p(g_act), _p(g_pos), _stream())
+        return g_motor, g_rot, g_trans, g_act, g_pos, None, None, None
+
+
+def kinematics_orientations(motor, rot_dev, trans_dev, act_opt, positions, act_non_opt, offset, linear: bool):
+    return _KinematicsFn.apply(motor, rot_dev, trans_dev, act_opt, positions, act_non_opt, offset, linear)
+
+
+def kinematics_align_incident(incident, aim_points, rot_dev, trans_dev, act_opt, positions, act_non_opt, offset,
+                              linear: bool, max_iterations: int = 4, min_eps: float = 1e-4):
+    """Forward-only (the reference never differentiates through this loop)."""
+    with torch.no_grad():
+        incident, aim_points = _f32(incident, "incident"), _f32(aim_points, "aim_points")
+        rot_dev, trans_dev = _f32(rot_dev.detach(), "rotation_deviation"), _f32(trans_dev.detach(), "translation_deviation")
+        positions, act_non_opt, offset = _f32(positions, "positions"), _f32(act_non_opt, "actuator params"), _f32(offset, "offset")
+        has_opt = act_opt is not None and act_opt.numel() > 0
+        act_opt_c = _f32(act_opt.detach(), "actuator_opt") if has_opt else None
+        n = incident.shape[0]
+        out = torch.empty(n, 4, 4, device=incident.device)
+        motor = torch.empty(n, 2, device=incident.device)
+        scratch = torch.empty(max(n, 1), device=incident.device)
+        k = _kin_args(positions, trans_dev, rot_dev, act_non_opt, act_opt_c, offset, linear)
+        _lib.call("ab200_kinematics_align_incident", C.byref(k), _p(incident), _p(aim_points), int(max_iterations),
+                  float(min_eps), _p(out), _p(motor), _p(scratch), _stream())
+    return out, motor
+
+
+# --------------------------------------------------------------------------------------------
+# apply orientation
+# --------------------------------------------------------------------------------------------
+class _AlignFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, normals, orientations, src_row):
+        points, normals, orientations = _f32(points, "surface_points"), _f32(normals, "surface_normals"), _f32(orientations, "orientations")
+        n = orientations.shape[0]
+        p = points.shape[1]
+        out_p = torch.empty(n, p, 4, device=points.device)
+        out_n = torch.empty(n, p, 4, device=points.device)
+        _lib.call("ab200_align_fwd", _p(points), _p(normals), _p(orientations), _p(src_row), n, p, _p(out_p), _p(out_n),
+                  _stream())
+        ctx.save_for_backward(points, normals, orientations, src_row)
+        return out_p, out_n
+
+    @staticmethod
+    def backward(ctx, g_op, g_on):
+        points, normals, orientations, src_row = ctx.saved_tensors
+        n, p = orientations.shape[0], points.shape[1]
+        need_data = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_ori = ctx.needs_input_grad[2]
+        g_op = _f32(g_op, "grad_points")
+        g_on = _f32(g_on, "grad_normals")
+        g_p = torch.empty(n, p, 4, device=points.device) if need_data else None
+        g_n = torch.empty(n, p, 4, device=points.device) if need_data else None
+        g_o = torch.empty(n, 4, 4, device=points.device) if need_ori else None
+        _lib.call("ab200_align_bwd", _p(points), _p(normals), _p(orientations), _p(src_row), n, p, _p(g_op), _p(g_on),
+                  _p(g_p), _p(g_n), _p(g_o), _stream())
+        if need_data and src_row is not None:
+            # replicated samples share one source row: sum their gradients (repeat_interleave backward)
+            gp_src = torch.zeros_like(points).index_add_(0, src_row.long(), g_p)
+            gn_src = torch.zeros_like(normals).index_add_(0, src_row.long(), g_n)
+            g_p, g_n = gp_src, gn_src
+        return g_p, g_n, g_o, None
+
+
+def align_surfaces(points, normals, orientations, src_row: torch.Tensor | None = None):
+    """``points @ O^T, normals @ O^T``; ``src_row`` folds ``repeat_interleave`` activation into the pass."""
+    if src_row is not None:
+        src_row = _i32(src_row, "src_row")
+    return _AlignFn.apply(points, normals, orientations, src_row)
+
+
+def debug_trig(angles: torch.Tensor, mode: int):
+    angles = _f32(angles, "angles").reshape(-1)
+    s = torch.empty_like(angles)
+    c = torch.empty_like(angles)
+    _lib.call("ab200_debug_trig", _p(angles), angles.numel(), int(mode), _p(s), _p(c), _stream())
+    return s, c

@@ -134,3 +134,41 @@ def synthetic_field_tensors(n_heliostats: int, control_points: tuple[int, int] =
                    cyl_normals=torch.zeros(0, 4), cyl_radii=torch.zeros(0), cyl_heights=torch.zeros(0),
                    cyl_opening_angles=torch.zeros(0))
     return out
+
+
+def build_synthetic_scenario(n_heliostats: int, number_of_rays: int = 10, points_per_facet: tuple[int, int] = (50, 50),
+                             control_points: tuple[int, int] = (10, 10), surface_bump: float = 0.0, seed: int = 0,
+                             device="cuda", with_cylinder: bool = True, field_tensors: dict | None = None):
+    """Assemble ``Scenario`` / ``HeliostatGroupRigidBody`` objects on ``device`` from the synthetic
+    tensors (surface points and normals evaluated by the NURBS kernel).  Returns ``(scenario, group)``."""
+    from ..field import (HeliostatField, HeliostatGroupRigidBody, SolarTower, TowerTargetAreasCylindrical,
+                         TowerTargetAreasPlanar)
+    from ..nurbs import NURBSSurfaces, create_nurbs_evaluation_grid
+    from ..scene import LightSourceArray, Sun
+    from .scenario import Scenario
+
+    dev = torch.device(device)
+    ft = field_tensors or synthetic_field_tensors(n_heliostats, control_points, surface_bump=surface_bump, seed=seed,
+                                                  with_cylinder=with_cylinder)
+    g = lambda k: ft[k].to(dev)
+    n = ft["positions"].shape[0]
+    grid = create_nurbs_evaluation_grid(torch.tensor(points_per_facet), device=dev)
+    ev = grid[None, None].expand(n, ft["canting"].shape[1], -1, -1)
+    surf = NURBSSurfaces(ft["nurbs_degrees"], g("nurbs_control_points"), device=dev)
+    pts, nrm = surf.calculate_surface_points_and_normals(ev, g("canting"), g("facet_translations"))
+    group = HeliostatGroupRigidBody(
+        names=ft["names"], positions=g("positions"), surface_points=pts.reshape(n, -1, 4),
+        surface_normals=nrm.reshape(n, -1, 4), canting=g("canting"), facet_translations=g("facet_translations"),
+        initial_orientations=g("initial_orientations"), nurbs_control_points=g("nurbs_control_points"),
+        nurbs_degrees=ft["nurbs_degrees"], kinematics_translation_deviation_parameters=g("translation_deviations"),
+        kinematics_rotation_deviation_parameters=g("rotation_deviations"),
+        actuator_parameters_non_optimizable=g("actuator_non_optimizable"),
+        actuator_parameters_optimizable=g("actuator_optimizable"), device=dev)
+    planar = TowerTargetAreasPlanar(ft["planar_names"], g("planar_centers"), g("planar_normals"), g("planar_dimensions"))
+    cyl = TowerTargetAreasCylindrical(ft["cyl_names"], g("cyl_centers"), g("cyl_normals"), g("cyl_axes"),
+                                      g("cyl_radii"), g("cyl_heights"), g("cyl_opening_angles"))
+    scenario = Scenario(power_plant_position=torch.tensor([50.91, 6.38, 87.0], dtype=torch.float64),
+                        solar_tower=SolarTower([planar, cyl], device=dev),
+                        light_sources=LightSourceArray([Sun(number_of_rays=number_of_rays, device=dev)]),
+                        heliostat_field=HeliostatField([group], device=dev))
+    return scenario, group

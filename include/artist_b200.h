@@ -1,0 +1,262 @@
+/*
+ * artist_b200 - C ABI of the B200-native heliostat ray-tracing hot path.
+ *
+ * The reference (ARTIST v2.0.0) is pure Python/PyTorch and has no FFI layer; its boundary for
+ * this path is the Python class API.  This header is the boundary a maintainer
+ * would bind instead of the eager-op bodies of the functions cited at each entry point.  Rules:
+ *   - plain pointers and sizes only (no torch types); all tensors are contiguous fp32 / int32
+ *     DEVICE buffers unless an entry point says "host";
+ *   - the library never allocates or frees caller-visible memory: the caller (torch) owns
+ *     every buffer, outputs are written in place;
+ *   - every launch goes to the `stream` argument (a cudaStream_t passed as void*); calls are
+ *     re-entrant for distinct streams; no global mutable state;
+ *   - return value: AB200_OK (0) or a negative AB200_E* code; ab200_error_string() explains.
+ *
+ * Layout vocabulary (as in the reference): N = active heliostat-samples, P = surface points
+ * per heliostat (all facets), R = rays per point, bitmap = [U rows, E columns], T = target
+ * areas (planar first, then cylindrical - artist/field/solar_tower.py:80-90).
+ */
+#ifndef ARTIST_B200_H
+#define ARTIST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB200_OK 0
+#define AB200_EINVAL (-1)   /* bad argument (null pointer, size <= 0, unsupported degree ...) */
+#define AB200_ECUDA (-2)    /* a CUDA runtime call or launch failed */
+#define AB200_ELIMIT (-3)   /* size beyond what the kernels support */
+
+#define AB200_ABI_VERSION 1
+
+/* trig source for the per-ray scatter rotation (artist/geometry/transforms.py:52-55) */
+#define AB200_TRIG_SINCOSF 0 /* libdevice sincosf (default) */
+#define AB200_TRIG_TABLE 1   /* strict parity: consume caller-computed cos/sin (args->trig) */
+#define AB200_TRIG_POLY 2    /* small-angle polynomial (<= 1 ulp for |x| <= pi/4), sincosf otherwise */
+
+/* flags */
+#define AB200_FLAG_FP32_ACCUM 1 /* accumulate the bitmap with fp32 shared-memory atomics instead of the
+                                   deterministic fixed-point histogram (order-dependent rounding) */
+
+/* Target-area SoA tensors: artist/field/tower_target_areas_planar.py:45-74 and
+ * tower_target_areas_cylindrical.py:56-102. */
+typedef struct ab200_targets {
+    int32_t n_planar;
+    int32_t n_cyl;
+    const float* planar_centers; /* [n_planar,4] */
+    const float* planar_normals; /* [n_planar,4] */
+    const float* planar_dims;    /* [n_planar,2] (width e, height u) */
+    const float* cyl_centers;    /* [n_cyl,4] */
+    const float* cyl_normals;    /* [n_cyl,4] */
+    const float* cyl_axes;       /* [n_cyl,4] */
+    const float* cyl_radii;      /* [n_cyl] */
+    const float* cyl_heights;    /* [n_cyl] */
+    const float* cyl_opening;    /* [n_cyl] opening angles (rad) */
+} ab200_targets;
+
+/* Blocking rectangles of ALL heliostats of the scenario (artist/raytracing/blocking.py:123-209). */
+typedef struct ab200_blockers {
+    int32_t n_blockers;          /* 0 = blocking off */
+    const float* corners;        /* [H,4,3] corner points (lower-left, upper-left, upper-right, lower-right) */
+    const float* spans;          /* [H,2,3] */
+    const float* normals;        /* [H,3] */
+    const int32_t* sample_to_blocker; /* [N] global heliostat index of each active sample (self-hit removal) */
+    float softness;              /* 1000 */
+    float epsilon;               /* 1e-12 */
+} ab200_blockers;
+
+/*
+ * ab200_trace_fwd - replaces the body of HeliostatRayTracer.trace_rays
+ * (artist/raytracing/heliostat_ray_tracer.py:285-508): reflect (geometry.py:32-41), scatter
+ * (transforms.py:52-83 + heliostat_ray_tracer.py:547-552), line-plane / line-cylinder
+ * intersection (geometry.py:100-204 / 287-445), intensities (:482-487), bilinear splat
+ * (:648-778) and the three factor outputs (:498-506), fused in one pass; no per-ray tensor
+ * is materialised.  Rows of `flux`/factors that are not in `local_rows` are zero-filled
+ * (the reference leaves them uninitialised - SURVEY.md 0.7).
+ */
+typedef struct ab200_trace_args {
+    int32_t abi_version;     /* AB200_ABI_VERSION */
+    int32_t n_samples;       /* N */
+    int32_t n_points;        /* P */
+    int32_t n_rays;          /* R */
+    int32_t res_e;           /* E = bitmap_resolution[0] */
+    int32_t res_u;           /* U = bitmap_resolution[1] */
+    int32_t n_local;         /* rows traced by this rank */
+    const int32_t* local_rows; /* [n_local] sample indices (sampler contract sampling.py:129-146); NULL = 0..N-1 */
+    const float* points;     /* [N,P,4] active_surface_points (aligned) */
+    const float* normals;    /* [N,P,4] active_surface_normals (aligned) */
+    const float* incident;   /* [N,4] incident_ray_directions */
+    const float* distortions;/* [N,R,P,2] (u,e) interleaved, exactly Sun.get_distortions' sample layout */
+    const float* trig;       /* AB200_TRIG_TABLE only: [N,R,P,4] = cos u, sin u, cos e, sin e */
+    const int32_t* target_idx; /* [N] target_area_indices */
+    ab200_targets targets;
+    ab200_blockers blockers;
+    float ray_magnitude;         /* HeliostatRayTracer.ray_magnitude (:185-203) */
+    float one_minus_extinction;  /* (float)(1 - ray_extinction_factor) */
+    float reflectivity;          /* mirror_reflectivity */
+    float scatter_sigma;         /* sqrt(sun covariance): sizes the shared-memory bitmap window; 0 = unknown */
+    int32_t trig_mode;           /* AB200_TRIG_* */
+    int32_t flags;               /* AB200_FLAG_* */
+    float* flux;             /* out [N,U,E] */
+    float* intercept;        /* out [N] */
+    float* on_target;        /* out [N] */
+    float* blocking;         /* out [N] */
+    /* optional per-ray parity probes (NULL to skip): the values line_plane/cylinder_intersections return */
+    float* dbg_be;           /* [N,R,P] */
+    float* dbg_bu;           /* [N,R,P] */
+    float* dbg_t;            /* [N,R,P] */
+    float* dbg_lambert;      /* [N,R,P] */
+} ab200_trace_args;
+
+int32_t ab200_trace_fwd(const ab200_trace_args* args, void* stream);
+
+/*
+ * ab200_trace_bwd - explicit backward of ab200_trace_fwd (replaces the autograd graph the
+ * reference retains, ~0.6 KB/ray): re-computes each ray, gathers the four bitmap-gradient taps
+ * and accumulates d/d(points) and d/d(normals) in registers over the R rays of a point.
+ * Gradients flow through be, bu and the intensity, not through trunc(), masks or counts
+ * (SURVEY.md Appendix A).
+ */
+typedef struct ab200_trace_bwd_args {
+    ab200_trace_args fwd;     /* same inputs as the forward call (outputs/dbg pointers ignored) */
+    const float* grad_flux;   /* [N,U,E] */
+    float* grad_points;       /* out [N,P,4] (w component 0) */
+    float* grad_normals;      /* out [N,P,4] (w component 0) */
+} ab200_trace_bwd_args;
+
+int32_t ab200_trace_bwd(const ab200_trace_bwd_args* args, void* stream);
+
+/*
+ * ab200_bitmaps_per_target - HeliostatRayTracer.get_bitmaps_per_target
+ * (heliostat_ray_tracer.py:593-608): out[t] = sum of the bitmaps of samples with target_idx == t,
+ * summed in ascending sample order (deterministic).  `out` is [T,U,E].
+ */
+int32_t ab200_bitmaps_per_target(const float* bitmaps, const int32_t* target_idx, int32_t n_samples,
+                                 int32_t n_targets, int32_t res_u, int32_t res_e, float* out, void* stream);
+
+/*
+ * ab200_nurbs_fwd / _bwd - NURBSSurfaces.calculate_surface_points_and_normals
+ * (artist/nurbs/surfaces.py:475-689): span lookup (:198-207), basis + first derivative
+ * (:325-415), tensor-product contraction (:592-613), normal = normalise(dS/du x dS/dv)
+ * (:615-661), optional canting + facet translation (geometry/transforms.py:321-347,
+ * surfaces.py:674-687).
+ */
+typedef struct ab200_nurbs_args {
+    int32_t abi_version;
+    int32_t n_surfaces;       /* N */
+    int32_t n_facets;         /* F */
+    int32_t n_eval;           /* evaluation points per facet */
+    int32_t n_ctrl_u, n_ctrl_v;
+    int32_t degree_u, degree_v;  /* 1..3 */
+    const float* control_points; /* [N,F,cu,cv,3] */
+    const float* eval_points;    /* (u,v) pairs; element (n,f,k) at eval_points + n*eval_stride_n + f*eval_stride_f + 2k */
+    int64_t eval_stride_n;       /* in floats; 0 = shared by all surfaces */
+    int64_t eval_stride_f;       /* in floats; 0 = shared by all facets */
+    const float* knots_u;        /* [cu+degree_u+1] */
+    const float* knots_v;        /* [cv+degree_v+1] */
+    const float* canting;        /* [N,F,2,4] or NULL */
+    const float* facet_translations; /* [N,F,4] or NULL (must be NULL iff canting is NULL) */
+    float* points;               /* out [N,F,n_eval,4] */
+    float* normals;              /* out [N,F,n_eval,4] */
+} ab200_nurbs_args;
+
+int32_t ab200_nurbs_fwd(const ab200_nurbs_args* args, void* stream);
+
+typedef struct ab200_nurbs_bwd_args {
+    ab200_nurbs_args fwd;
+    const float* grad_points;    /* [N,F,n_eval,4] */
+    const float* grad_normals;   /* [N,F,n_eval,4] */
+    float* grad_control_points;  /* out [N,F,cu,cv,3] (overwritten) */
+} ab200_nurbs_bwd_args;
+
+int32_t ab200_nurbs_bwd(const ab200_nurbs_bwd_args* args, void* stream);
+
+/*
+ * ab200_kinematics_* - RigidBody forward kinematics with linear / ideal actuators
+ * (artist/field/kinematics_rigid_body.py:194-324,510-538; actuators_linear.py:79-291;
+ * actuators_ideal.py:66-111) and the <=4-iteration alignment to incident ray directions
+ * (:540-634 with the closed-form inverse kinematics :326-508).
+ */
+typedef struct ab200_kinematics_args {
+    int32_t abi_version;
+    int32_t n;                       /* active heliostat-samples */
+    int32_t linear_actuators;        /* 1 = LinearActuators, 0 = IdealActuators */
+    const float* positions;          /* [n,4] */
+    const float* translation_dev;    /* [n,9] */
+    const float* rotation_dev;       /* [n,4] */
+    const float* actuator_non_opt;   /* [n,7,2] */
+    const float* actuator_opt;       /* [n,2,2] (ignored for ideal actuators) */
+    const float* orientation_offset; /* [4,4] RigidBody.initial_orientation_offsets (:186-190) */
+} ab200_kinematics_args;
+
+/* motor_positions [n,2] -> orientations [n,4,4] (motor_positions_to_orientations, :510-538) */
+int32_t ab200_kinematics_fwd(const ab200_kinematics_args* args, const float* motor_positions,
+                             float* orientations, void* stream);
+
+/* backward of the above: grad_orientations [n,4,4] -> grads (any output pointer may be NULL) */
+int32_t ab200_kinematics_bwd(const ab200_kinematics_args* args, const float* motor_positions,
+                             const float* grad_orientations, float* grad_motor_positions /* [n,2] */,
+                             float* grad_rotation_dev /* [n,4] */, float* grad_translation_dev /* [n,9] */,
+                             float* grad_actuator_opt /* [n,2,2] */, float* grad_positions /* [n,4] */,
+                             void* stream);
+
+/* incident_ray_directions_to_orientations (:540-634): writes orientations [n,4,4] and the final
+ * motor positions [n,2].  The reference stops iterating when ALL heliostats converged; the same
+ * batch-wide rule is applied on the device (no host sync). */
+int32_t ab200_kinematics_align_incident(const ab200_kinematics_args* args, const float* incident /* [n,4] */,
+                                        const float* aim_points /* [n,4] */, int32_t max_iterations,
+                                        float min_eps, float* orientations, float* motor_positions,
+                                        float* scratch /* [n] floats (last-iteration loss) */, void* stream);
+
+/*
+ * ab200_align_fwd / _bwd - HeliostatGroupRigidBody.align_surfaces_with_* tail
+ * (artist/field/heliostat_group_rigid_body.py:217-222,265-270): points @ O^T, normals @ O^T for
+ * row-vector [N,P,4] data.  `src_row` (NULL = identity) maps an active sample to its source
+ * heliostat row, which folds HeliostatGroup.activate_heliostats' repeat_interleave
+ * (heliostat_group.py:258-263) into the same pass.
+ */
+int32_t ab200_align_fwd(const float* points, const float* normals, const float* orientations,
+                        const int32_t* src_row, int32_t n_samples, int32_t n_points,
+                        float* out_points, float* out_normals, void* stream);
+
+/* grads w.r.t. the un-aligned points/normals (per active sample, [N,P,4]) and w.r.t. the
+ * orientations ([N,4,4]); any output pointer may be NULL. */
+int32_t ab200_align_bwd(const float* points, const float* normals, const float* orientations,
+                        const int32_t* src_row, int32_t n_samples, int32_t n_points,
+                        const float* grad_out_points, const float* grad_out_normals,
+                        float* grad_points, float* grad_normals, float* grad_orientations, void* stream);
+
+/*
+ * ab200_trace_host - end-to-end convenience entry with HOST buffers: uploads the per-call inputs
+ * (incident directions, target indices, aligned points/normals if given on the host), traces,
+ * and downloads the per-target bitmaps.  Device scratch is supplied by the caller.
+ * Used by bench.py's e2e leg; see INTEGRATION.md.
+ */
+typedef struct ab200_host_trace_args {
+    ab200_trace_args dev;            /* device-side argument block; points/normals/incident/target_idx are
+                                        DEVICE scratch buffers that this call fills from the host pointers below */
+    const float* h_points;           /* host [N,P,4] or NULL (already resident in dev.points) */
+    const float* h_normals;          /* host [N,P,4] or NULL */
+    const float* h_incident;         /* host [N,4] */
+    const int32_t* h_target_idx;     /* host [N] */
+    float* d_target_bitmaps;         /* device scratch [T,U,E] */
+    float* h_target_bitmaps;         /* host out [T,U,E] */
+    float* h_factors;                /* host out [3,N] (intercept, on_target, blocking) or NULL */
+} ab200_host_trace_args;
+
+int32_t ab200_trace_host(const ab200_host_trace_args* args, void* stream);
+
+/* misc */
+int32_t ab200_abi_version(void);
+const char* ab200_error_string(int32_t code);
+const char* ab200_last_error_detail(void); /* thread-local detail of the last failing call */
+/* per-ray trig probe for parity tests: out_sin/out_cos [n] with the kernel's trig for `mode` */
+int32_t ab200_debug_trig(const float* angles, int32_t n, int32_t mode, float* out_sin, float* out_cos, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARTIST_B200_H */

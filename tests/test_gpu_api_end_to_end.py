@@ -1,0 +1,110 @@
+"""-m gpu: the reference-shaped class API (Scenario / HeliostatGroupRigidBody / HeliostatRayTracer) end to end
+against the oracle chain NURBS -> alignment -> trace on the CPU."""
+import pytest
+import torch
+
+from oracle import artist_oracle as O
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _oracle_chain(ft, ppf, tidx, inc, rays, res, seed=7):
+    n = ft["positions"].shape[0]
+    tg = cases.targets_from(ft)
+    ev = O.nurbs_evaluation_grid(*ppf)[None, None].expand(n, 4, -1, -1)
+    pts, nrm = O.nurbs_points_and_normals(ft["nurbs_control_points"], 3, 3, ev, ft["canting"], ft["facet_translations"])
+    kin = O.Kin(ft["positions"], ft["translation_deviations"], ft["rotation_deviations"],
+                ft["actuator_non_optimizable"], ft["actuator_optimizable"], True)
+    ori, motor = O.incident_ray_directions_to_orientations(kin, inc, cases.aim_points(tg, tidx))
+    ap, an = O.align_surfaces(pts.reshape(n, -1, 4), nrm.reshape(n, -1, 4), ori)
+    return tg, ap, an, motor
+
+
+def test_flux_prediction_through_class_api():
+    from artist_b200 import HeliostatRayTracer, build_synthetic_scenario, synthetic_field_tensors
+
+    n, ppf, rays, res = 5, (14, 14), 6, (128, 128)
+    ft = synthetic_field_tensors(n, control_points=(8, 8), surface_bump=0.002)
+    scenario, group = build_synthetic_scenario(n, number_of_rays=rays, points_per_facet=ppf, device=DEV, field_tensors=ft)
+    mask, tidx, inc = scenario.index_mapping(group, single_incident_ray_direction=torch.tensor([0.0, 0.96, -0.28, 0.0]),
+                                             single_target_area_index=0)
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_incident_ray_directions(
+        aim_points=scenario.solar_tower.get_centers_of_target_areas(tidx), incident_ray_directions=inc,
+        active_heliostats_mask=mask)
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor(res))
+    flux, ic, ot, bl = tracer.trace_rays(inc, mask, tidx)
+    per_target = tracer.get_bitmaps_per_target(flux, tidx)
+    assert per_target.shape == (2, 128, 128)
+    tg, ap, an, motor = _oracle_chain(ft, ppf, tidx.cpu(), inc.cpu(), rays, res)
+    assert (group.active_surface_points.cpu() - ap).abs().max() <= 2e-4
+    assert ((group.kinematics.active_motor_positions.cpu() - motor).abs() / motor.abs().clamp_min(1)).max() < 2e-4
+    du, de = tracer.distortions_dataset.distortions_u.cpu(), tracer.distortions_dataset.distortions_e.cpu()
+    # the oracle traces the CUDA-aligned surfaces with the same distortion samples
+    ref, ric, rot, _ = O.trace_rays(group.active_surface_points.cpu(), group.active_surface_normals.cpu(), inc.cpu(),
+                                    du, de, tidx.cpu(), tg, res)
+    assert (flux.cpu() - ref).abs().max() <= 1e-4 * ref.max()
+    assert (per_target[0].cpu() - ref.sum(0)).abs().max() <= 1e-4 * ref.sum(0).max()
+    assert (ic.cpu() - ric).abs().max() <= 1e-3 and (ot.cpu() - rot).abs().max() <= 1e-3
+
+
+def test_surface_reconstruction_step_gradients():
+    """Config 4 shape: control points -> NURBS -> align -> trace -> loss -> backward to the control points."""
+    from artist_b200 import HeliostatRayTracer, NURBSSurfaces, build_synthetic_scenario, synthetic_field_tensors
+    from artist_b200.nurbs import create_nurbs_evaluation_grid
+
+    n, ppf, rays, res = 3, (12, 12), 8, (64, 64)
+    ft = synthetic_field_tensors(n, control_points=(6, 6), surface_bump=0.002)
+    scenario, group = build_synthetic_scenario(n, number_of_rays=rays, points_per_facet=ppf, device=DEV, field_tensors=ft)
+    mask, tidx, inc = scenario.index_mapping(group)
+    cp = group.nurbs_control_points.detach().clone().requires_grad_(True)
+    group.nurbs_control_points = cp
+    group.activate_heliostats(mask)
+    surf = NURBSSurfaces(group.nurbs_degrees, group.active_nurbs_control_points, device=torch.device(DEV))
+    ev = create_nurbs_evaluation_grid(torch.tensor(ppf), device=torch.device(DEV))[None, None].expand(n, 4, -1, -1)
+    pts, nrm = surf.calculate_surface_points_and_normals(ev, group.active_canting, group.active_facet_translations)
+    group.active_surface_points, group.active_surface_normals = pts.reshape(n, -1, 4), nrm.reshape(n, -1, 4)
+    group.align_surfaces_with_incident_ray_directions(scenario.solar_tower.get_centers_of_target_areas(tidx), inc, mask)
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor(res))
+    flux, *_ = tracer.trace_rays(inc, mask, tidx)
+    torch.manual_seed(1)
+    wgt = torch.rand(n, res[1], res[0])
+    (flux * wgt.to(DEV)).sum().backward()
+    # oracle: same chain with autograd on the CPU, same distortions
+    cpo = ft["nurbs_control_points"].clone().requires_grad_(True)
+    tg = cases.targets_from(ft)
+    evo = O.nurbs_evaluation_grid(*ppf)[None, None].expand(n, 4, -1, -1)
+    po, no = O.nurbs_points_and_normals(cpo, 3, 3, evo, ft["canting"], ft["facet_translations"])
+    kin = O.Kin(ft["positions"], ft["translation_deviations"], ft["rotation_deviations"],
+                ft["actuator_non_optimizable"], ft["actuator_optimizable"], True)
+    ori, _ = O.incident_ray_directions_to_orientations(kin, inc.cpu(), cases.aim_points(tg, tidx.cpu()))
+    ap, an = O.align_surfaces(po.reshape(n, -1, 4), no.reshape(n, -1, 4), ori)
+    ref, *_ = O.trace_rays(ap, an, inc.cpu(), tracer.distortions_dataset.distortions_u.cpu(),
+                           tracer.distortions_dataset.distortions_e.cpu(), tidx.cpu(), tg, res)
+    (ref * wgt).sum().backward()
+    scale = cpo.grad.abs().max()
+    err = (cp.grad.cpu() - cpo.grad).abs().max() / scale
+    assert err <= 5e-3, f"control-point gradient error {err:.3e}"
+
+
+def test_motor_position_gradients_and_mask_assertion():
+    from artist_b200 import HeliostatRayTracer, build_synthetic_scenario
+
+    scenario, group = build_synthetic_scenario(4, number_of_rays=5, points_per_facet=(10, 10), device=DEV)
+    mask, tidx, inc = scenario.index_mapping(group)
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_incident_ray_directions(scenario.solar_tower.get_centers_of_target_areas(tidx), inc, mask)
+    motor = group.kinematics.active_motor_positions.detach().clone().requires_grad_(True)
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_motor_positions(motor, mask)
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor([64, 64]))
+    flux, *_ = tracer.trace_rays(inc, mask, tidx)
+    col = torch.linspace(0, 1, 64, device=DEV)
+    (flux * col).sum().backward()
+    assert torch.isfinite(motor.grad).all() and motor.grad.abs().max() > 0
+    with pytest.raises(AssertionError, match="not aligned"):
+        tracer.trace_rays(inc, torch.zeros_like(mask), tidx)
+    with pytest.raises(NotImplementedError):
+        HeliostatRayTracer(scenario, group, blocking_active=True).trace_rays(inc, mask, tidx)

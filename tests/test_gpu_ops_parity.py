@@ -1,0 +1,181 @@
+"""-m gpu: NURBS, kinematics, alignment and per-target reduction kernels against the CPU oracle."""
+import pytest
+import torch
+
+from oracle import artist_oracle as O
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _nurbs_inputs(n=3, cps=(7, 6), ppf=(11, 9), bump=0.004, seed=2):
+    from artist_b200.scenario.synthetic import synthetic_field_tensors
+
+    ft = synthetic_field_tensors(n, control_points=cps, surface_bump=bump, seed=seed)
+    ev = O.nurbs_evaluation_grid(*ppf)[None, None].expand(n, 4, -1, -1)
+    return ft, ev
+
+
+@pytest.mark.parametrize("canting", [True, False])
+@pytest.mark.parametrize("cps,ppf", [((7, 6), (11, 9)), ((10, 10), (50, 50)), ((20, 20), (13, 13))])
+def test_nurbs_forward_bit_equal_points(canting, cps, ppf):
+    from artist_b200 import NURBSSurfaces
+
+    ft, ev = _nurbs_inputs(cps=cps, ppf=ppf)
+    cant = ft["canting"] if canting else None
+    tr = ft["facet_translations"] if canting else None
+    pts, nrm = O.nurbs_points_and_normals(ft["nurbs_control_points"], 3, 3, ev, cant, tr)
+    surf = NURBSSurfaces(ft["nurbs_degrees"], ft["nurbs_control_points"].to(DEV), device=torch.device(DEV))
+    gp, gn = surf.calculate_surface_points_and_normals(ev.to(DEV), None if cant is None else cant.to(DEV),
+                                                       None if tr is None else tr.to(DEV))
+    # points follow the reference's op order exactly; normals go through a vector norm whose CPU
+    # accumulation is not reproducible op by op (<= 1 ulp differences)
+    assert torch.equal(gp.cpu(), pts), f"max diff {(gp.cpu() - pts).abs().max():.3e}"
+    assert (gn.cpu() - nrm).abs().max() <= 2.4e-7
+
+
+def test_nurbs_degree_2_and_shared_grid():
+    from artist_b200 import ops
+
+    ft, ev = _nurbs_inputs(n=2, cps=(5, 6), ppf=(8, 8))
+    pts, nrm = O.nurbs_points_and_normals(ft["nurbs_control_points"], 2, 3, ev, ft["canting"], ft["facet_translations"])
+    cp = ft["nurbs_control_points"].to(DEV)
+    gp, gn = ops.nurbs_points_and_normals(cp, ev.to(DEV), O.uniform_knots(5, 2).to(DEV), O.uniform_knots(6, 3).to(DEV), 2, 3,
+                                          ft["canting"].to(DEV), ft["facet_translations"].to(DEV))
+    assert (gp.cpu() - pts).abs().max() <= 1e-6 and (gn.cpu() - nrm).abs().max() <= 1e-6
+
+
+def test_nurbs_backward_matches_autograd():
+    from artist_b200 import NURBSSurfaces
+
+    ft, ev = _nurbs_inputs(n=3, cps=(6, 7), ppf=(12, 10))
+    torch.manual_seed(0)
+    wp, wn = torch.randn(3, 4, 120, 4), torch.randn(3, 4, 120, 4)
+    cp = ft["nurbs_control_points"].clone().requires_grad_(True)
+    pts, nrm = O.nurbs_points_and_normals(cp, 3, 3, ev, ft["canting"], ft["facet_translations"])
+    ((pts * wp).sum() + (nrm * wn).sum()).backward()
+    cpc = ft["nurbs_control_points"].to(DEV).requires_grad_(True)
+    surf = NURBSSurfaces(ft["nurbs_degrees"], cpc, device=torch.device(DEV))
+    gp, gn = surf.calculate_surface_points_and_normals(ev.to(DEV), ft["canting"].to(DEV), ft["facet_translations"].to(DEV))
+    ((gp * wp.to(DEV)).sum() + (gn * wn.to(DEV)).sum()).backward()
+    scale = cp.grad.abs().max()
+    assert (cpc.grad.cpu() - cp.grad).abs().max() <= 2e-5 * scale
+
+
+def _kin_dev(kin):
+    f = lambda x: x.to(DEV).float().contiguous()
+    return dict(positions=f(kin.positions), trans=f(kin.translation_deviations), rot=f(kin.rotation_deviations),
+                non_opt=f(kin.actuator_non_optimizable), opt=f(kin.actuator_optimizable))
+
+
+@pytest.mark.parametrize("linear", [True, False])
+def test_kinematics_forward_and_backward(linear):
+    from artist_b200 import ops
+
+    case = cases.make_case(n=7, points_per_facet=(4, 4), rays=1)
+    kin = case["kin"]
+    kin.linear = linear
+    if not linear:
+        kin.actuator_non_optimizable = kin.actuator_non_optimizable.clone()
+        kin.actuator_non_optimizable[:, 0] = 1.0
+        kin.actuator_non_optimizable[:, 2] = -10.0
+        kin.actuator_non_optimizable[:, 3] = 10.0
+    g = torch.Generator().manual_seed(1)
+    motor = (20000 + 30000 * torch.rand(7, 2, generator=g)) if linear else (torch.rand(7, 2, generator=g) - 0.3)
+    wgt = torch.randn(7, 4, 4, generator=g)
+    m = motor.clone().requires_grad_(True)
+    kin.rotation_deviations = kin.rotation_deviations.clone().requires_grad_(True)
+    kin.translation_deviations = kin.translation_deviations.clone().requires_grad_(True)
+    kin.actuator_optimizable = kin.actuator_optimizable.clone().requires_grad_(True)
+    ref = O.motor_positions_to_orientations(kin, m)
+    (ref * wgt).sum().backward()
+    d = _kin_dev(kin)
+    off = O.initial_orientation_offset().reshape(4, 4).to(DEV)
+    mc = motor.to(DEV).requires_grad_(True)
+    rot, trans, opt = (d[k].detach().requires_grad_(True) for k in ("rot", "trans", "opt"))
+    out = ops.kinematics_orientations(mc, rot, trans, opt if linear else None, d["positions"], d["non_opt"], off, linear)
+    assert (out.detach().cpu() - ref.detach()).abs().max() <= 2e-5
+    (out * wgt.to(DEV)).sum().backward()
+    for got, want, name in ((mc.grad, m.grad, "motor"), (rot.grad, kin.rotation_deviations.grad, "rotation dev"),
+                            (trans.grad, kin.translation_deviations.grad, "translation dev")):
+        scale = want.abs().max().clamp_min(1e-12)
+        assert (got.cpu() - want).abs().max() <= 2e-3 * scale, name
+    if linear:
+        want = kin.actuator_optimizable.grad
+        assert (opt.grad.cpu() - want).abs().max() <= 2e-3 * want.abs().max()
+
+
+@pytest.mark.parametrize("linear", [True, False])
+def test_alignment_to_incident_rays(linear):
+    from artist_b200 import ops
+
+    case = cases.make_case(n=9, points_per_facet=(4, 4), rays=1, target_pattern=(0, 1))
+    kin = case["kin"]
+    if not linear:
+        kin.linear = False
+        kin.actuator_non_optimizable = kin.actuator_non_optimizable.clone()
+        kin.actuator_non_optimizable[:, 0] = 1.0
+        kin.actuator_non_optimizable[:, 2] = -10.0
+        kin.actuator_non_optimizable[:, 3] = 10.0
+    ori, motor = O.incident_ray_directions_to_orientations(kin, case["incident"], case["aim"])
+    d = _kin_dev(kin)
+    off = O.initial_orientation_offset().reshape(4, 4).to(DEV)
+    got, gm = ops.kinematics_align_incident(case["incident"].to(DEV), case["aim"].to(DEV), d["rot"], d["trans"],
+                                            d["opt"] if linear else None, d["positions"], d["non_opt"], off, linear)
+    assert (got.cpu() - ori).abs().max() <= 5e-5
+    assert ((gm.cpu() - motor).abs() / motor.abs().clamp_min(1.0)).max() <= 2e-4
+
+
+def test_align_apply_forward_backward():
+    from artist_b200 import ops
+
+    case = cases.make_case(n=5, points_per_facet=(6, 7), rays=1)
+    pts, nrm, ori = case["surface_points"], case["surface_normals"], case["orientations"]
+    ap, an = O.align_surfaces(pts, nrm, ori)
+    gp, gn = ops.align_surfaces(pts.to(DEV), nrm.to(DEV), ori.to(DEV))
+    assert torch.equal(gp.cpu(), ap) and torch.equal(gn.cpu(), an)   # FMA chain == CPU GEMM accumulation
+    torch.manual_seed(3)
+    w1, w2 = torch.randn_like(ap), torch.randn_like(an)
+    p, n_, o = pts.clone().requires_grad_(True), nrm.clone().requires_grad_(True), ori.clone().requires_grad_(True)
+    a, b = O.align_surfaces(p, n_, o)
+    ((a * w1).sum() + (b * w2).sum()).backward()
+    pc, nc, oc = (x.to(DEV).requires_grad_(True) for x in (pts, nrm, ori))
+    a2, b2 = ops.align_surfaces(pc, nc, oc)
+    ((a2 * w1.to(DEV)).sum() + (b2 * w2.to(DEV)).sum()).backward()
+    for got, want in ((pc.grad, p.grad), (nc.grad, n_.grad), (oc.grad, o.grad)):
+        assert (got.cpu() - want).abs().max() <= 2e-5 * want.abs().max()
+    # replicated samples (mask values > 1) through src_row
+    rows = torch.tensor([0, 0, 2, 4, 4, 4], dtype=torch.int32)
+    ori6 = ori[rows.long()]
+    a3, b3 = ops.align_surfaces(pts.to(DEV), nrm.to(DEV), ori6.to(DEV), src_row=rows.to(DEV))
+    ra, rb = O.align_surfaces(pts[rows.long()], nrm[rows.long()], ori6)
+    assert torch.equal(a3.cpu(), ra) and torch.equal(b3.cpu(), rb)
+
+
+def test_bitmaps_per_target():
+    from artist_b200 import ops
+
+    torch.manual_seed(0)
+    bm = torch.rand(11, 37, 41)
+    tidx = torch.tensor([0, 2, 2, 1, 0, 3, 3, 3, 0, 2, 1], dtype=torch.int32)
+    ref = O.bitmaps_per_target(bm, tidx, 5)
+    got = ops.bitmaps_per_target(bm.to(DEV), tidx.to(DEV), 5)
+    assert (got.cpu() - ref).abs().max() <= 1e-6
+    assert (got[4] == 0).all()
+    bm2 = torch.rand(6, 64, 64)
+    got2 = ops.bitmaps_per_target(bm2.to(DEV), tidx[:6].to(DEV), 4)
+    assert (got2.cpu() - O.bitmaps_per_target(bm2, tidx[:6], 4)).abs().max() <= 1e-6
+
+
+def test_device_trig_accuracy():
+    """Kernel trig vs torch CPU (SLEEF u10) on sun-shape sized angles: never more than 1 ulp apart."""
+    from artist_b200 import ops
+
+    torch.manual_seed(0)
+    x = torch.randn(1 << 20) * 2.09e-3
+    for mode in (0, 2):
+        s, c = ops.debug_trig(x.to(DEV), mode)
+        ds = (s.cpu() - torch.sin(x)).abs() / torch.sin(x).abs().clamp_min(1e-30)
+        dc = (c.cpu() - torch.cos(x)).abs()
+        assert ds.max() <= 1.2e-7 and dc.max() <= 6e-8

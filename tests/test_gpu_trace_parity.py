@@ -1,0 +1,155 @@
+"""-m gpu: the CUDA trace (through the C ABI) against the CPU oracle on identical seeded inputs."""
+import pytest
+import torch
+
+from oracle import artist_oracle as O
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev_targets(tg, dev):
+    from artist_b200.ops import TargetTensors
+
+    f = lambda x: x.to(dev).float().contiguous()
+    return TargetTensors(f(tg.planar_centers), f(tg.planar_normals), f(tg.planar_dimensions), f(tg.cyl_centers),
+                         f(tg.cyl_normals), f(tg.cyl_axes), f(tg.cyl_radii), f(tg.cyl_heights), f(tg.cyl_opening_angles))
+
+
+def _run_cuda(case, res, trig_mode, debug=False, fp32=False, local_rows=None, magnitude=1.0):
+    from artist_b200 import ops
+
+    dev = torch.device("cuda:0")
+    opt = ops.TraceOptions(res_e=res[0], res_u=res[1], trig_mode=trig_mode, scatter_sigma=(4.3681e-06) ** 0.5,
+                           fp32_accumulate=fp32, ray_magnitude=magnitude)
+    dist = ops.pack_distortions(case["dist_u"].to(dev), case["dist_e"].to(dev))
+    trig = cases.cpu_trig(case["dist_u"], case["dist_e"]).to(dev) if trig_mode == 1 else None
+    tg = _dev_targets(case["targets"], dev)
+    args = (case["points"].to(dev), case["normals"].to(dev), case["incident"].to(dev), dist,
+            case["target_idx"].to(dev), tg, opt)
+    if debug:
+        return ops.trace_debug(*args, trig=trig)
+    lr = None if local_rows is None else torch.tensor(local_rows, dtype=torch.int32, device=dev)
+    return ops.trace(*args, local_rows=lr, trig=trig)
+
+
+@pytest.mark.parametrize("res", [(256, 256), (64, 48), (230, 276)])
+def test_planar_strict_bit_exact_coordinates_and_flux(res):
+    """Strict mode (shared trig values): pixel coordinates bit-exact, flux within 1e-5 of peak, factors exact."""
+    case = cases.make_case(n=5, points_per_facet=(14, 14), rays=6, target_pattern=(0,))
+    be, bu, t, lam = O.ray_pixel_coordinates(case["points"], case["normals"], case["incident"], case["dist_u"],
+                                             case["dist_e"], case["target_idx"], case["targets"], res)
+    (flux, ic, ot, bl), (dbe, dbu, dt, dlam) = _run_cuda(case, res, trig_mode=1, debug=True)
+    assert torch.equal(dbe.cpu(), be), "east pixel coordinates differ"
+    assert torch.equal(dbu.cpu(), bu), "up pixel coordinates differ"
+    assert torch.equal(dt.cpu(), t)
+    assert torch.equal(dlam.cpu(), lam)
+    ref, ric, rot, rbl = O.trace_rays(case["points"], case["normals"], case["incident"], case["dist_u"], case["dist_e"],
+                                      case["target_idx"], case["targets"], res)
+    assert ref.max() > 0
+    tol = 1e-5 * ref.max()   # fp32 tolerance relative to peak flux (north_star allows 1e-4)
+    assert (flux.cpu() - ref).abs().max() <= tol
+    assert torch.equal(ic.cpu(), ric) and torch.equal(ot.cpu(), rot) and torch.equal(bl.cpu(), rbl)
+
+
+@pytest.mark.parametrize("trig_mode", [0, 2])
+def test_planar_device_trig_index_flip_rate(trig_mode):
+    """Device trig (sincosf / polynomial): pixel INDICES may flip only for rays within an ulp of a pixel edge."""
+    case = cases.make_case(n=6, points_per_facet=(25, 25), rays=8)
+    res = (256, 256)
+    be, bu, _, _ = O.ray_pixel_coordinates(case["points"], case["normals"], case["incident"], case["dist_u"],
+                                           case["dist_e"], case["target_idx"], case["targets"], res)
+    (flux, *_), (dbe, dbu, _, _) = _run_cuda(case, res, trig_mode=trig_mode, debug=True)
+    flips = ((dbe.cpu().long() != be.long()) | (dbu.cpu().long() != bu.long())).sum().item()
+    assert flips <= 1e-4 * be.numel(), f"{flips} index flips of {be.numel()} rays"
+    assert (dbe.cpu() - be).abs().max() < 1e-3 and (dbu.cpu() - bu).abs().max() < 1e-3
+    ref, *_ = O.trace_rays(case["points"], case["normals"], case["incident"], case["dist_u"], case["dist_e"],
+                           case["target_idx"], case["targets"], res)
+    assert (flux.cpu() - ref).abs().max() <= 1e-4 * ref.max()
+
+
+def test_fixed_point_is_bit_reproducible_and_fp32_mode_agrees():
+    case = cases.make_case(n=4, points_per_facet=(20, 20), rays=7)
+    a = _run_cuda(case, (256, 256), 0)[0]
+    b = _run_cuda(case, (256, 256), 0)[0]
+    assert torch.equal(a, b), "deterministic fixed-point accumulation must be bit-reproducible"
+    c = _run_cuda(case, (256, 256), 0, fp32=True)[0]
+    assert (a - c).abs().max() <= 1e-5 * a.max()
+
+
+def test_cylindrical_and_mixed_targets():
+    """Cylinder hits are ill-conditioned in fp32 (b^2-4ac cancels ~3 digits, so one-ulp differences in the
+    frame transform move a hit by ~0.01 px): coordinates within 0.05 px; this low-count bitmap (peak ~4 rays per
+    pixel) then differs by at most one ray-weight step, 5e-3 of peak."""
+    case = cases.make_case(n=6, points_per_facet=(16, 16), rays=6, target_pattern=(1, 0, 1))
+    res = (256, 256)
+    be, bu, t, lam = O.ray_pixel_coordinates(case["points"], case["normals"], case["incident"], case["dist_u"],
+                                             case["dist_e"], case["target_idx"], case["targets"], res)
+    (flux, ic, ot, bl), (dbe, dbu, dt, dlam) = _run_cuda(case, res, trig_mode=1, debug=True)
+    cyl = case["target_idx"] == 1
+    assert lam[cyl].sum() > 0, "case must hit the cylinder"
+    both = (lam > 0) & (dlam.cpu() > 0)
+    assert (both.float().mean() - (lam > 0).float().mean()).abs() < 1e-3
+    assert (dbe.cpu() - be)[both].abs().max() < 0.05 and (dbu.cpu() - bu)[both].abs().max() < 0.05
+    ref, ric, rot, _ = O.trace_rays(case["points"], case["normals"], case["incident"], case["dist_u"], case["dist_e"],
+                                    case["target_idx"], case["targets"], res)
+    assert (flux.cpu() - ref).abs().max() <= 5e-3 * ref.max()
+    assert (ic.cpu() - ric).abs().max() < 2e-3 and (ot.cpu() - rot).abs().max() < 2e-3
+    # planar rows of the mixed batch stay bit-exact in coordinates
+    assert torch.equal(dbe.cpu()[~cyl], be[~cyl]) and torch.equal(dbu.cpu()[~cyl], bu[~cyl])
+
+
+def test_local_rows_zero_fill_and_split_modes():
+    """Sharded call: rows not owned by the rank are zero (reference leaves them uninitialised)."""
+    case = cases.make_case(n=6, points_per_facet=(10, 10), rays=4)
+    full = _run_cuda(case, (128, 128), 0)
+    part = _run_cuda(case, (128, 128), 0, local_rows=[1, 4])
+    for a, b in zip(full, part):
+        assert torch.equal(a[[1, 4]], b[[1, 4]])
+        assert (b[[0, 2, 3, 5]] == 0).all()
+
+
+def test_ray_magnitude_and_dni_scaling():
+    case = cases.make_case(n=3, points_per_facet=(10, 10), rays=4)
+    a = _run_cuda(case, (64, 64), 1, magnitude=1.0)[0]
+    b = _run_cuda(case, (64, 64), 1, magnitude=0.0375)[0]
+    ref, *_ = O.trace_rays(case["points"], case["normals"], case["incident"], case["dist_u"], case["dist_e"],
+                           case["target_idx"], case["targets"], (64, 64), ray_magnitude=0.0375)
+    assert (b.cpu() - ref).abs().max() <= 1e-5 * ref.max()
+    assert (a * 0.0375 - b).abs().max() <= 1e-5 * b.max()
+
+
+@pytest.mark.parametrize("pattern", [(0,), (1, 0)])
+def test_backward_matches_oracle_autograd(pattern):
+    """Planar rows: CUDA gradients within 2e-4 (of the largest entry) of the fp32 oracle's autograd.
+    Cylindrical rows: the reference formula loses ~3 digits in b^2-4ac, its own fp32 autograd is 20-30 % off
+    the float64 truth, so the CUDA gradients are checked against the FLOAT64 oracle and must be no worse than
+    twice the fp32 oracle's own error."""
+    case = cases.make_case(n=4, points_per_facet=(12, 12), rays=6, target_pattern=pattern)
+    res = (96, 96)
+    torch.manual_seed(5)
+    wgt = torch.rand(4, res[1], res[0])
+    _, gp32, gn32 = cases.oracle_trace_with_grads(case, res, wgt, torch.float32)
+    _, gp64, gn64 = cases.oracle_trace_with_grads(case, res, wgt, torch.float64)
+    from artist_b200 import ops
+
+    dev = torch.device("cuda:0")
+    pc = case["points"].to(dev).requires_grad_(True)
+    nc = case["normals"].to(dev).requires_grad_(True)
+    opt = ops.TraceOptions(res_e=res[0], res_u=res[1], trig_mode=1, scatter_sigma=2.09e-3)
+    dist = ops.pack_distortions(case["dist_u"].to(dev), case["dist_e"].to(dev))
+    trig = cases.cpu_trig(case["dist_u"], case["dist_e"]).to(dev)
+    flux, *_ = ops.trace(pc, nc, case["incident"].to(dev), dist, case["target_idx"].to(dev),
+                         _dev_targets(case["targets"], dev), opt, trig=trig)
+    (flux * wgt.to(dev)).sum().backward()
+    planar = case["target_idx"] < case["targets"].n_planar
+    for got, g32, g64, name in ((pc.grad.cpu(), gp32, gp64, "points"), (nc.grad.cpu(), gn32, gn64, "normals")):
+        scale = g32[planar].abs().max()
+        assert scale > 0
+        err = (got[planar] - g32[planar]).abs().max() / scale
+        assert err <= 2e-4, f"planar grad {name}: {err:.3e}"
+        if (~planar).any():
+            scale64 = g64[~planar].abs().max()
+            ref_err = (g32[~planar].double() - g64[~planar]).abs().max() / scale64
+            err = (got[~planar].double() - g64[~planar]).abs().max() / scale64
+            assert err <= max(2 * ref_err, 1e-3), f"cylinder grad {name}: {err:.3e} (fp32 oracle itself {ref_err:.3e})"
