@@ -48,7 +48,8 @@ class TraceArgs(C.Structure):
 
 
 class TraceBwdArgs(C.Structure):
-    _fields_ = [("fwd", TraceArgs), ("grad_flux", c_float_p), ("grad_points", c_float_p), ("grad_normals", c_float_p)]
+    _fields_ = [("fwd", TraceArgs), ("grad_flux", c_float_p), ("grad_flux_stride", C.c_int64),
+                ("grad_points", c_float_p), ("grad_normals", c_float_p)]
 
 
 class NurbsArgs(C.Structure):
@@ -99,6 +100,7 @@ EXPORTS = {
                          c_float_p, c_float_p, c_float_p, C.c_void_p], C.c_int32),
     "ab200_trace_host": ([C.POINTER(HostTraceArgs), C.c_void_p], C.c_int32),
     "ab200_abi_version": ([], C.c_int32),
+    "ab200_kernel_launch_count": ([], C.c_int64),
     "ab200_error_string": ([C.c_int32], C.c_char_p),
     "ab200_last_error_detail": ([], C.c_char_p),
     "ab200_debug_trig": ([c_float_p, C.c_int32, C.c_int32, c_float_p, c_float_p, C.c_void_p], C.c_int32),
@@ -137,7 +139,25 @@ def check(rc: int, what: str) -> None:
         raise Ab200Error(f"{what} failed: {h.ab200_error_string(rc).decode()} - {h.ab200_last_error_detail().decode()}")
 
 
+# Optional per-entry-point device timing (bench.py): CUDA events on the launching stream.
+timing_enabled = False
+timing_events: dict[str, list] = {}
+
+
 def call(name: str, *args) -> None:
     global launch_count
     launch_count += 1
-    check(getattr(lib(), name)(*args), name)
+    if timing_enabled:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(*args), name)
+        e1.record()
+        timing_events.setdefault(name, []).append((e0, e1))
+    else:
+        check(getattr(lib(), name)(*args), name)
+
+
+def kernel_launches() -> int:
+    return int(lib().ab200_kernel_launch_count())

@@ -475,6 +475,7 @@ extern "C" int32_t ab200_kinematics_fwd(const ab200_kinematics_args* k, const fl
     AB200_REQUIRE(motor && out, AB200_EINVAL, "NULL pointer");
     if (k->n == 0) return AB200_OK;
     kinematics_fwd_kernel<<<(k->n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(*k, motor, out);
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }
@@ -487,6 +488,7 @@ extern "C" int32_t ab200_kinematics_bwd(const ab200_kinematics_args* k, const fl
     if (k->n == 0) return AB200_OK;
     kinematics_bwd_kernel<<<(k->n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(*k, motor, gout, g_motor, g_rot, g_trans,
                                                                                          g_act, g_pos);
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }
@@ -501,6 +503,7 @@ extern "C" int32_t ab200_kinematics_align_incident(const ab200_kinematics_args* 
     if (k->n == 0) return AB200_OK;
     kinematics_align_loop_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*k, incident, aim, max_iterations, min_eps,
                                                                                     orientations, motor_positions, scratch);
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }
@@ -515,6 +518,7 @@ extern "C" int32_t ab200_align_fwd(const float* points, const float* normals, co
     align_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(points), reinterpret_cast<const float4*>(normals), orientations, src_row, n_points,
         reinterpret_cast<float4*>(out_points), reinterpret_cast<float4*>(out_normals));
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }
@@ -530,6 +534,7 @@ extern "C" int32_t ab200_align_bwd(const float* points, const float* normals, co
         reinterpret_cast<const float4*>(points), reinterpret_cast<const float4*>(normals), orientations, src_row, n_points,
         reinterpret_cast<const float4*>(g_op), reinterpret_cast<const float4*>(g_on), reinterpret_cast<float4*>(g_p),
         reinterpret_cast<float4*>(g_n), g_ori);
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }
@@ -548,6 +553,7 @@ extern "C" int32_t ab200_bitmaps_per_target(const float* bitmaps, const int32_t*
         dim3 grid((unsigned)((ue + 255) / 256), (unsigned)n_targets);
         bitmaps_per_target_scalar_kernel<<<grid, 256, 0, st>>>(bitmaps, target_idx, n_samples, ue, out);
     }
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }

@@ -9,6 +9,7 @@
 // profiles/r01_atomics_microbench.txt).  Integer adds are order independent, so the bitmap is
 // bit-reproducible run to run.  Rays that fall outside the window use integer REDG atomics on
 // the (pre-zeroed) output row itself, which is converted to fp32 in place afterwards.
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
 #include "trace_device.cuh"
@@ -23,6 +24,9 @@ void set_error_detail(const char* fmt, ...) {
     vsnprintf(g_error_detail, sizeof(g_error_detail), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_kernel_launches{0};
+void note_launch(int n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int sm_count() {
     int dev = 0, n = 148;
@@ -337,8 +341,8 @@ __global__ void finalize_split_fp32_kernel(const TraceParams prm) {
 // ---------------------------------------------------------------------------------------------
 template <int THREADS, int TRIG>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 1024 ? 1 : 2))
-trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, float* __restrict__ grad_points,
-                 float* __restrict__ grad_normals) {
+trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
+                 float* __restrict__ grad_points, float* __restrict__ grad_normals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* win_g = reinterpret_cast<float*>(smem_raw);
     __shared__ TargetCtx T_sh;
@@ -361,7 +365,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, flo
 
     Window W;
     place_window<THREADS>(W, prm, T, h, p_begin, p_end, i0, i1, i2, red, &win_sh);
-    const float* gf = grad_flux + (size_t)h * U * E;
+    const float* gf = grad_flux + (size_t)h * grad_stride;
     {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
         const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
         for (int r = warp; r < W.wh; r += nwarps) {
@@ -544,6 +548,7 @@ static cudaError_t launch_fwd(const TraceParams& prm, const LaunchPlan& pl, cuda
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes); \
         if (e != cudaSuccess) return e;                                                                      \
         kern<<<grid, THREADS, pl.smem_bytes, st>>>(prm);                                                     \
+        note_launch();                                                                                       \
     } while (0)
     if (dbg) { if (fp32acc) AB200_LAUNCH_FWD(true, true); else AB200_LAUNCH_FWD(true, false); }
     else     { if (fp32acc) AB200_LAUNCH_FWD(false, true); else AB200_LAUNCH_FWD(false, false); }
@@ -562,21 +567,22 @@ static cudaError_t launch_fwd_trig(const TraceParams& prm, const LaunchPlan& pl,
 
 template <int THREADS, int TRIG>
 static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                              float* gpts, float* gnrm) {
+                              long long gstride, float* gpts, float* gnrm) {
     auto kern = trace_bwd_kernel<THREADS, TRIG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
     if (e != cudaSuccess) return e;
-    kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gpts, gnrm);
+    kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm);
+    note_launch();
     return cudaGetLastError();
 }
 
 template <int THREADS>
 static cudaError_t launch_bwd_trig(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                                   float* gpts, float* gnrm) {
+                                   long long gstride, float* gpts, float* gnrm) {
     switch (prm.a.trig_mode) {
-        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gpts, gnrm);
-        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gpts, gnrm);
-        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gpts, gnrm);
+        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gstride, gpts, gnrm);
+        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gstride, gpts, gnrm);
+        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gstride, gpts, gnrm);
     }
 }
 
@@ -608,8 +614,10 @@ extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
         if (!fp32acc) {
             dim3 grid((unsigned)((ue + 1023) / 1024 < 64 ? (ue + 1023) / 1024 : 64), (unsigned)a->n_local);
             finalize_split_kernel<<<grid, 256, 0, st>>>(prm);
+            note_launch();
         } else {
             finalize_split_fp32_kernel<<<(a->n_local + 127) / 128, 128, 0, st>>>(prm);
+            note_launch();
         }
         AB200_CUDA_TRY(cudaGetLastError());
     }
@@ -632,12 +640,15 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
     const LaunchPlan pl = make_plan(a->n_local, a->n_points, 512);
     TraceParams prm;
     fill_params(prm, a, pl);
-    cudaError_t e = launch_bwd_trig<512>(prm, pl, st, b->grad_flux, b->grad_points, b->grad_normals);
+    const long long gstride = b->grad_flux_stride >= 0 ? b->grad_flux_stride : (long long)a->res_u * a->res_e;
+    cudaError_t e = launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_bwd launch failed: %s", cudaGetErrorString(e));
     return AB200_OK;
 }
 
 extern "C" int32_t ab200_abi_version(void) { return AB200_ABI_VERSION; }
+
+extern "C" int64_t ab200_kernel_launch_count(void) { return ab200::g_kernel_launches.load(); }
 
 extern "C" const char* ab200_error_string(int32_t code) {
     switch (code) {
@@ -665,6 +676,7 @@ extern "C" int32_t ab200_debug_trig(const float* angles, int32_t n, int32_t mode
     AB200_REQUIRE(angles && out_sin && out_cos && n >= 0, AB200_EINVAL, "bad arguments");
     if (n == 0) return AB200_OK;
     debug_trig_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(angles, n, mode, out_sin, out_cos);
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }

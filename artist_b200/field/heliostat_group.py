@@ -65,10 +65,15 @@ class HeliostatGroup:
         device = get_device(device) if device is not None else self.positions.device
         if active_heliostats_mask is None:
             active_heliostats_mask = torch.ones(self.number_of_heliostats, dtype=torch.int32, device=device)
-        self.number_of_active_heliostats = int(active_heliostats_mask.sum().item())
+        key = (id(active_heliostats_mask), active_heliostats_mask._version)
+        if getattr(self, "_mask_key", None) == key:   # same mask tensor as last time: skip the two host syncs
+            n_active, identity = self._mask_info
+        else:
+            n_active = int(active_heliostats_mask.sum().item())
+            identity = n_active == self.number_of_heliostats and bool((active_heliostats_mask == 1).all().item())
+            self._mask_key, self._mask_info, self._mask_ref = key, (n_active, identity), active_heliostats_mask
+        self.number_of_active_heliostats = n_active
         self.active_heliostats_mask = active_heliostats_mask
-        identity = self.number_of_active_heliostats == self.number_of_heliostats and bool(
-            (active_heliostats_mask == 1).all().item())
         kin = self.kinematics
         act = getattr(kin, "actuators", None)
         if identity:

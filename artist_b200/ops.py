@@ -154,13 +154,21 @@ class _TraceFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_flux, _gi, _go, _gb):
         points, normals, incident, distortions, trig, target_idx, local_rows = ctx.saved_tensors
-        g_flux = _f32(g_flux, "grad_flux")
+        if not g_flux.is_cuda:
+            raise _lib.Ab200Error("grad_flux must be a CUDA tensor")
+        u, e = g_flux.shape[1], g_flux.shape[2]
+        if g_flux.dtype == torch.float32 and g_flux.stride(2) == 1 and g_flux.stride(1) == e and g_flux.stride(0) in (0, u * e):
+            g_stride = g_flux.stride(0)       # dense, or one [U,E] gradient shared by every sample (expanded view)
+        else:
+            g_flux = _f32(g_flux, "grad_flux")
+            g_stride = u * e
         g_points = torch.empty_like(points)
         g_normals = torch.empty_like(normals)
         b = _lib.TraceBwdArgs()
         b.fwd = _trace_args(points, normals, incident, distortions, trig, target_idx, ctx.targets, ctx.opt, local_rows,
                             None, None, None, None)
         b.grad_flux, b.grad_points, b.grad_normals = _p(g_flux), _p(g_points), _p(g_normals)
+        b.grad_flux_stride = g_stride
         _lib.call("ab200_trace_bwd", C.byref(b), _stream())
         return g_points, g_normals, None, None, None, None, None, None, None
 
@@ -205,11 +213,16 @@ class _PerTargetFn(torch.autograd.Function):
         out = torch.empty(n_targets, u, e, device=bitmaps.device)
         _lib.call("ab200_bitmaps_per_target", _p(bitmaps), _p(target_idx), n, n_targets, u, e, _p(out), _stream())
         ctx.save_for_backward(target_idx)
+        ctx.n = n
         return out
 
     @staticmethod
     def backward(ctx, g):
         (target_idx,) = ctx.saved_tensors
+        if g.shape[0] == 1:
+            # a single target: every sample sees the same [U,E] gradient - hand an expanded (stride-0) view to
+            # the trace backward, which reads it in place
+            return g.expand(ctx.n, -1, -1), None, None
         return g.index_select(0, target_idx.long()), None, None
 
 

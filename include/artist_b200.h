@@ -122,7 +122,9 @@ int32_t ab200_trace_fwd(const ab200_trace_args* args, void* stream);
  */
 typedef struct ab200_trace_bwd_args {
     ab200_trace_args fwd;     /* same inputs as the forward call (outputs/dbg pointers ignored) */
-    const float* grad_flux;   /* [N,U,E] */
+    const float* grad_flux;   /* [N,U,E]; row n starts at grad_flux + n * grad_flux_stride */
+    int64_t grad_flux_stride; /* in floats: U*E (or -1) for a dense tensor, 0 when every sample shares one [U,E] gradient
+                                 (e.g. the loss is taken on the per-target sum) - no [N,U,E] expansion is materialised */
     float* grad_points;       /* out [N,P,4] (w component 0) */
     float* grad_normals;      /* out [N,P,4] (w component 0) */
 } ab200_trace_bwd_args;
@@ -251,6 +253,7 @@ int32_t ab200_trace_host(const ab200_host_trace_args* args, void* stream);
 
 /* misc */
 int32_t ab200_abi_version(void);
+int64_t ab200_kernel_launch_count(void); /* kernels launched by this library so far (diagnostic) */
 const char* ab200_error_string(int32_t code);
 const char* ab200_last_error_detail(void); /* thread-local detail of the last failing call */
 /* per-ray trig probe for parity tests: out_sin/out_cos [n] with the kernel's trig for `mode` */

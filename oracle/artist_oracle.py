@@ -63,6 +63,26 @@ class Targets:
         return self.n_planar + self.n_cyl
 
 
+def targets_from_field_tensors(ft: dict) -> Targets:
+    """Targets from a ``synthetic_field_tensors`` dictionary."""
+    return Targets(ft["planar_centers"], ft["planar_normals"], ft["planar_dimensions"], ft["cyl_centers"],
+                   ft["cyl_normals"], ft["cyl_axes"], ft["cyl_radii"], ft["cyl_heights"], ft["cyl_opening_angles"])
+
+
+def aim_points(targets: Targets, tidx: torch.Tensor) -> torch.Tensor:
+    """``SolarTower.get_centers_of_target_areas`` (``artist/field/solar_tower.py:160-188``): plane centre, or
+    cylinder centre + radius * normal; w = 1."""
+    out = torch.zeros(tidx.shape[0], 4)
+    for i, t in enumerate(tidx.tolist()):
+        if t < targets.n_planar:
+            out[i] = targets.planar_centers[t]
+        else:
+            k = t - targets.n_planar
+            out[i] = targets.cyl_centers[k] + targets.cyl_radii[k] * targets.cyl_normals[k]
+    out[:, 3] = 1.0
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # a16  sampler  (artist/raytracing/sampling.py:88-157)
 # --------------------------------------------------------------------------------------
@@ -491,18 +511,26 @@ def nurbs_points_and_normals(control_points: torch.Tensor, degree_u: int, degree
     bi = torch.arange(n, device=cp.device).view(n, 1, 1).expand(n, f, xu.shape[2])
     fi = torch.arange(f, device=cp.device).view(1, f, 1).expand(n, f, xu.shape[2])
 
-    def contract(bu_list, bv_list):
-        out = torch.zeros(n, f, xu.shape[2], 4, device=cp.device)
+    def temps(bu_list):
+        # temp[s] = sum_r N_u[r] * P[span_u - p + r, span_v - q + s]   (surfaces.py:592-605)
+        out = []
         for s in range(degree_v + 1):
             tmp = torch.zeros(n, f, xu.shape[2], 4, device=cp.device)
             for r in range(degree_u + 1):
                 tmp = tmp + bu_list[r].unsqueeze(-1) * cp[bi, fi, su - degree_u + r, sv - degree_v + s]
-            out = out + bv_list[s].unsqueeze(-1) * tmp
+            out.append(tmp)
         return out
 
-    s00 = contract(nu0, nv0)
-    s10 = contract(nu1, nv0)
-    s01 = contract(nu0, nv1)
+    def combine(tmp, bv_list):
+        out = torch.zeros(n, f, xu.shape[2], 4, device=cp.device)
+        for s in range(degree_v + 1):
+            out = out + bv_list[s].unsqueeze(-1) * tmp[s]
+        return out
+
+    t_k0 = temps(nu0)
+    s00 = combine(t_k0, nv0)
+    s01 = combine(t_k0, nv1)
+    s10 = combine(temps(nu1), nv0)
     normals = torch.nn.functional.normalize(torch.linalg.cross(s10[..., :3], s01[..., :3]), dim=3)
     points = torch.cat([s00[..., :3] / s00[..., 3:4], torch.ones(n, f, xu.shape[2], 1, device=cp.device)], dim=3)
     normals = torch.cat([normals, torch.zeros(n, f, xu.shape[2], 1, device=cp.device)], dim=3)

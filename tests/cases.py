@@ -8,9 +8,7 @@ from artist_b200.scenario.synthetic import synthetic_field_tensors
 from oracle import artist_oracle as O
 
 
-def targets_from(ft: dict) -> O.Targets:
-    return O.Targets(ft["planar_centers"], ft["planar_normals"], ft["planar_dimensions"], ft["cyl_centers"],
-                     ft["cyl_normals"], ft["cyl_axes"], ft["cyl_radii"], ft["cyl_heights"], ft["cyl_opening_angles"])
+targets_from = O.targets_from_field_tensors
 
 
 def incident_directions(n: int, seed: int = 3, spread: float = 0.25) -> torch.Tensor:
@@ -20,17 +18,7 @@ def incident_directions(n: int, seed: int = 3, spread: float = 0.25) -> torch.Te
     return torch.cat([d, torch.zeros(n, 1)], dim=1)
 
 
-def aim_points(targets: O.Targets, tidx: torch.Tensor) -> torch.Tensor:
-    """``SolarTower.get_centers_of_target_areas`` (artist/field/solar_tower.py:160-188)."""
-    out = torch.zeros(tidx.shape[0], 4)
-    for i, t in enumerate(tidx.tolist()):
-        if t < targets.n_planar:
-            out[i] = targets.planar_centers[t]
-        else:
-            k = t - targets.n_planar
-            out[i] = targets.cyl_centers[k] + targets.cyl_radii[k] * targets.cyl_normals[k]
-    out[:, 3] = 1.0
-    return out
+aim_points = O.aim_points
 
 
 def make_case(n: int = 4, points_per_facet=(12, 12), rays: int = 5, control_points=(6, 6), bump: float = 0.002,
