@@ -1,0 +1,87 @@
+"""-m gpu: the CUDA path against the committed fixtures that the REAL reference produced
+(tests/golden/make_golden.py) - no oracle in between."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hotpath_golden.pt")
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(GOLDEN, weights_only=False)
+
+
+def _targets(f):
+    from artist_b200.ops import TargetTensors
+
+    d = lambda k: f[k].to(DEV).float().contiguous()
+    return TargetTensors(d("planar_centers"), d("planar_normals"), d("planar_dimensions"), d("cyl_centers"), d("cyl_normals"),
+                         d("cyl_axes"), d("cyl_radii"), d("cyl_heights"), d("cyl_opening_angles"))
+
+
+@pytest.mark.parametrize("key", ["trace_linear", "trace_ideal"])
+def test_trace_against_reference_fixture(golden, key):
+    from artist_b200 import ops
+
+    g = golden[key]
+    res = g["res"]
+    opt = ops.TraceOptions(res_e=res[0], res_u=res[1], trig_mode=1, scatter_sigma=2.09e-3)
+    trig = torch.stack([torch.cos(g["dist_u"]), torch.sin(g["dist_u"]), torch.cos(g["dist_e"]), torch.sin(g["dist_e"])], -1)
+    (flux, ic, ot, bl), (be, bu, t, lam) = ops.trace_debug(
+        g["aligned_points"].to(DEV), g["aligned_normals"].to(DEV), g["incident"].to(DEV),
+        ops.pack_distortions(g["dist_u"].to(DEV), g["dist_e"].to(DEV)), g["target_idx"].to(DEV), _targets(g["field"]), opt,
+        trig=trig.contiguous().to(DEV))
+    planar = g["target_idx"] == 0
+    assert torch.equal(be.cpu()[planar], g["be"][planar]) and torch.equal(bu.cpu()[planar], g["bu"][planar])
+    assert torch.equal(lam.cpu()[planar], g["lambert"][planar]) and torch.equal(t.cpu()[planar], g["t"][planar])
+    assert (flux.cpu()[planar] - g["flux"][planar]).abs().max() <= 1e-5 * g["flux"][planar].max()
+    assert torch.equal(ic.cpu()[planar], g["intercept"][planar]) and torch.equal(ot.cpu()[planar], g["on_target"][planar])
+    assert torch.equal(bl.cpu(), g["blocking"])
+    hit = (lam.cpu() > 0) & (g["lambert"] > 0) & ~planar[:, None, None]
+    assert hit.any()
+    assert (be.cpu() - g["be"])[hit].abs().max() < 0.05 and (bu.cpu() - g["bu"])[hit].abs().max() < 0.05
+    per_target = ops.bitmaps_per_target(flux, g["target_idx"].to(DEV), 2)
+    assert (per_target[0].cpu() - g["per_target"][0]).abs().max() <= 1e-5 * g["per_target"][0].max()
+
+
+@pytest.mark.parametrize("key", ["trace_linear", "trace_ideal"])
+def test_kinematics_and_alignment_against_reference_fixture(golden, key):
+    from artist_b200 import ops
+    from artist_b200.field.kinematics_rigid_body import _initial_orientation_offset
+
+    g = golden[key]
+    f = g["field"]
+    d = lambda k: f[k].to(DEV).float().contiguous()
+    linear = bool((f["actuator_non_optimizable"][:, 0] == 0).all())
+    off = _initial_orientation_offset().to(DEV)
+    ori, motor = ops.kinematics_align_incident(g["incident"].to(DEV), g["aim"].to(DEV), d("rotation_deviations"),
+                                               d("translation_deviations"), d("actuator_optimizable") if linear else None,
+                                               d("positions"), d("actuator_non_optimizable"), off, linear)
+    assert (ori.cpu() - g["orientations_incident"]).abs().max() <= 5e-5
+    assert ((motor.cpu() - g["motor"]).abs() / g["motor"].abs().clamp_min(1.0)).max() <= 2e-4
+    o2 = ops.kinematics_orientations(g["motor"].to(DEV), d("rotation_deviations"), d("translation_deviations"),
+                                     d("actuator_optimizable") if linear else None, d("positions"),
+                                     d("actuator_non_optimizable"), off, linear)
+    assert (o2.cpu() - g["orientations_motor"]).abs().max() <= 2e-5
+    ap, an = ops.align_surfaces(g["surface_points"].to(DEV), g["surface_normals"].to(DEV), g["orientations_incident"].to(DEV))
+    assert torch.equal(ap.cpu(), g["aligned_points"]) and torch.equal(an.cpu(), g["aligned_normals"])
+
+
+def test_nurbs_against_reference_fixture(golden):
+    from artist_b200 import NURBSSurfaces
+
+    for g in golden["nurbs"]:
+        cp = g["control_points"].to(DEV).requires_grad_(True)
+        surf = NURBSSurfaces(torch.tensor(g["degrees"]), cp, device=torch.device(DEV))
+        c = None if g["canting"] is None else g["canting"].to(DEV)
+        tr = None if g["facet_translations"] is None else g["facet_translations"].to(DEV)
+        pts, nrm = surf.calculate_surface_points_and_normals(g["eval_points"].to(DEV), c, tr)
+        assert torch.equal(pts.detach().cpu(), g["points"])
+        assert (nrm.detach().cpu() - g["normals"]).abs().max() <= 2.4e-7
+        ((pts * g["weight_points"].to(DEV)).sum() + (nrm * g["weight_normals"].to(DEV)).sum()).backward()
+        scale = g["grad_control_points"].abs().max()
+        assert (cp.grad.cpu() - g["grad_control_points"]).abs().max() <= 2e-5 * scale

@@ -1,0 +1,86 @@
+"""CPU: inline known-answer vectors of the reference's own unit tests, restated against the oracle.
+Sources: tests/raytracing/test_geometry.py:13-83 (reflect), tests/raytracing/test_sampling.py:6-51,
+tests/nurbs/test_surfaces.py:202-300 (NURBS forward), tests/geometry/test_transforms.py (rotate_distortions)."""
+import math
+
+import pytest
+import torch
+
+from oracle import artist_oracle as O
+
+
+def test_reflect_kat():
+    inc = torch.tensor([[1.0, 1.0, 1.0, 0.0], [1.0, 1.0, 1.0, 0.0], [1.0, 1.0, 1.0, 0.0], [2.0, 1.0, 3.0, 0.0]])
+    nrm = torch.tensor([[0.0, 0.0, 1.0, 0.0], [0.0, 1.0, 0.0, 0.0], [1.0, 0.0, 0.0, 0.0], [0.3, 0.6, 0.7, 0.0]])
+    want = torch.tensor([[1.0, 1.0, -1.0, 0.0], [1.0, -1.0, 1.0, 0.0], [-1.0, 1.0, 1.0, 0.0], [0.02, -2.96, -1.62, 0.0]])
+    torch.testing.assert_close(O.reflect(inc, nrm), want, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("ns,nh,ws,want", [
+    (12, 4, 1, [[0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]]),
+    (12, 4, 2, [[0, 1, 2, 6, 7, 8], [3, 4, 5, 9, 10, 11]]),
+    (12, 4, 3, [[0, 1, 2, 9, 10, 11], [3, 4, 5], [6, 7, 8]]),
+    (12, 4, 4, [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 10, 11]]),
+    (4, 1, 3, [[0, 1, 2, 3], [], []]),
+    (4, 2, 3, [[0, 1], [2, 3], []]),
+])
+def test_sampler_kat(ns, nh, ws, want):
+    from artist_b200.raytracing import RestrictedDistributedSampler
+
+    for rank in range(ws):
+        assert O.sampler_indices(ns, nh, ws, rank) == want[rank]
+        assert list(RestrictedDistributedSampler(ns, nh, ws, rank)) == want[rank]
+
+
+def test_nurbs_forward_kat():
+    canting = torch.tensor([[[[8.0249e-01, -0.0, -4.7736e-03, 0.0], [1.7949e-05, 6.3749e-01, 3.0172e-03, 0.0]]]])
+    tr = torch.tensor([[[1.0, 0.0, 0.0, 0.0]]])
+    ev = torch.cartesian_prod(torch.linspace(1e-5, 1 - 1e-5, 2), torch.linspace(1e-5, 1 - 1e-5, 2))[None, None]
+    cp = O.planar_control_points(4, 4, canting[0])[None]
+    pts, nrm = O.nurbs_points_and_normals(cp, 2, 2, ev, canting, tr)
+    want_p = torch.tensor([[[[1.975133419037e-01, -6.374730467796e-01, 1.756353536621e-03, 1.0],
+                             [1.975492835045e-01, 6.374730467796e-01, 7.790592499077e-03, 1.0],
+                             [1.802450656891e00, -6.374730467796e-01, -7.790592499077e-03, 1.0],
+                             [1.802486538887e00, 6.374729871750e-01, -1.756352838129e-03, 1.0]]]])
+    want_n = torch.tensor([0.005948313046, -0.004732967820, 0.999971091747, 0.0]).expand(1, 1, 4, 4)
+    torch.testing.assert_close(pts, want_p)
+    torch.testing.assert_close(nrm, want_n)
+
+
+def test_rotate_distortions_structure():
+    e, u = torch.tensor([[[0.3]]]), torch.tensor([[[-0.2]]])
+    m = O.rotate_distortions(e=e, u=u)[0, 0, 0]
+    ce, se, cu, su = math.cos(0.3), math.sin(0.3), math.cos(-0.2), math.sin(-0.2)
+    want = torch.tensor([[cu, -su, 0, 0], [ce * su, ce * cu, -se, 0], [se * su, se * cu, ce, 0], [0, 0, 0, 1.0]])
+    torch.testing.assert_close(m, want)
+    with pytest.raises(ValueError):
+        O.rotate_distortions(e=torch.zeros(1, 2, 3), u=torch.zeros(1, 2, 4))
+
+
+def test_line_plane_axis_aligned_kat():
+    """One ray straight at the centre of an 8x8 target facing +N: lands in the middle pixel, full cosine."""
+    tg = O.Targets(planar_centers=torch.tensor([[0.0, 0.0, 50.0, 1.0]]), planar_normals=torch.tensor([[0.0, 1.0, 0.0, 0.0]]),
+                   planar_dimensions=torch.tensor([[8.0, 8.0]]))
+    dirs = torch.tensor([[[[0.0, -1.0, 0.0, 0.0]]]])
+    origins = torch.tensor([[[1.0, 30.0, 51.0, 1.0]]])
+    be, bu, t, lam = O.line_plane_intersections(dirs, torch.ones(1, 1, 1), origins, tg.planar_centers, tg.planar_normals,
+                                                tg.planar_dimensions, torch.zeros(1, dtype=torch.int32), torch.tensor([256, 256]))
+    torch.testing.assert_close(t, torch.tensor([[[30.0]]]))
+    torch.testing.assert_close(lam, torch.tensor([[[1.0]]]))
+    torch.testing.assert_close(be, torch.tensor([[[255.0 - (1.0 + 4.0) / 8.0 * 255.0]]]))
+    torch.testing.assert_close(bu, torch.tensor([[[(1.0 + 4.0) / 8.0 * 255.0]]]))
+    # a ray travelling away from the plane is invalid: everything zero except the flipped e coordinate
+    be, bu, t, lam = O.line_plane_intersections(-dirs, torch.ones(1, 1, 1), origins, tg.planar_centers, tg.planar_normals,
+                                                tg.planar_dimensions, torch.zeros(1, dtype=torch.int32), torch.tensor([256, 256]))
+    assert be.item() == 255.0 and bu.item() == 0.0 and t.item() == 0.0 and lam.item() == 0.0
+
+
+def test_splat_drops_last_row_and_column():
+    """Rays exactly on the last pixel row/column are dropped (heliostat_ray_tracer.py:723-728)."""
+    res = torch.tensor([8, 6])
+    be = torch.tensor([[[7.0, 3.25, 0.0]]])
+    bu = torch.tensor([[[2.0, 5.0, 1.5]]])
+    out = O.bilinear_splatting(be, bu, torch.ones(1, 1, 3), res)
+    assert out.shape == (1, 6, 8)
+    torch.testing.assert_close(out.sum(), torch.tensor(1.0))          # only the third ray lands
+    assert out[0, 6 - 1 - 1, 0] == 0.5 and out[0, 6 - 1 - 2, 0] == 0.5  # rows flipped
