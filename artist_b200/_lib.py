@@ -58,7 +58,8 @@ class NurbsArgs(C.Structure):
         ("n_ctrl_u", C.c_int32), ("n_ctrl_v", C.c_int32), ("degree_u", C.c_int32), ("degree_v", C.c_int32),
         ("control_points", c_float_p), ("eval_points", c_float_p), ("eval_stride_n", C.c_int64),
         ("eval_stride_f", C.c_int64), ("knots_u", c_float_p), ("knots_v", c_float_p), ("canting", c_float_p),
-        ("facet_translations", c_float_p), ("points", c_float_p), ("normals", c_float_p),
+        ("facet_translations", c_float_p), ("grid_u", C.c_int32), ("grid_v", C.c_int32), ("points", c_float_p),
+        ("normals", c_float_p),
     ]
 
 

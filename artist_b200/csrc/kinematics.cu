@@ -428,18 +428,30 @@ __global__ void __launch_bounds__(256) align_bwd_kernel(const float4* __restrict
 }
 
 // ---- per-target reduction ---------------------------------------------------------------------
+// 256 threads = 8 sample lanes (one warp each) x 32 pixel quads: every warp streams 512 contiguous bytes of one
+// sample's bitmap; the 8 partial sums are combined in a fixed order (bit-reproducible).
 __global__ void __launch_bounds__(256) bitmaps_per_target_kernel(const float4* __restrict__ bm, const int* __restrict__ tidx,
                                                                  int n_samples, int ue4, float4* __restrict__ out) {
+    __shared__ float4 part[8][32];
     const int t = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ue4) return;
+    const int lane = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     float4 acc = make_float4(0, 0, 0, 0);
-    for (int n = 0; n < n_samples; ++n) {
-        if (__ldg(tidx + n) != t) continue;  // uniform across the CTA
-        const float4 v = __ldcs(bm + (size_t)n * ue4 + i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (i < ue4) {
+        for (int n = sl; n < n_samples; n += 8) {
+            if (__ldg(tidx + n) != t) continue;  // uniform across the warp
+            const float4 v = __ldcs(bm + (size_t)n * ue4 + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
     }
-    out[(size_t)t * ue4 + i] = acc;
+    part[sl][lane] = acc;
+    __syncthreads();
+    if (sl == 0 && i < ue4) {
+        float4 s = part[0][lane];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) { s.x += part[k][lane].x; s.y += part[k][lane].y; s.z += part[k][lane].z; s.w += part[k][lane].w; }
+        out[(size_t)t * ue4 + i] = s;
+    }
 }
 
 __global__ void bitmaps_per_target_scalar_kernel(const float* __restrict__ bm, const int* __restrict__ tidx, int n_samples,
@@ -546,7 +558,7 @@ extern "C" int32_t ab200_bitmaps_per_target(const float* bitmaps, const int32_t*
     const int ue = res_u * res_e;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (ue % 4 == 0) {
-        dim3 grid((unsigned)((ue / 4 + 255) / 256), (unsigned)n_targets);
+        dim3 grid((unsigned)((ue / 4 + 31) / 32), (unsigned)n_targets);
         bitmaps_per_target_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(bitmaps), target_idx, n_samples, ue / 4,
                                                         reinterpret_cast<float4*>(out));
     } else {

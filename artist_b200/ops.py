@@ -233,6 +233,39 @@ def bitmaps_per_target(bitmaps, target_idx, n_targets: int):
 # --------------------------------------------------------------------------------------------
 # NURBS
 # --------------------------------------------------------------------------------------------
+_grid_cache: dict = {}
+
+
+def detect_evaluation_grid(eval_points: torch.Tensor) -> tuple[int, int]:
+    """``(pu, pv)`` if the ``[N,F,K,2]`` evaluation points are ONE sorted cartesian grid ``u_i x v_j`` (v fastest)
+    shared by all surfaces and facets - what ``create_nurbs_evaluation_grid(...).expand(N, F, -1, -1)`` gives -
+    else ``(0, 0)``.  One small device->host copy per distinct tensor; the answer is cached."""
+    key = (eval_points.data_ptr(), tuple(eval_points.shape), tuple(eval_points.stride()), eval_points._version)
+    hit = _grid_cache.get(key)
+    if hit is not None:
+        return hit
+    result = (0, 0)
+    n, f, k, _ = eval_points.shape
+    shared = (n == 1 or eval_points.stride(0) == 0) and (f == 1 or eval_points.stride(1) == 0)
+    if not shared:  # materialised copies of one grid are fine too
+        shared = bool((eval_points == eval_points[:1, :1]).all().item())
+    if shared and k >= 4:
+        base = eval_points[0, 0].detach().cpu()
+        u, v = base[:, 0], base[:, 1]
+        pv = int((u == u[0]).sum())
+        if 1 < pv < k and k % pv == 0:
+            pu = k // pv
+            ug, vg = u.reshape(pu, pv), v.reshape(pu, pv)
+            ok = bool((ug == ug[:, :1]).all() and (vg == vg[:1]).all() and (ug[1:, 0] > ug[:-1, 0]).all()
+                      and (vg[0, 1:] > vg[0, :-1]).all())
+            if ok and pu <= 128 and pv <= 128:
+                result = (pu, pv)
+    if len(_grid_cache) > 64:
+        _grid_cache.clear()
+    _grid_cache[key] = result
+    return result
+
+
 def _nurbs_args(cp, eval_points, knots_u, knots_v, degree_u, degree_v, canting, translations, points, normals):
     n, f, cu, cv, _ = cp.shape
     a = _lib.NurbsArgs()
@@ -250,6 +283,7 @@ def _nurbs_args(cp, eval_points, knots_u, knots_v, degree_u, degree_v, canting, 
     a.eval_stride_f = st[1] if eval_points.shape[1] > 1 else 0
     a.knots_u, a.knots_v = _p(knots_u), _p(knots_v)
     a.canting, a.facet_translations = _p(canting), _p(translations)
+    a.grid_u, a.grid_v = detect_evaluation_grid(eval_points)
     a.points, a.normals = _p(points), _p(normals)
     return a
 

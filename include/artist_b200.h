@@ -134,7 +134,7 @@ int32_t ab200_trace_bwd(const ab200_trace_bwd_args* args, void* stream);
 /*
  * ab200_bitmaps_per_target - HeliostatRayTracer.get_bitmaps_per_target
  * (heliostat_ray_tracer.py:593-608): out[t] = sum of the bitmaps of samples with target_idx == t,
- * summed in ascending sample order (deterministic).  `out` is [T,U,E].
+ * summed in a fixed order (8 interleaved partial sums, then combined; deterministic).  `out` is [T,U,E].
  */
 int32_t ab200_bitmaps_per_target(const float* bitmaps, const int32_t* target_idx, int32_t n_samples,
                                  int32_t n_targets, int32_t res_u, int32_t res_e, float* out, void* stream);
@@ -161,6 +161,9 @@ typedef struct ab200_nurbs_args {
     const float* knots_v;        /* [cv+degree_v+1] */
     const float* canting;        /* [N,F,2,4] or NULL */
     const float* facet_translations; /* [N,F,4] or NULL (must be NULL iff canting is NULL) */
+    int32_t grid_u, grid_v;      /* > 0: the evaluation points are a sorted cartesian grid u_i x v_j with v fastest
+                                    (nurbs/utils.py:7-49) of grid_u x grid_v = n_eval points - enables the separable
+                                    backward; 0 = arbitrary points */
     float* points;               /* out [N,F,n_eval,4] */
     float* normals;              /* out [N,F,n_eval,4] */
 } ab200_nurbs_args;

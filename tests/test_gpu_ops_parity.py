@@ -63,6 +63,27 @@ def test_nurbs_backward_matches_autograd():
     assert (cpc.grad.cpu() - cp.grad).abs().max() <= 2e-5 * scale
 
 
+def test_nurbs_backward_unstructured_points_use_generic_gather():
+    from artist_b200 import ops
+
+    ft, _ = _nurbs_inputs(n=2, cps=(6, 6), ppf=(5, 5))
+    torch.manual_seed(4)
+    ev = (0.01 + 0.98 * torch.rand(2, 4, 300, 2)).contiguous()
+    assert ops.detect_evaluation_grid(ev.to(DEV)) == (0, 0)
+    grid = O.nurbs_evaluation_grid(9, 7)[None, None].expand(2, 4, -1, -1)
+    assert ops.detect_evaluation_grid(grid.to(DEV)) == (9, 7)
+    wp, wn = torch.randn(2, 4, 300, 4), torch.randn(2, 4, 300, 4)
+    cp = ft["nurbs_control_points"].clone().requires_grad_(True)
+    pts, nrm = O.nurbs_points_and_normals(cp, 3, 3, ev, ft["canting"], ft["facet_translations"])
+    ((pts * wp).sum() + (nrm * wn).sum()).backward()
+    cpc = ft["nurbs_control_points"].to(DEV).requires_grad_(True)
+    gp, gn = ops.nurbs_points_and_normals(cpc, ev.to(DEV), O.uniform_knots(6, 3).to(DEV), O.uniform_knots(6, 3).to(DEV), 3, 3,
+                                          ft["canting"].to(DEV), ft["facet_translations"].to(DEV))
+    assert (gp.detach().cpu() - pts.detach()).abs().max() <= 1e-6
+    ((gp * wp.to(DEV)).sum() + (gn * wn.to(DEV)).sum()).backward()
+    assert (cpc.grad.cpu() - cp.grad).abs().max() <= 2e-5 * cp.grad.abs().max()
+
+
 def _kin_dev(kin):
     f = lambda x: x.to(DEV).float().contiguous()
     return dict(positions=f(kin.positions), trans=f(kin.translation_deviations), rot=f(kin.rotation_deviations),

@@ -1,0 +1,18 @@
+"""Small driver for ncu: a few full fwd+bwd steps of the bench workload at a reduced heliostat count."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import bench
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+dev = torch.device("cuda:0")
+torch.cuda.set_device(dev)
+wl = bench.Workload(dev, n, 1, 0)
+for _ in range(steps):
+    wl.step()
+torch.cuda.synchronize()
+print("done", n, steps)
