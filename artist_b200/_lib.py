@@ -104,6 +104,7 @@ EXPORTS = {
     "ab200_kernel_launch_count": ([], C.c_int64),
     "ab200_error_string": ([C.c_int32], C.c_char_p),
     "ab200_last_error_detail": ([], C.c_char_p),
+    "ab200_debug_const_div": ([c_float_p, C.c_int32, C.c_float, c_float_p, c_float_p, C.c_void_p], C.c_int32),
     "ab200_debug_trig": ([c_float_p, C.c_int32, C.c_int32, c_float_p, c_float_p, C.c_void_p], C.c_int32),
 }
 

@@ -50,6 +50,8 @@ struct Window {
 };
 
 constexpr int kWindowSampleStride = 4;
+constexpr int kFwdThreadsLarge = 1024;  // one CTA per SM with a ~200 KB bitmap window
+constexpr int kBwdThreadsLarge = 1024;
 
 // ---------------------------------------------------------------------------------------------
 // window placement: bounding box of the undistorted reflections of a subset of the CTA's points,
@@ -123,8 +125,103 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+struct FwdCtx {
+    unsigned* win_u;     // shared-memory window (fixed point) ...
+    float* win_f;        // ... or fp32 (AB200_FLAG_FP32_ACCUM)
+    float* out_f;        // this sample's [U,E] output row
+    int e0, u0, ww, wwm1, whm1;  // window origin, row pitch, (width-1), (height-1); an empty window has wwm1 = whm1 = 0
+    int wh;
+};
+
+// The per-ray loop of one CTA, specialised on the target type and on whether the exact constant-divisor quotient
+// may be used, so that the hot loop carries no target-type branch.
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool PLANAR, bool FASTDIV>
+__device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h, int p_begin,
+                                         int p_end, float i0, float i1, float i2, int& cnt_lam_out, int& cnt_int_out,
+                                         bool& fell_back_out) {
+    const int tid = threadIdx.x;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
+    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
+    const float fxs = prm.fx_scale;
+    int cnt_lam = 0, cnt_int = 0;
+    bool fell_back = false;
+
+    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+        PointCtx pc;
+        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        const float2* dp = dist + p;
+        float2 d_next = __ldcs(dp);
+        for (int r = 0; r < R; ++r) {
+            const float2 d = d_next;
+            dp += P;
+            if (r + 1 < R) d_next = __ldcs(dp);
+            Scatter s;
+            ray_trig<TRIG>(d.x, d.y, trig, (size_t)r * P + p, s.cu, s.su, s.ce, s.se);
+            scatter(s, pc);
+            Hit hit;
+            if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
+            // intensities = lambert * (1 - blocked) * (1 - extinction) * reflectivity   (:482-487); lambert * 1 is exact
+            const float inten = smul(smul(hit.lam, ome), refl);
+            if (DBG) {
+                const size_t q = ((size_t)h * R + r) * P + p;
+                if (prm.a.dbg_be) prm.a.dbg_be[q] = hit.be;
+                if (prm.a.dbg_bu) prm.a.dbg_bu[q] = hit.bu;
+                if (prm.a.dbg_t) prm.a.dbg_t[q] = hit.t;
+                if (prm.a.dbg_lambert) prm.a.dbg_lambert[q] = hit.lam;
+            }
+            cnt_lam += (hit.lam > 0.0f);
+            cnt_int += (inten > 0.0f);
+            if (!hit.valid) continue;
+            Splat sp;
+            splat_weights(sp, hit.be, hit.bu, E, U);
+            if (!sp.on) continue;
+            const int ce = sp.ie - fc.e0, cu = sp.iu - fc.u0;
+            const bool fast = ((unsigned)ce < (unsigned)fc.wwm1) && ((unsigned)cu < (unsigned)fc.whm1);
+            if (FP32ACC) {
+                const float v1 = smul(smul(sp.wle, sp.whu), inten), v2 = smul(smul(sp.whe, sp.whu), inten);
+                const float v3 = smul(smul(sp.whe, sp.wlu), inten), v4 = smul(smul(sp.wle, sp.wlu), inten);
+                if (fast) {
+                    float* b = fc.win_f + cu * fc.ww + ce;
+                    atomicAdd(b + fc.ww, v1); atomicAdd(b + fc.ww + 1, v2); atomicAdd(b + 1, v3); atomicAdd(b, v4);
+                } else {
+                    float* row_hi = fc.out_f + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
+                    float* row_lo = row_hi + E;
+                    atomicAdd(row_hi, v1); atomicAdd(row_hi + 1, v2); atomicAdd(row_lo + 1, v3); atomicAdd(row_lo, v4);
+                }
+            } else {
+                const float ahi = fabsf(sp.whu * inten) * fxs, alo = fabsf(sp.wlu * inten) * fxs;
+                const unsigned q1 = __float2uint_rn(sp.wle * ahi), q2 = __float2uint_rn(sp.whe * ahi);
+                const unsigned q3 = __float2uint_rn(sp.whe * alo), q4 = __float2uint_rn(sp.wle * alo);
+                if (fast) {
+                    unsigned* b = fc.win_u + cu * fc.ww + ce;
+                    atomicAdd(b + fc.ww, q1); atomicAdd(b + fc.ww + 1, q2); atomicAdd(b + 1, q3); atomicAdd(b, q4);
+                } else {
+                    // per-tap routing: a tap inside the window region must go to shared memory so that window pixels
+                    // are owned by shared memory only
+                    fell_back = true;
+                    const bool e_in0 = (unsigned)ce < (unsigned)fc.ww, e_in1 = (unsigned)(ce + 1) < (unsigned)fc.ww;
+                    const bool u_in0 = (unsigned)cu < (unsigned)fc.wh, u_in1 = (unsigned)(cu + 1) < (unsigned)fc.wh;
+                    unsigned* g_hi = out_u + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
+                    unsigned* g_lo = g_hi + E;
+                    unsigned* b = fc.win_u + cu * fc.ww + ce;
+                    if (u_in1 && e_in0) atomicAdd(b + fc.ww, q1); else atomicAdd(g_hi, q1);
+                    if (u_in1 && e_in1) atomicAdd(b + fc.ww + 1, q2); else atomicAdd(g_hi + 1, q2);
+                    if (u_in0 && e_in1) atomicAdd(b + 1, q3); else atomicAdd(g_lo + 1, q3);
+                    if (u_in0 && e_in0) atomicAdd(b, q4); else atomicAdd(g_lo, q4);
+                }
+            }
+        }
+    }
+    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; fell_back_out = fell_back;
+}
+
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 1024 ? 1 : 2))
+__global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_fwd_kernel(const TraceParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned* win_u = reinterpret_cast<unsigned*>(smem_raw);
@@ -158,84 +255,20 @@ trace_fwd_kernel(const TraceParams prm) {
     for (int i = tid; i < wcells; i += THREADS) win_u[i] = 0u;
     __syncthreads();
 
-    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
-    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
-    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
     float* out_f = prm.a.flux + (size_t)h * U * E;
     unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
-    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
-    const float fxs = prm.fx_scale;
+    FwdCtx fc;
+    fc.win_u = win_u; fc.win_f = win_f; fc.out_f = out_f;
+    fc.e0 = W.e0; fc.u0 = W.u0; fc.ww = W.ww; fc.wh = W.wh;
+    fc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; fc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
 
     int cnt_lam = 0, cnt_int = 0;
     bool fell_back = false;
-
-    for (int p = p_begin + tid; p < p_end; p += THREADS) {
-        PointCtx pc;
-        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
-        const float2* dp = dist + p;
-        float2 d_next = __ldcs(dp);
-        for (int r = 0; r < R; ++r) {
-            const float2 d = d_next;
-            if (r + 1 < R) d_next = __ldcs(dp + (size_t)(r + 1) * P);
-            Scatter s;
-            ray_trig<TRIG>(d.x, d.y, trig, (size_t)r * P + p, s.cu, s.su, s.ce, s.se);
-            scatter(s, pc);
-            Hit hit;
-            if (T.planar) hit_planar(hit, T, pc, s, mag); else hit_cylinder(hit, T, pc, s, mag);
-            // intensities = lambert * (1 - blocked) * (1 - extinction) * reflectivity   (:482-487)
-            const float inten = smul(smul(smul(hit.lam, 1.0f), ome), refl);
-            if (DBG) {
-                const size_t q = ((size_t)h * R + r) * P + p;
-                if (prm.a.dbg_be) prm.a.dbg_be[q] = hit.be;
-                if (prm.a.dbg_bu) prm.a.dbg_bu[q] = hit.bu;
-                if (prm.a.dbg_t) prm.a.dbg_t[q] = hit.t;
-                if (prm.a.dbg_lambert) prm.a.dbg_lambert[q] = hit.lam;
-            }
-            cnt_lam += (hit.lam > 0.0f);
-            cnt_int += (inten > 0.0f);
-            if (!hit.valid) continue;
-            Splat sp;
-            splat_weights(sp, hit.be, hit.bu, E, U);
-            if (!sp.on) continue;
-            const int ce = sp.ie - W.e0, cu = sp.iu - W.u0;
-            const bool fast = (ce >= 0) && (ce + 1 < W.ww) && (cu >= 0) && (cu + 1 < W.wh);
-            if (FP32ACC) {
-                const float v1 = smul(smul(sp.wle, sp.whu), inten), v2 = smul(smul(sp.whe, sp.whu), inten);
-                const float v3 = smul(smul(sp.whe, sp.wlu), inten), v4 = smul(smul(sp.wle, sp.wlu), inten);
-                if (fast) {
-                    const int b = cu * W.ww + ce;
-                    atomicAdd(win_f + b + W.ww, v1); atomicAdd(win_f + b + W.ww + 1, v2);
-                    atomicAdd(win_f + b + 1, v3);    atomicAdd(win_f + b, v4);
-                } else {
-                    float* row_hi = out_f + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
-                    float* row_lo = out_f + (size_t)(U - 1 - sp.iu) * E + sp.ie;
-                    atomicAdd(row_hi, v1); atomicAdd(row_hi + 1, v2); atomicAdd(row_lo + 1, v3); atomicAdd(row_lo, v4);
-                }
-            } else {
-                const float ahi = fabsf(sp.whu * inten) * fxs, alo = fabsf(sp.wlu * inten) * fxs;
-                const unsigned q1 = __float2uint_rn(sp.wle * ahi), q2 = __float2uint_rn(sp.whe * ahi);
-                const unsigned q3 = __float2uint_rn(sp.whe * alo), q4 = __float2uint_rn(sp.wle * alo);
-                if (fast) {
-                    const int b = cu * W.ww + ce;
-                    atomicAdd(win_u + b + W.ww, q1); atomicAdd(win_u + b + W.ww + 1, q2);
-                    atomicAdd(win_u + b + 1, q3);    atomicAdd(win_u + b, q4);
-                } else {
-                    // per-tap routing: a tap inside the window region must go to shared memory so that
-                    // window pixels are owned by shared memory only
-                    fell_back = true;
-                    const bool e_in0 = (ce >= 0) && (ce < W.ww), e_in1 = (ce + 1 >= 0) && (ce + 1 < W.ww);
-                    const bool u_in0 = (cu >= 0) && (cu < W.wh), u_in1 = (cu + 1 >= 0) && (cu + 1 < W.wh);
-                    unsigned* g_hi = out_u + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
-                    unsigned* g_lo = out_u + (size_t)(U - 1 - sp.iu) * E + sp.ie;
-                    const int b = cu * W.ww + ce;
-                    if (u_in1 && e_in0) atomicAdd(win_u + b + W.ww, q1); else atomicAdd(g_hi, q1);
-                    if (u_in1 && e_in1) atomicAdd(win_u + b + W.ww + 1, q2); else atomicAdd(g_hi + 1, q2);
-                    if (u_in0 && e_in1) atomicAdd(win_u + b + 1, q3); else atomicAdd(g_lo + 1, q3);
-                    if (u_in0 && e_in0) atomicAdd(win_u + b, q4); else atomicAdd(g_lo, q4);
-                }
-            }
-        }
+    if (T.planar) {
+        if (T.fastdiv) fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, true>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
+        else fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
+    } else {
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
     }
 
     // ---- epilogue: counters, window flush -----------------------------------------------------
@@ -339,48 +372,25 @@ __global__ void finalize_split_fp32_kernel(const TraceParams prm) {
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-template <int THREADS, int TRIG>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 1024 ? 1 : 2))
-trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
-                 float* __restrict__ grad_points, float* __restrict__ grad_normals) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* win_g = reinterpret_cast<float*>(smem_raw);
-    __shared__ TargetCtx T_sh;
-    __shared__ Window win_sh;
-    __shared__ float red[6 * 32];
+struct BwdCtx {
+    const float* win_g;  // shared-memory window of the bitmap gradient
+    const float* gf;     // this sample's [U,E] gradient in global memory
+    int e0, u0, ww, wwm1, whm1;
+};
 
+template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV>
+__device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, int h, int p_begin,
+                                         int p_end, float i0, float i1, float i2, float* __restrict__ grad_points,
+                                         float* __restrict__ grad_normals) {
     const int tid = threadIdx.x;
-    const int li = blockIdx.x / prm.split;
-    const int chunk = blockIdx.x - li * prm.split;
-    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
-    const int p_begin = chunk * prm.pts_per_chunk;
-    const int p_end = min(P, p_begin + prm.pts_per_chunk);
-
-    if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
-    __syncthreads();
-    const TargetCtx T = T_sh;
-    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
-                i2 = __ldg(prm.a.incident + 4 * h + 2);
-
-    Window W;
-    place_window<THREADS>(W, prm, T, h, p_begin, p_end, i0, i1, i2, red, &win_sh);
-    const float* gf = grad_flux + (size_t)h * grad_stride;
-    {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
-        const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
-        for (int r = warp; r < W.wh; r += nwarps) {
-            const float* grow = gf + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
-            for (int c = lane; c < W.ww; c += 32) win_g[r * W.ww + c] = __ldg(grow + c);
-        }
-    }
-    __syncthreads();
-
     const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
     const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
     const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
     const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
     const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
-    const float k_int = mag * ome * refl;          // d intensity / d lambert-cosine
+    const float k_or = ome * refl;
+    const float k_int = mag * k_or;                 // d intensity / d lambert-cosine
     const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
@@ -393,38 +403,39 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
         float2 d_next = __ldcs(dp);
         for (int r = 0; r < R; ++r) {
             const float2 d = d_next;
-            if (r + 1 < R) d_next = __ldcs(dp + (size_t)(r + 1) * P);
+            dp += P;
+            if (r + 1 < R) d_next = __ldcs(dp);
             Scatter s;
             ray_trig<TRIG>(d.x, d.y, trig, (size_t)r * P + p, s.cu, s.su, s.ce, s.se);
             scatter(s, pc);
             Hit hit;
-            if (T.planar) hit_planar(hit, T, pc, s, mag); else hit_cylinder(hit, T, pc, s, mag);
+            if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
             if (!hit.valid) continue;
             Splat sp;
             splat_weights(sp, hit.be, hit.bu, E, U);
             if (!sp.on) continue;
             // gather the four gradient taps
             float g1, g2, g3, g4;
-            const int ce = sp.ie - W.e0, cu = sp.iu - W.u0;
-            if ((ce >= 0) && (ce + 1 < W.ww) && (cu >= 0) && (cu + 1 < W.wh)) {
-                const int b = cu * W.ww + ce;
-                g1 = win_g[b + W.ww]; g2 = win_g[b + W.ww + 1]; g3 = win_g[b + 1]; g4 = win_g[b];
+            const int ce = sp.ie - bc.e0, cu = sp.iu - bc.u0;
+            if (((unsigned)ce < (unsigned)bc.wwm1) && ((unsigned)cu < (unsigned)bc.whm1)) {
+                const float* b = bc.win_g + cu * bc.ww + ce;
+                g1 = b[bc.ww]; g2 = b[bc.ww + 1]; g3 = b[1]; g4 = b[0];
             } else {
-                const float* row_hi = gf + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
-                const float* row_lo = gf + (size_t)(U - 1 - sp.iu) * E + sp.ie;
+                const float* row_hi = bc.gf + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
+                const float* row_lo = row_hi + E;
                 g1 = __ldg(row_hi); g2 = __ldg(row_hi + 1); g3 = __ldg(row_lo + 1); g4 = __ldg(row_lo);
             }
-            const float inten = hit.lam * ome * refl;
+            const float inten = hit.lam * k_or;
             const float g_int = sp.whu * (sp.wle * g1 + sp.whe * g2) + sp.wlu * (sp.whe * g3 + sp.wle * g4);
             const float g_be = inten * (sp.whu * (g2 - g1) + sp.wlu * (g3 - g4));
             const float g_bu = inten * (sp.wle * (g1 - g4) + sp.whe * (g2 - g3));
             float gdx, gdy, gdz;
-            if (T.planar) {
+            if (PLANAR) {
                 const float g_a0 = -g_int * k_int;                 // lam = mag * (-a)
                 const float gX = -g_be * k_e, gZ = g_bu * k_u;     // be = (E-1) - te/w*(E-1)
                 go0 += gX; go2 += gZ;
                 const float gt = gX * s.dx + gZ * s.dz;
-                const float gnum = gt / hit.a;                     // t = num / a
+                const float gnum = __fdividef(gt, hit.a);          // t = num / a
                 const float g_a = g_a0 - gnum * hit.t;
                 go0 -= gnum * T.n0; go1 -= gnum * T.n1; go2 -= gnum * T.n2;
                 gdx = gX * hit.t + g_a * T.n0;
@@ -465,7 +476,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
             gr2 += -s.se * gdy + s.ce * gdz;
         }
         float gp0, gp1, gp2;
-        if (T.planar) { gp0 = go0; gp1 = go1; gp2 = go2; }
+        if (PLANAR) { gp0 = go0; gp1 = go1; gp2 = go2; }
         else {  // origin_local = Rot (o - c)
             gp0 = T.ux * go0 + T.n0 * go1 + T.ax0 * go2;
             gp1 = T.uy * go0 + T.n1 * go1 + T.ax1 * go2;
@@ -478,6 +489,52 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
         const float gn2 = -2.0f * (pc.dot * gr2 + grn * i2);
         reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = make_float4(gp0, gp1, gp2, 0.f);
         reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = make_float4(gn0, gn1, gn2, 0.f);
+    }
+}
+
+template <int THREADS, int TRIG>
+__global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
+trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
+                 float* __restrict__ grad_points, float* __restrict__ grad_normals) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* win_g = reinterpret_cast<float*>(smem_raw);
+    __shared__ TargetCtx T_sh;
+    __shared__ Window win_sh;
+    __shared__ float red[6 * 32];
+
+    const int tid = threadIdx.x;
+    const int li = blockIdx.x / prm.split;
+    const int chunk = blockIdx.x - li * prm.split;
+    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
+    const int P = prm.a.n_points, E = prm.a.res_e, U = prm.a.res_u;
+    const int p_begin = chunk * prm.pts_per_chunk;
+    const int p_end = min(P, p_begin + prm.pts_per_chunk);
+
+    if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
+    __syncthreads();
+    const TargetCtx T = T_sh;
+    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
+                i2 = __ldg(prm.a.incident + 4 * h + 2);
+
+    Window W;
+    place_window<THREADS>(W, prm, T, h, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    const float* gf = grad_flux + (size_t)h * grad_stride;
+    {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
+        const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
+        for (int r = warp; r < W.wh; r += nwarps) {
+            const float* grow = gf + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
+            for (int c = lane; c < W.ww; c += 32) win_g[r * W.ww + c] = __ldg(grow + c);
+        }
+    }
+    __syncthreads();
+    BwdCtx bc;
+    bc.win_g = win_g; bc.gf = gf; bc.e0 = W.e0; bc.u0 = W.u0; bc.ww = W.ww;
+    bc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; bc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
+    if (T.planar) {
+        if (T.fastdiv) bwd_rays<THREADS, TRIG, true, true>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+        else bwd_rays<THREADS, TRIG, true, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+    } else {
+        bwd_rays<THREADS, TRIG, false, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
     }
 }
 
@@ -602,13 +659,13 @@ extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
     AB200_CUDA_TRY(cudaMemsetAsync(a->on_target, 0, (size_t)a->n_samples * sizeof(float), st));
     AB200_CUDA_TRY(cudaMemsetAsync(a->blocking, 0, (size_t)a->n_samples * sizeof(float), st));
     if (a->n_local == 0 || a->n_samples == 0) return AB200_OK;
-    const LaunchPlan pl = make_plan(a->n_local, a->n_points, 1024);
+    const LaunchPlan pl = make_plan(a->n_local, a->n_points, kFwdThreadsLarge);
     TraceParams prm;
     fill_params(prm, a, pl);
     const bool dbg = a->dbg_be || a->dbg_bu || a->dbg_t || a->dbg_lambert;
     const bool fp32acc = (a->flags & AB200_FLAG_FP32_ACCUM) != 0;
-    cudaError_t e = (pl.threads == 1024) ? launch_fwd_trig<1024>(prm, pl, st, dbg, fp32acc)
-                                         : launch_fwd_trig<512>(prm, pl, st, dbg, fp32acc);
+    cudaError_t e = (pl.threads == kFwdThreadsLarge) ? launch_fwd_trig<kFwdThreadsLarge>(prm, pl, st, dbg, fp32acc)
+                                                     : launch_fwd_trig<512>(prm, pl, st, dbg, fp32acc);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_fwd launch failed: %s", cudaGetErrorString(e));
     if (pl.split > 1) {
         if (!fp32acc) {
@@ -637,11 +694,13 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
         AB200_CUDA_TRY(cudaMemsetAsync(b->grad_normals, 0, np4 * sizeof(float), st));
     }
     if (a->n_local == 0 || a->n_samples == 0) return AB200_OK;
-    const LaunchPlan pl = make_plan(a->n_local, a->n_points, 512);
+    const LaunchPlan pl = make_plan(a->n_local, a->n_points, kBwdThreadsLarge);
     TraceParams prm;
     fill_params(prm, a, pl);
     const long long gstride = b->grad_flux_stride >= 0 ? b->grad_flux_stride : (long long)a->res_u * a->res_e;
-    cudaError_t e = launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals);
+    cudaError_t e = (pl.threads == kBwdThreadsLarge)
+                        ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals)
+                        : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_bwd launch failed: %s", cudaGetErrorString(e));
     return AB200_OK;
 }
@@ -671,6 +730,25 @@ __global__ void debug_trig_kernel(const float* x, int n, int mode, float* s, flo
     s[i] = ss; c[i] = cc;
 }
 }  // namespace ab200
+
+namespace ab200 {
+__global__ void debug_const_div_kernel(const float* a, int n, float b, float* q_fast, float* q_ieee) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float rb = __frcp_rn(b);
+    q_fast[i] = const_div(a[i], b, rb);
+    q_ieee[i] = __fdiv_rn(a[i], b);
+}
+}  // namespace ab200
+
+extern "C" int32_t ab200_debug_const_div(const float* a, int32_t n, float b, float* q_fast, float* q_ieee, void* stream) {
+    AB200_REQUIRE(a && q_fast && q_ieee && n >= 0, AB200_EINVAL, "bad arguments");
+    if (n == 0) return AB200_OK;
+    debug_const_div_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, n, b, q_fast, q_ieee);
+    note_launch();
+    AB200_CUDA_TRY(cudaGetLastError());
+    return AB200_OK;
+}
 
 extern "C" int32_t ab200_debug_trig(const float* angles, int32_t n, int32_t mode, float* out_sin, float* out_cos, void* stream) {
     AB200_REQUIRE(angles && out_sin && out_cos && n >= 0, AB200_EINVAL, "bad arguments");

@@ -20,7 +20,26 @@ struct TargetCtx {
     float ux, uy, uz, ax0, ax1, ax2, rad2, opn, ang0;
     // pixel-per-metre scale used only for sizing the shared-memory window
     float px_per_m_e, px_per_m_u;
+    // correctly rounded reciprocals of the two per-target divisors (planar: w, h; cylinder: opening, h) and whether the
+    // 3-instruction exact quotient (const_div) may be used for them
+    float rw, rh;
+    int fastdiv;
 };
+
+// a / b for a divisor b that is constant per CTA, given rb = RN(1/b): q0 = RN(a*rb); r = a - q0*b (exact, FMA);
+// q = RN(q0 + r*rb).  By Markstein's theorem q is the correctly rounded quotient for every a unless b's significand is
+// all ones (checked once per target -> IEEE division path); inputs outside the normal range give the same inf/NaN
+// classification, which is all the validity test needs.  tests/test_gpu_ops_parity.py checks it against __fdiv_rn.
+__device__ __forceinline__ float const_div(float a, float b, float rb) {
+    const float q0 = __fmul_rn(a, rb);
+    const float r = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(r, rb, q0);
+}
+__device__ __forceinline__ bool const_div_ok(float b) {
+    const unsigned u = __float_as_uint(b);
+    const unsigned ex = (u >> 23) & 0xffu;
+    return ((u & 0x7fffffu) != 0x7fffffu) && ex > 40u && ex < 210u;
+}
 
 __device__ inline void load_target(TargetCtx& T, const ab200_targets& tg, int tidx, int res_e, int res_u) {
     T.em1 = (float)(res_e - 1);
@@ -37,6 +56,9 @@ __device__ inline void load_target(TargetCtx& T, const ab200_targets& tg, int ti
         T.half_h = sdiv(T.h, 2.0f);
         T.px_per_m_e = T.em1 / T.w;
         T.px_per_m_u = T.um1 / T.h;
+        T.rw = __frcp_rn(T.w);
+        T.rh = __frcp_rn(T.h);
+        T.fastdiv = const_div_ok(T.w) && const_div_ok(T.h);
     } else {
         const int k = tidx - tg.n_planar;
         T.planar = 0;
@@ -60,6 +82,9 @@ __device__ inline void load_target(TargetCtx& T, const ab200_targets& tg, int ti
         T.ang0 = ssub(atan2f(T.n1, T.n0), sdiv(T.opn, 2.0f));
         T.px_per_m_e = T.em1 / fmaxf(rad * T.opn, 1e-6f);
         T.px_per_m_u = T.um1 / T.h;
+        T.rw = __frcp_rn(T.opn);
+        T.rh = __frcp_rn(T.h);
+        T.fastdiv = const_div_ok(T.opn) && const_div_ok(T.h);
     }
 }
 
@@ -125,6 +150,7 @@ struct Hit {
     int near_root;
 };
 
+template <bool FASTDIV>
 __device__ __forceinline__ void hit_planar(Hit& h, const TargetCtx& T, const PointCtx& pc, const Scatter& s, float mag) {
     const float a = sadd(sadd(smul(s.dx, T.n0), smul(s.dy, T.n1)), smul(s.dz, T.n2));
     const bool ff = a < 0.0f;
@@ -133,8 +159,8 @@ __device__ __forceinline__ void hit_planar(Hit& h, const TargetCtx& T, const Poi
     const float Z = sadd(pc.o2, smul(s.dz, t));
     const float te = ssub(sadd(X, T.half_w), T.c0);
     const float tu = ssub(sadd(Z, T.half_h), T.c2);
-    const float be0 = smul(sdiv(te, T.w), T.em1);
-    const float bu0 = smul(sdiv(tu, T.h), T.um1);
+    const float be0 = smul(FASTDIV ? const_div(te, T.w, T.rw) : sdiv(te, T.w), T.em1);
+    const float bu0 = smul(FASTDIV ? const_div(tu, T.h, T.rh) : sdiv(tu, T.h), T.um1);
     const bool valid = ff && (0.0f <= be0) && (be0 <= T.em1) && (0.0f <= bu0) && (bu0 <= T.um1);
     h.a = a;
     h.valid = valid;
@@ -156,6 +182,7 @@ __device__ __forceinline__ bool centre_planar(const TargetCtx& T, const PointCtx
     return true;
 }
 
+template <bool FASTDIV>
 __device__ __forceinline__ void hit_cylinder(Hit& h, const TargetCtx& T, const PointCtx& pc, const Scatter& s, float mag) {
     // directions @ rot^T (FMA chain over k, as the CPU GEMM does)
     const float dlx = fmaf(s.dz, T.uz, fmaf(s.dy, T.uy, smul(s.dx, T.ux)));
@@ -188,8 +215,8 @@ __device__ __forceinline__ void hit_cylinder(Hit& h, const TargetCtx& T, const P
     const bool on = (z >= 0.0f) && (z <= T.h) && (ang >= 0.0f) && (ang <= T.opn);
     const bool valid = on && vd;
     h.valid = valid;
-    h.bu = valid ? smul(sdiv(z, T.h), T.um1) : 0.0f;
-    h.be = valid ? smul(sdiv(ang, T.opn), T.em1) : 0.0f;
+    h.bu = valid ? smul(FASTDIV ? const_div(z, T.h, T.rh) : sdiv(z, T.h), T.um1) : 0.0f;
+    h.be = valid ? smul(FASTDIV ? const_div(ang, T.opn, T.rw) : sdiv(ang, T.opn), T.em1) : 0.0f;
     h.t = valid ? t : 0.0f;
     h.lam = valid ? smul(mag, lam) : 0.0f;
     h.dlx = dlx; h.dly = dly; h.dlz = dlz; h.x = x; h.y = y; h.qa = qa; h.qb = qb; h.sq = sq; h.nrm = nrm;
@@ -202,13 +229,14 @@ __device__ __forceinline__ bool centre_cylinder(const TargetCtx& T, const PointC
     Scatter s;
     s.dx = pc.r0; s.dy = pc.r1; s.dz = pc.r2;
     Hit h;
-    hit_cylinder(h, T, pc, s, 1.0f);
+    hit_cylinder<false>(h, T, pc, s, 1.0f);
     if (!h.valid) return false;
     be = h.be; bu = h.bu; t = h.t; cosi = fmaxf(h.lam, 0.05f);
     return true;
 }
 
-// Bilinear splat weights (heliostat_ray_tracer.py:674-728)
+// Bilinear splat weights (heliostat_ray_tracer.py:674-728).  Precondition: the ray is valid, so 0 <= be <= E-1 and
+// 0 <= bu <= U-1 and the lower-bound tests of the reference's on-target mask are always true.
 struct Splat {
     int ie, iu;
     bool on;
@@ -216,13 +244,14 @@ struct Splat {
 };
 
 __device__ __forceinline__ void splat_weights(Splat& sp, float be, float bu, int res_e, int res_u) {
-    sp.ie = (int)be;  // trunc toward zero == tensor.long() for the valid range
-    sp.iu = (int)bu;
-    sp.on = (0 <= sp.ie) && (sp.ie + 1 < res_e) && (0 <= sp.iu) && (sp.iu + 1 < res_u);
-    sp.wle = ssub((float)(sp.ie + 1), be);
-    sp.wlu = ssub((float)(sp.iu + 1), bu);
-    sp.whe = ssub(be, (float)sp.ie);
-    sp.whu = ssub(bu, (float)sp.iu);
+    const float fe = truncf(be), fu = truncf(bu);  // == tensor.long() for non-negative coordinates
+    sp.ie = __float2int_rz(be);
+    sp.iu = __float2int_rz(bu);
+    sp.on = (sp.ie + 1 < res_e) && (sp.iu + 1 < res_u);
+    sp.wle = ssub(sadd(fe, 1.0f), be);   // (ie + 1) - be: ie + 1 is exact in fp32
+    sp.wlu = ssub(sadd(fu, 1.0f), bu);
+    sp.whe = ssub(be, fe);
+    sp.whu = ssub(bu, fu);
 }
 
 }  // namespace ab200

@@ -86,7 +86,7 @@ class TraceOptions:
     ray_extinction_factor: float = 0.0
     mirror_reflectivity: float = 0.935
     scatter_sigma: float = 0.0
-    trig_mode: int = _lib.TRIG_SINCOSF
+    trig_mode: int = _lib.TRIG_POLY
     fp32_accumulate: bool = False
 
 
@@ -445,3 +445,10 @@ def debug_trig(angles: torch.Tensor, mode: int):
     c = torch.empty_like(angles)
     _lib.call("ab200_debug_trig", _p(angles), angles.numel(), int(mode), _p(s), _p(c), _stream())
     return s, c
+
+
+def debug_const_div(a: torch.Tensor, b: float):
+    a = _f32(a, "a").reshape(-1)
+    qf, qi = torch.empty_like(a), torch.empty_like(a)
+    _lib.call("ab200_debug_const_div", _p(a), a.numel(), float(b), _p(qf), _p(qi), _stream())
+    return qf, qi

@@ -279,7 +279,7 @@ def workload_config(gpus: int, note: str | None = None) -> dict:
         "heliostats_per_gpu": N_HELIOSTATS, "surface_points": 4 * POINTS_PER_FACET[0] * POINTS_PER_FACET[1], "rays_per_point": RAYS,
         "bitmap": list(RES), "control_points": list(CONTROL_POINTS), "parallelism": f"heliostat-sharded x{gpus}, NCCL all-reduce of the [T,U,E] flux",
         "l2_policy": "inputs larger than L2 (2.9 GB of distortions/points/normals per step per GPU vs 126 MB L2)",
-        "trig": "sincosf", "accumulate": "fixed-point (deterministic)",
+        "trig": "polynomial sin/cos (<= 1 ulp), FMA-free coordinate path", "accumulate": "fixed-point (deterministic)",
     }
     if note:
         cfg["note"] = note

@@ -260,6 +260,8 @@ int64_t ab200_kernel_launch_count(void); /* kernels launched by this library so 
 const char* ab200_error_string(int32_t code);
 const char* ab200_last_error_detail(void); /* thread-local detail of the last failing call */
 /* per-ray trig probe for parity tests: out_sin/out_cos [n] with the kernel's trig for `mode` */
+/* parity probe: the kernels' exact constant-divisor quotient (q_fast) next to IEEE division (q_ieee), a[i] / b */
+int32_t ab200_debug_const_div(const float* a, int32_t n, float b, float* q_fast, float* q_ieee, void* stream);
 int32_t ab200_debug_trig(const float* angles, int32_t n, int32_t mode, float* out_sin, float* out_cos, void* stream);
 
 #ifdef __cplusplus

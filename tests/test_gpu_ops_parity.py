@@ -200,3 +200,17 @@ def test_device_trig_accuracy():
         ds = (s.cpu() - torch.sin(x)).abs() / torch.sin(x).abs().clamp_min(1e-30)
         dc = (c.cpu() - torch.cos(x)).abs()
         assert ds.max() <= 1.2e-7 and dc.max() <= 6e-8
+
+
+@pytest.mark.parametrize("b", [8.0, 8.62967, 7.0, 5.41, 6.39, 7.22, 1.0472, 5.229, 3.0, 0.1, 123.456, 1.9999999])
+def test_constant_divisor_quotient_is_ieee_exact(b):
+    """The 3-instruction quotient used for the per-target divisors equals IEEE division bit for bit."""
+    from artist_b200 import ops
+
+    torch.manual_seed(int(b * 1000))
+    n = 1 << 24
+    a = torch.cat([torch.rand(n // 2, device=DEV) * 2 * b - 0.5 * b,            # the range the kernels see
+                   torch.randn(n // 4, device=DEV) * 1e3, torch.randn(n // 4, device=DEV) * 1e-6])
+    qf, qi = ops.debug_const_div(a, b)
+    bad = (qf != qi).sum().item()
+    assert bad == 0, f"{bad} of {a.numel()} quotients differ for b={b}"
