@@ -36,6 +36,7 @@ def _source_digest() -> str:
                 h.update(name.encode())
                 h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(os.environ.get("AB200_NVCC_EXTRA", "").encode())
     return h.hexdigest()
 
 
@@ -49,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if fh.read().strip() == digest:
                 return LIB_PATH
     nvcc = _nvcc()
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("AB200_NVCC_EXTRA", "").split()
     objs = []
     procs = []
     for src in SOURCES:

@@ -44,6 +44,7 @@ class TraceArgs(C.Structure):
         ("scatter_sigma", C.c_float), ("trig_mode", C.c_int32), ("flags", C.c_int32),
         ("flux", c_float_p), ("intercept", c_float_p), ("on_target", c_float_p), ("blocking", c_float_p),
         ("dbg_be", c_float_p), ("dbg_bu", c_float_p), ("dbg_t", c_float_p), ("dbg_lambert", c_float_p),
+        ("stats", C.c_void_p),
     ]
 
 
@@ -105,6 +106,7 @@ EXPORTS = {
     "ab200_error_string": ([C.c_int32], C.c_char_p),
     "ab200_last_error_detail": ([], C.c_char_p),
     "ab200_debug_const_div": ([c_float_p, C.c_int32, C.c_float, c_float_p, c_float_p, C.c_void_p], C.c_int32),
+    "ab200_debug_div_regular": ([c_float_p, c_float_p, C.c_int32, c_float_p, c_float_p, C.c_void_p], C.c_int32),
     "ab200_debug_trig": ([c_float_p, C.c_int32, C.c_int32, c_float_p, c_float_p, C.c_void_p], C.c_int32),
 }
 

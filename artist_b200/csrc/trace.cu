@@ -49,9 +49,22 @@ struct Window {
     int e0, u0, ww, wh;
 };
 
-constexpr int kWindowSampleStride = 4;
-constexpr int kFwdThreadsLarge = 1024;  // one CTA per SM with a ~200 KB bitmap window
-constexpr int kBwdThreadsLarge = 1024;
+constexpr int kWindowSampleStride = 8;
+#ifndef AB200_FWD_THREADS
+#define AB200_FWD_THREADS 1024
+#endif
+#ifndef AB200_BWD_THREADS
+#define AB200_BWD_THREADS 1024
+#endif
+#ifndef AB200_WIN_KB
+#define AB200_WIN_KB 224   // shared-memory bitmap window per CTA in the one-CTA-per-sample mode
+#endif
+#ifndef AB200_RAY_UNROLL
+#define AB200_RAY_UNROLL 1
+#endif
+constexpr int kFwdThreadsLarge = AB200_FWD_THREADS;  // one CTA per SM with a ~200 KB bitmap window
+constexpr int kBwdThreadsLarge = AB200_BWD_THREADS;
+constexpr int kRayUnroll = AB200_RAY_UNROLL;
 
 // ---------------------------------------------------------------------------------------------
 // window placement: bounding box of the undistorted reflections of a subset of the CTA's points,
@@ -67,15 +80,36 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
     const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
     const float inf = __int_as_float(0x7f800000);
     float emin = inf, emax = -inf, umin = inf, umax = -inf, tmax = 0.f, cmin = inf;
-    for (int p = p_begin + tid * kWindowSampleStride; p < p_end; p += THREADS * kWindowSampleStride) {
-        PointCtx pc;
-        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
-        float be, bu, t, cosi;
-        const bool ok = T.planar ? centre_planar(T, pc, be, bu, t, cosi) : centre_cylinder(T, pc, be, bu, t, cosi);
-        if (ok && be == be && bu == bu && fabsf(be) < 1e6f && fabsf(bu) < 1e6f) {
-            emin = fminf(emin, be); emax = fmaxf(emax, be);
-            umin = fminf(umin, bu); umax = fmaxf(umax, bu);
-            tmax = fmaxf(tmax, t);  cmin = fminf(cmin, cosi);
+    {
+        // every kWindowSampleStride-th point; both candidate loads are issued before any math (latency overlap)
+        const int pa = p_begin + tid * kWindowSampleStride, pb = pa + THREADS * kWindowSampleStride;
+        const bool has_a = pa < p_end, has_b = pb < p_end;
+        float4 oa = make_float4(0, 0, 0, 0), na = oa, ob = oa, nb = oa;
+        if (has_a) { oa = __ldg(pts + pa); na = __ldg(nrm + pa); }
+        if (has_b) { ob = __ldg(pts + pb); nb = __ldg(nrm + pb); }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!(k == 0 ? has_a : has_b)) continue;
+            PointCtx pc;
+            make_point(pc, T, i0, i1, i2, k == 0 ? oa : ob, k == 0 ? na : nb);
+            float be, bu, t, cosi;
+            const bool ok = T.planar ? centre_planar(T, pc, be, bu, t, cosi) : centre_cylinder(T, pc, be, bu, t, cosi);
+            if (ok && be == be && bu == bu && fabsf(be) < 1e6f && fabsf(bu) < 1e6f) {
+                emin = fminf(emin, be); emax = fmaxf(emax, be);
+                umin = fminf(umin, bu); umax = fmaxf(umax, bu);
+                tmax = fmaxf(tmax, t);  cmin = fminf(cmin, cosi);
+            }
+        }
+        for (int p = pb + THREADS * kWindowSampleStride; p < p_end; p += THREADS * kWindowSampleStride) {  // very large P only
+            PointCtx pc;
+            make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+            float be, bu, t, cosi;
+            const bool ok = T.planar ? centre_planar(T, pc, be, bu, t, cosi) : centre_cylinder(T, pc, be, bu, t, cosi);
+            if (ok && be == be && bu == bu && fabsf(be) < 1e6f && fabsf(bu) < 1e6f) {
+                emin = fminf(emin, be); emax = fmaxf(emax, be);
+                umin = fminf(umin, bu); umax = fmaxf(umax, bu);
+                tmax = fmaxf(tmax, t);  cmin = fminf(cmin, cosi);
+            }
         }
     }
     emin = warp_min(emin); emax = warp_max(emax); umin = warp_min(umin); umax = warp_max(umax);
@@ -131,11 +165,25 @@ struct FwdCtx {
     float* out_f;        // this sample's [U,E] output row
     int e0, u0, ww, wwm1, whm1;  // window origin, row pitch, (width-1), (height-1); an empty window has wwm1 = whm1 = 0
     int wh;
+    int* fb_box;         // shared: bounding box (output rows/cols) of the taps that took the global path
 };
 
 // The per-ray loop of one CTA, specialised on the target type and on whether the exact constant-divisor quotient
 // may be used, so that the hot loop carries no target-type branch.
-template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool PLANAR, bool FASTDIV>
+// "Irregular" rays are the ones the branch-free fast loops skip: scatter angles beyond the polynomial's range,
+// a grazing ray (|d.n_t| < 1e-18) or a degenerate point (|(c-o).n_t| outside [1e-18, 1e18]) - none of which occur
+// with physical inputs.  A CTA that saw any re-runs the generic loop for just those rays (ONLY_IRREGULAR).
+__device__ __forceinline__ bool point_regular(const PointCtx& pc) {
+    const float n = fabsf(pc.num);
+    return n > 1e-18f && n < 1e18f;
+}
+template <int TRIG>
+__device__ __forceinline__ bool angles_regular(float u, float e) {
+    return TRIG == AB200_TRIG_TABLE ? true : (fmaxf(fabsf(u), fabsf(e)) <= 0.785f);
+}
+__device__ __forceinline__ bool cosine_regular(float a) { return !(a < 0.0f) || (a < -1e-18f && a > -1e18f); }
+
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR>
 __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h, int p_begin,
                                          int p_end, float i0, float i1, float i2, int& cnt_lam_out, int& cnt_int_out,
                                          bool& fell_back_out) {
@@ -165,6 +213,7 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
             scatter(s, pc);
             Hit hit;
             if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
+            if (ONLY_IRREGULAR && point_regular(pc) && angles_regular<TRIG>(d.x, d.y) && cosine_regular(hit.a)) continue;
             // intensities = lambert * (1 - blocked) * (1 - extinction) * reflectivity   (:482-487); lambert * 1 is exact
             const float inten = smul(smul(hit.lam, ome), refl);
             if (DBG) {
@@ -204,6 +253,8 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
                     // per-tap routing: a tap inside the window region must go to shared memory so that window pixels
                     // are owned by shared memory only
                     fell_back = true;
+                    atomicMin(fc.fb_box + 0, U - 2 - sp.iu); atomicMax(fc.fb_box + 1, U - 1 - sp.iu);
+                    atomicMin(fc.fb_box + 2, sp.ie); atomicMax(fc.fb_box + 3, sp.ie + 1);
                     const bool e_in0 = (unsigned)ce < (unsigned)fc.ww, e_in1 = (unsigned)(ce + 1) < (unsigned)fc.ww;
                     const bool u_in0 = (unsigned)cu < (unsigned)fc.wh, u_in1 = (unsigned)(cu + 1) < (unsigned)fc.wh;
                     unsigned* g_hi = out_u + (size_t)(U - 1 - (sp.iu + 1)) * E + sp.ie;
@@ -220,6 +271,117 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
     cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; fell_back_out = fell_back;
 }
 
+// Branch-free fast loop for planar targets: polynomial (or table) trig, range-guarded exact divisions, everything
+// predicated; irregular rays are only counted (n_irregular) and left to the generic loop.
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC>
+__device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h,
+                                                     int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
+                                                     int& cnt_int_out, bool& fell_back_out, int& n_irregular_out) {
+    const int tid = threadIdx.x;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
+    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
+    const float fxs = prm.fx_scale;
+    const float e_lim = (float)E, u_lim = (float)U;
+    int cnt_lam = 0, cnt_int = 0, n_irr = 0;
+    bool fell_back = false;
+
+    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+        PointCtx pc;
+        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        if (!point_regular(pc)) { n_irr += R; continue; }
+        const float2* dp = dist + p;
+        float2 d_next = __ldcs(dp);
+#pragma unroll kRayUnroll
+        for (int r = 0; r < R; ++r) {
+            const float2 d = d_next;
+            dp += P;
+            if (r + 1 < R) d_next = __ldcs(dp);
+            Scatter s;
+            if (TRIG == AB200_TRIG_TABLE) {
+                const float4 t4 = __ldg(trig + (size_t)r * P + p);
+                s.cu = t4.x; s.su = t4.y; s.ce = t4.z; s.se = t4.w;
+            } else {
+                sincos_poly_core(d.x, &s.su, &s.cu);
+                sincos_poly_core(d.y, &s.se, &s.ce);
+            }
+            scatter(s, pc);
+            const float a = sadd(sadd(smul(s.dx, T.n0), smul(s.dy, T.n1)), smul(s.dz, T.n2));
+            if (!(angles_regular<TRIG>(d.x, d.y) && cosine_regular(a))) { ++n_irr; continue; }
+            const bool ff = a < 0.0f;
+            const float t = div_regular(pc.num, a);                       // == __fdiv_rn for regular operands
+            const float X = sadd(pc.o0, smul(s.dx, t));
+            const float Z = sadd(pc.o2, smul(s.dz, t));
+            const float te = ssub(sadd(X, T.half_w), T.c0);
+            const float tu = ssub(sadd(Z, T.half_h), T.c2);
+            const float be0 = smul(const_div(te, T.w, T.rw), T.em1);
+            const float bu0 = smul(const_div(tu, T.h, T.rh), T.um1);
+            const bool valid = ff && (0.0f <= be0) && (be0 <= T.em1) && (0.0f <= bu0) && (bu0 <= T.um1);
+            const float lam = valid ? smul(mag, -a) : 0.0f;
+            const float inten = smul(smul(lam, ome), refl);
+            const float be = ssub(T.em1, valid ? be0 : 0.0f);
+            const float bu = valid ? bu0 : 0.0f;
+            if (DBG) {
+                const size_t q = ((size_t)h * R + r) * P + p;
+                if (prm.a.dbg_be) prm.a.dbg_be[q] = be;
+                if (prm.a.dbg_bu) prm.a.dbg_bu[q] = bu;
+                if (prm.a.dbg_t) prm.a.dbg_t[q] = valid ? t : 0.0f;
+                if (prm.a.dbg_lambert) prm.a.dbg_lambert[q] = lam;
+            }
+            cnt_lam += (lam > 0.0f);
+            cnt_int += (inten > 0.0f);
+            // splat weights (valid rays have 0 <= be <= E-1, 0 <= bu <= U-1)
+            const float fe = truncf(be), fu = truncf(bu);
+            const float fe1 = sadd(fe, 1.0f), fu1 = sadd(fu, 1.0f);
+            const int ie = __float2int_rz(be), iu = __float2int_rz(bu);
+            const bool go = valid && (fe1 < e_lim) && (fu1 < u_lim);
+            const float wle = ssub(fe1, be), wlu = ssub(fu1, bu), whe = ssub(be, fe), whu = ssub(bu, fu);
+            const int ce = ie - fc.e0, cu = iu - fc.u0;
+            const bool fast = ((unsigned)ce < (unsigned)fc.wwm1) && ((unsigned)cu < (unsigned)fc.whm1);
+            if (FP32ACC) {
+                if (go) {
+                    const float v1 = smul(smul(wle, whu), inten), v2 = smul(smul(whe, whu), inten);
+                    const float v3 = smul(smul(whe, wlu), inten), v4 = smul(smul(wle, wlu), inten);
+                    if (fast) {
+                        float* b = fc.win_f + cu * fc.ww + ce;
+                        atomicAdd(b + fc.ww, v1); atomicAdd(b + fc.ww + 1, v2); atomicAdd(b + 1, v3); atomicAdd(b, v4);
+                    } else {
+                        float* row_hi = fc.out_f + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                        float* row_lo = row_hi + E;
+                        atomicAdd(row_hi, v1); atomicAdd(row_hi + 1, v2); atomicAdd(row_lo + 1, v3); atomicAdd(row_lo, v4);
+                    }
+                }
+            } else {
+                const float ahi = fabsf(whu * inten) * fxs, alo = fabsf(wlu * inten) * fxs;
+                const unsigned q1 = __float2uint_rn(wle * ahi), q2 = __float2uint_rn(whe * ahi);
+                const unsigned q3 = __float2uint_rn(whe * alo), q4 = __float2uint_rn(wle * alo);
+                if (go && fast) {
+                    unsigned* b = fc.win_u + cu * fc.ww + ce;
+                    atomicAdd(b + fc.ww, q1); atomicAdd(b + fc.ww + 1, q2); atomicAdd(b + 1, q3); atomicAdd(b, q4);
+                } else if (go) {
+                    fell_back = true;
+                    atomicMin(fc.fb_box + 0, U - 2 - iu); atomicMax(fc.fb_box + 1, U - 1 - iu);
+                    atomicMin(fc.fb_box + 2, ie); atomicMax(fc.fb_box + 3, ie + 1);
+                    const bool e_in0 = (unsigned)ce < (unsigned)fc.ww, e_in1 = (unsigned)(ce + 1) < (unsigned)fc.ww;
+                    const bool u_in0 = (unsigned)cu < (unsigned)fc.wh, u_in1 = (unsigned)(cu + 1) < (unsigned)fc.wh;
+                    unsigned* g_hi = out_u + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                    unsigned* g_lo = g_hi + E;
+                    unsigned* b = fc.win_u + cu * fc.ww + ce;
+                    if (u_in1 && e_in0) atomicAdd(b + fc.ww, q1); else atomicAdd(g_hi, q1);
+                    if (u_in1 && e_in1) atomicAdd(b + fc.ww + 1, q2); else atomicAdd(g_hi + 1, q2);
+                    if (u_in0 && e_in1) atomicAdd(b + 1, q3); else atomicAdd(g_lo + 1, q3);
+                    if (u_in0 && e_in0) atomicAdd(b, q4); else atomicAdd(g_lo, q4);
+                }
+            }
+        }
+    }
+    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; fell_back_out = fell_back; n_irregular_out = n_irr;
+}
+
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_fwd_kernel(const TraceParams prm) {
@@ -231,6 +393,7 @@ trace_fwd_kernel(const TraceParams prm) {
     __shared__ float red[6 * 32];
     __shared__ int cnt_sh[2];
     __shared__ int fallback_sh;
+    __shared__ int fb_box[4];   // output rows / columns touched by global-path taps: row min, row max, col min, col max
 
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
@@ -243,6 +406,7 @@ trace_fwd_kernel(const TraceParams prm) {
     if (tid == 0) {
         load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
         cnt_sh[0] = 0; cnt_sh[1] = 0; fallback_sh = 0;
+        fb_box[0] = 1 << 30; fb_box[1] = -1; fb_box[2] = 1 << 30; fb_box[3] = -1;
     }
     __syncthreads();
     const TargetCtx T = T_sh;
@@ -261,14 +425,23 @@ trace_fwd_kernel(const TraceParams prm) {
     fc.win_u = win_u; fc.win_f = win_f; fc.out_f = out_f;
     fc.e0 = W.e0; fc.u0 = W.u0; fc.ww = W.ww; fc.wh = W.wh;
     fc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; fc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
+    fc.fb_box = fb_box;
 
     int cnt_lam = 0, cnt_int = 0;
     bool fell_back = false;
-    if (T.planar) {
-        if (T.fastdiv) fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, true>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
-        else fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
+    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
+        int n_irr = 0;
+        fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back, n_irr);
+        if (__syncthreads_or(n_irr != 0)) {   // never with physical inputs: the generic loop picks up the skipped rays
+            int c1 = 0, c2 = 0;
+            bool fb = false;
+            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, c1, c2, fb);
+            cnt_lam += c1; cnt_int += c2; fell_back = fell_back || fb;
+        }
+    } else if (T.planar) {
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
     } else {
-        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
     }
 
     // ---- epilogue: counters, window flush -----------------------------------------------------
@@ -279,6 +452,11 @@ trace_fwd_kernel(const TraceParams prm) {
         if (cnt_int) atomicAdd(&cnt_sh[1], cnt_int);
     }
     if (!FP32ACC && fell_back) fallback_sh = 1;
+    if (prm.a.stats && tid == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(prm.a.stats) + 1, (unsigned long long)(W.ww * W.wh));
+        atomicAdd(reinterpret_cast<unsigned long long*>(prm.a.stats) + 2, 1ull);
+    }
+    if (prm.a.stats && fell_back) atomicAdd(reinterpret_cast<unsigned long long*>(prm.a.stats) + 0, 1ull);
     if (!FP32ACC) __threadfence();  // integer REDs of this thread are performed before the barrier
     __syncthreads();
 
@@ -315,10 +493,11 @@ trace_fwd_kernel(const TraceParams prm) {
         }
         if (any_fb) {
             // rare: convert the integer taps that landed outside the window, in place
-            for (int row = warp; row < U; row += nwarps) {
+            const int r_lo = max(fb_box[0], 0), r_hi = min(fb_box[1], U - 1), c_lo = max(fb_box[2], 0), c_hi = min(fb_box[3], E - 1);
+            for (int row = r_lo + warp; row <= r_hi; row += nwarps) {
                 const int iu = U - 1 - row;
                 const bool row_in = (iu >= W.u0) && (iu < W.u0 + W.wh);
-                for (int c = lane; c < E; c += 32) {
+                for (int c = c_lo + lane; c <= c_hi; c += 32) {
                     if (row_in && c >= W.e0 && c < W.e0 + W.ww) continue;
                     const unsigned q = __ldcg(out_u + (size_t)row * E + c);
                     if (q) out_f[(size_t)row * E + c] = __uint2float_rn(q) * inv;
@@ -378,7 +557,7 @@ struct BwdCtx {
     int e0, u0, ww, wwm1, whm1;
 };
 
-template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV>
+template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR>
 __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, int h, int p_begin,
                                          int p_end, float i0, float i1, float i2, float* __restrict__ grad_points,
                                          float* __restrict__ grad_normals) {
@@ -399,6 +578,7 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
         make_point(pc, T, i0, i1, i2, o4, n4);
         float go0 = 0.f, go1 = 0.f, go2 = 0.f;   // planar: grad origin (world); cylindrical: grad origin (cylinder frame)
         float gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;   // grad preferred reflection direction
+        bool touched = false;
         const float2* dp = dist + p;
         float2 d_next = __ldcs(dp);
         for (int r = 0; r < R; ++r) {
@@ -410,10 +590,12 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
             scatter(s, pc);
             Hit hit;
             if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
+            if (ONLY_IRREGULAR && point_regular(pc) && angles_regular<TRIG>(d.x, d.y) && cosine_regular(hit.a)) continue;
             if (!hit.valid) continue;
             Splat sp;
             splat_weights(sp, hit.be, hit.bu, E, U);
             if (!sp.on) continue;
+            touched = true;
             // gather the four gradient taps
             float g1, g2, g3, g4;
             const int ce = sp.ie - bc.e0, cu = sp.iu - bc.u0;
@@ -487,9 +669,114 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
         const float gn0 = -2.0f * (pc.dot * gr0 + grn * i0);
         const float gn1 = -2.0f * (pc.dot * gr1 + grn * i1);
         const float gn2 = -2.0f * (pc.dot * gr2 + grn * i2);
-        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = make_float4(gp0, gp1, gp2, 0.f);
+        float4* gpp = reinterpret_cast<float4*>(grad_points) + (size_t)h * P + p;
+        float4* gnp = reinterpret_cast<float4*>(grad_normals) + (size_t)h * P + p;
+        if (ONLY_IRREGULAR) {   // add to what the fast loop wrote for this point
+            if (touched) {
+                const float4 a4 = *gpp, b4 = *gnp;
+                *gpp = make_float4(a4.x + gp0, a4.y + gp1, a4.z + gp2, 0.f);
+                *gnp = make_float4(b4.x + gn0, b4.y + gn1, b4.z + gn2, 0.f);
+            }
+        } else {
+            *gpp = make_float4(gp0, gp1, gp2, 0.f);
+            *gnp = make_float4(gn0, gn1, gn2, 0.f);
+        }
+    }
+}
+
+// Branch-light fast loop for planar targets (see fwd_rays_planar_fast).
+template <int THREADS, int TRIG>
+__device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, int h,
+                                                     int p_begin, int p_end, float i0, float i1, float i2,
+                                                     float* __restrict__ grad_points, float* __restrict__ grad_normals,
+                                                     int& n_irregular_out) {
+    const int tid = threadIdx.x;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    const float mag = prm.a.ray_magnitude;
+    const float k_or = prm.a.one_minus_extinction * prm.a.reflectivity;
+    const float k_lam = mag * k_or;                         // intensity = k_lam * (-a)
+    const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
+    const float e_lim = (float)E, u_lim = (float)U;
+    int n_irr = 0;
+
+    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+        const float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+        PointCtx pc;
+        make_point(pc, T, i0, i1, i2, o4, n4);
+        float go0 = 0.f, go1 = 0.f, go2 = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
+        if (point_regular(pc)) {
+            const float2* dp = dist + p;
+            float2 d_next = __ldcs(dp);
+#pragma unroll kRayUnroll
+            for (int r = 0; r < R; ++r) {
+                const float2 d = d_next;
+                dp += P;
+                if (r + 1 < R) d_next = __ldcs(dp);
+                Scatter s;
+                if (TRIG == AB200_TRIG_TABLE) {
+                    const float4 t4 = __ldg(trig + (size_t)r * P + p);
+                    s.cu = t4.x; s.su = t4.y; s.ce = t4.z; s.se = t4.w;
+                } else {
+                    sincos_poly_core(d.x, &s.su, &s.cu);
+                    sincos_poly_core(d.y, &s.se, &s.ce);
+                }
+                scatter(s, pc);
+                const float a = sadd(sadd(smul(s.dx, T.n0), smul(s.dy, T.n1)), smul(s.dz, T.n2));
+                if (!(angles_regular<TRIG>(d.x, d.y) && cosine_regular(a))) { ++n_irr; continue; }
+                const float t = div_regular(pc.num, a);
+                const float X = sadd(pc.o0, smul(s.dx, t));
+                const float Z = sadd(pc.o2, smul(s.dz, t));
+                const float te = ssub(sadd(X, T.half_w), T.c0);
+                const float tu = ssub(sadd(Z, T.half_h), T.c2);
+                const float be0 = smul(const_div(te, T.w, T.rw), T.em1);
+                const float bu0 = smul(const_div(tu, T.h, T.rh), T.um1);
+                const bool valid = (a < 0.0f) && (0.0f <= be0) && (be0 <= T.em1) && (0.0f <= bu0) && (bu0 <= T.um1);
+                const float be = ssub(T.em1, be0), bu = bu0;
+                const float fe = truncf(be), fu = truncf(bu);
+                const float fe1 = sadd(fe, 1.0f), fu1 = sadd(fu, 1.0f);
+                if (!(valid && (fe1 < e_lim) && (fu1 < u_lim))) continue;
+                const int ie = __float2int_rz(be), iu = __float2int_rz(bu);
+                const float wle = ssub(fe1, be), wlu = ssub(fu1, bu), whe = ssub(be, fe), whu = ssub(bu, fu);
+                float g1, g2, g3, g4;
+                const int ce = ie - bc.e0, cu = iu - bc.u0;
+                if (((unsigned)ce < (unsigned)bc.wwm1) && ((unsigned)cu < (unsigned)bc.whm1)) {
+                    const float* b = bc.win_g + cu * bc.ww + ce;
+                    g1 = b[bc.ww]; g2 = b[bc.ww + 1]; g3 = b[1]; g4 = b[0];
+                } else {
+                    const float* row_hi = bc.gf + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                    const float* row_lo = row_hi + E;
+                    g1 = __ldg(row_hi); g2 = __ldg(row_hi + 1); g3 = __ldg(row_lo + 1); g4 = __ldg(row_lo);
+                }
+                const float inten = -a * k_lam;
+                const float g_int = whu * fmaf(wle, g1, whe * g2) + wlu * fmaf(whe, g3, wle * g4);
+                const float gX = -k_e * inten * fmaf(whu, g2 - g1, wlu * (g3 - g4));   // d/dX through be = (E-1) - te/w*(E-1)
+                const float gZ = k_u * inten * fmaf(wle, g1 - g4, whe * (g2 - g3));
+                const float gt = fmaf(gX, s.dx, gZ * s.dz);
+                const float gnum = __fdividef(gt, a);                                   // t = num / a
+                const float g_a = fmaf(-gnum, t, -g_int * k_lam);                       // lam = mag * (-a)
+                go0 += fmaf(-gnum, T.n0, gX);
+                go1 = fmaf(-gnum, T.n1, go1);
+                go2 += fmaf(-gnum, T.n2, gZ);
+                const float gdx = fmaf(gX, t, g_a * T.n0), gdy = g_a * T.n1, gdz = fmaf(gZ, t, g_a * T.n2);
+                gr0 += fmaf(s.cu, gdx, fmaf(s.m10, gdy, s.m20 * gdz));
+                gr1 += fmaf(-s.su, gdx, fmaf(s.m11, gdy, s.m21 * gdz));
+                gr2 += fmaf(-s.se, gdy, s.ce * gdz);
+            }
+        } else {
+            n_irr += R;
+        }
+        const float grn = gr0 * n4.x + gr1 * n4.y + gr2 * n4.z;
+        const float gn0 = -2.0f * (pc.dot * gr0 + grn * i0);
+        const float gn1 = -2.0f * (pc.dot * gr1 + grn * i1);
+        const float gn2 = -2.0f * (pc.dot * gr2 + grn * i2);
+        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = make_float4(go0, go1, go2, 0.f);
         reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = make_float4(gn0, gn1, gn2, 0.f);
     }
+    n_irregular_out = n_irr;
 }
 
 template <int THREADS, int TRIG>
@@ -530,11 +817,15 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     BwdCtx bc;
     bc.win_g = win_g; bc.gf = gf; bc.e0 = W.e0; bc.u0 = W.u0; bc.ww = W.ww;
     bc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; bc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
-    if (T.planar) {
-        if (T.fastdiv) bwd_rays<THREADS, TRIG, true, true>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
-        else bwd_rays<THREADS, TRIG, true, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
+        int n_irr = 0;
+        bwd_rays_planar_fast<THREADS, TRIG>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, n_irr);
+        if (__syncthreads_or(n_irr != 0))   // never with physical inputs (each thread re-reads only its own points)
+            bwd_rays<THREADS, TRIG, true, false, true>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+    } else if (T.planar) {
+        bwd_rays<THREADS, TRIG, true, false, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
     } else {
-        bwd_rays<THREADS, TRIG, false, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+        bwd_rays<THREADS, TRIG, false, false, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
     }
 }
 
@@ -565,7 +856,7 @@ static LaunchPlan make_plan(int n_local, int n_points, int max_threads_large) {
     LaunchPlan pl;
     const int sms = sm_count();
     if (n_local >= 2 * sms) {
-        pl.threads = max_threads_large; pl.split = 1; pl.smem_bytes = 200 * 1024;
+        pl.threads = max_threads_large; pl.split = 1; pl.smem_bytes = AB200_WIN_KB * 1024;
     } else {
         pl.threads = 512;
         const int want = (4 * sms + (n_local > 0 ? n_local : 1) - 1) / (n_local > 0 ? n_local : 1);
@@ -740,6 +1031,24 @@ __global__ void debug_const_div_kernel(const float* a, int n, float b, float* q_
     q_ieee[i] = __fdiv_rn(a[i], b);
 }
 }  // namespace ab200
+
+namespace ab200 {
+__global__ void debug_div_regular_kernel(const float* a, const float* b, int n, float* q_fast, float* q_ieee) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    q_fast[i] = div_regular(a[i], b[i]);
+    q_ieee[i] = __fdiv_rn(a[i], b[i]);
+}
+}  // namespace ab200
+
+extern "C" int32_t ab200_debug_div_regular(const float* a, const float* b, int32_t n, float* q_fast, float* q_ieee, void* stream) {
+    AB200_REQUIRE(a && b && q_fast && q_ieee && n >= 0, AB200_EINVAL, "bad arguments");
+    if (n == 0) return AB200_OK;
+    debug_div_regular_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, n, q_fast, q_ieee);
+    note_launch();
+    AB200_CUDA_TRY(cudaGetLastError());
+    return AB200_OK;
+}
 
 extern "C" int32_t ab200_debug_const_div(const float* a, int32_t n, float b, float* q_fast, float* q_ieee, void* stream) {
     AB200_REQUIRE(a && q_fast && q_ieee && n >= 0, AB200_EINVAL, "bad arguments");

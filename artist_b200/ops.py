@@ -128,7 +128,11 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
     a.flux, a.intercept, a.on_target, a.blocking = _p(flux), _p(intercept), _p(on_target), _p(blocking)
     if dbg is not None:
         a.dbg_be, a.dbg_bu, a.dbg_t, a.dbg_lambert = (_p(d) for d in dbg)
+    a.stats = _p(trace_stats)
     return a
+
+
+trace_stats: torch.Tensor | None = None  # set to a zeroed int64[4] CUDA tensor to collect window diagnostics
 
 
 class _TraceFn(torch.autograd.Function):
@@ -451,4 +455,11 @@ def debug_const_div(a: torch.Tensor, b: float):
     a = _f32(a, "a").reshape(-1)
     qf, qi = torch.empty_like(a), torch.empty_like(a)
     _lib.call("ab200_debug_const_div", _p(a), a.numel(), float(b), _p(qf), _p(qi), _stream())
+    return qf, qi
+
+
+def debug_div_regular(a: torch.Tensor, b: torch.Tensor):
+    a, b = _f32(a, "a").reshape(-1), _f32(b, "b").reshape(-1)
+    qf, qi = torch.empty_like(a), torch.empty_like(a)
+    _lib.call("ab200_debug_div_regular", _p(a), _p(b), a.numel(), _p(qf), _p(qi), _stream())
     return qf, qi

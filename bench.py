@@ -35,6 +35,7 @@ CONTROL_POINTS = (10, 10)
 RAYS = 10                    # rays per surface point
 RES = (256, 256)             # bitmap E x U
 CPU_SAMPLE_HELIOSTATS = 48   # bounded CPU sample of the same per-heliostat workload
+SURFACE_BUMP = float(os.environ.get("AB200_BENCH_BUMP", "1e-4"))  # control-point height noise (m): 0.1 mm ~ 0.6 mrad slope error
 
 
 def bytes_per_ray(r: int, p: int, ue: int) -> tuple[float, float]:
@@ -119,7 +120,7 @@ class Workload:
         self.dev, self.n, self.world = dev, n, world
         self.scenario, self.group = build_synthetic_scenario(
             n, number_of_rays=RAYS, points_per_facet=POINTS_PER_FACET, control_points=CONTROL_POINTS,
-            surface_bump=0.0005, seed=rank, device=dev)
+            surface_bump=SURFACE_BUMP, seed=rank, device=dev)
         g = self.group
         self.mask, self.tidx, self.inc = self.scenario.index_mapping(g)
         self.inc = self.inc.contiguous()
@@ -214,7 +215,7 @@ def cpu_oracle_step_factory(n: int, threads: int):
     from oracle import artist_oracle as O
 
     torch.set_num_threads(threads)
-    ft = synthetic_field_tensors(n, control_points=CONTROL_POINTS, surface_bump=0.0005, seed=0)
+    ft = synthetic_field_tensors(n, control_points=CONTROL_POINTS, surface_bump=SURFACE_BUMP, seed=0)
     tg = O.targets_from_field_tensors(ft)
     ev = O.nurbs_evaluation_grid(*POINTS_PER_FACET)[None, None].expand(n, 4, -1, -1)
     tidx = torch.zeros(n, dtype=torch.int32)

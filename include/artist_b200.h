@@ -109,6 +109,8 @@ typedef struct ab200_trace_args {
     float* dbg_bu;           /* [N,R,P] */
     float* dbg_t;            /* [N,R,P] */
     float* dbg_lambert;      /* [N,R,P] */
+    int64_t* stats;          /* optional diagnostics (NULL to skip), accumulated: [0] threads that used the global fallback
+                                path, [1] sum of window cells, [2] CTAs */
 } ab200_trace_args;
 
 int32_t ab200_trace_fwd(const ab200_trace_args* args, void* stream);
@@ -262,6 +264,8 @@ const char* ab200_last_error_detail(void); /* thread-local detail of the last fa
 /* per-ray trig probe for parity tests: out_sin/out_cos [n] with the kernel's trig for `mode` */
 /* parity probe: the kernels' exact constant-divisor quotient (q_fast) next to IEEE division (q_ieee), a[i] / b */
 int32_t ab200_debug_const_div(const float* a, int32_t n, float b, float* q_fast, float* q_ieee, void* stream);
+/* parity probe: the range-guarded division of the fast ray loops (q_fast) next to IEEE division, a[i] / b[i] */
+int32_t ab200_debug_div_regular(const float* a, const float* b, int32_t n, float* q_fast, float* q_ieee, void* stream);
 int32_t ab200_debug_trig(const float* angles, int32_t n, int32_t mode, float* out_sin, float* out_cos, void* stream);
 
 #ifdef __cplusplus

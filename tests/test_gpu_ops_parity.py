@@ -214,3 +214,19 @@ def test_constant_divisor_quotient_is_ieee_exact(b):
     qf, qi = ops.debug_const_div(a, b)
     bad = (qf != qi).sum().item()
     assert bad == 0, f"{bad} of {a.numel()} quotients differ for b={b}"
+
+
+def test_range_guarded_division_is_ieee_exact():
+    """div_regular (MUFU.RCP + 5 FFMA, no range check) == __fdiv_rn on the domain the fast ray loops guard:
+    |numerator| and |denominator| in [1e-18, 1e18]."""
+    from artist_b200 import ops
+
+    torch.manual_seed(0)
+    n = 1 << 25
+    num = torch.randn(n, device=DEV) * 80.0                                  # (c - o) . n_t, tens of metres
+    den = -(torch.rand(n, device=DEV) * 0.999 + 1e-3)                        # d . n_t in (-1, -1e-3)
+    num[: n // 8] = torch.exp(torch.empty(n // 8, device=DEV).uniform_(-41.0, 41.0)) * torch.sign(num[: n // 8])
+    den[: n // 8] = -torch.exp(torch.empty(n // 8, device=DEV).uniform_(-41.0, 41.0))
+    qf, qi = ops.debug_div_regular(num, den)
+    bad = (qf != qi).sum().item()
+    assert bad == 0, f"{bad} of {n} quotients differ"

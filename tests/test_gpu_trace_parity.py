@@ -153,3 +153,33 @@ def test_backward_matches_oracle_autograd(pattern):
             ref_err = (g32[~planar].double() - g64[~planar]).abs().max() / scale64
             err = (got[~planar].double() - g64[~planar]).abs().max() / scale64
             assert err <= max(2 * ref_err, 1e-3), f"cylinder grad {name}: {err:.3e} (fp32 oracle itself {ref_err:.3e})"
+
+
+def test_irregular_rays_take_the_generic_path():
+    """Scatter angles beyond the polynomial's range (never produced by a physical sun shape) are skipped by the
+    branch-free fast loops and re-traced by the generic loop: forward and backward still match the oracle."""
+    from artist_b200 import ops
+
+    case = cases.make_case(n=3, points_per_facet=(10, 10), rays=5)
+    du, de = case["dist_u"].clone(), case["dist_e"].clone()
+    torch.manual_seed(3)
+    pick = torch.rand_like(du) < 0.03
+    du[pick] = 0.8 + 0.5 * torch.rand(int(pick.sum()))       # > pi/4
+    pick2 = torch.rand_like(de) < 0.03
+    de[pick2] = -(0.0005 + 0.0005 * torch.rand(int(pick2.sum())))   # regular values, other rays irregular
+    case["dist_u"], case["dist_e"] = du, de
+    res = (64, 64)
+    wgt = torch.rand(3, res[1], res[0])
+    ref, gp, gn = cases.oracle_trace_with_grads(case, res, wgt)
+    dev = torch.device("cuda:0")
+    pc = case["points"].to(dev).requires_grad_(True)
+    nc = case["normals"].to(dev).requires_grad_(True)
+    opt = ops.TraceOptions(res_e=res[0], res_u=res[1], trig_mode=2, scatter_sigma=2.09e-3)
+    flux, ic, ot, _ = ops.trace(pc, nc, case["incident"].to(dev), ops.pack_distortions(du.to(dev), de.to(dev)),
+                                case["target_idx"].to(dev), _dev_targets(case["targets"], dev), opt)
+    assert (flux.detach().cpu() - ref).abs().max() <= 1e-4 * ref.max()
+    rref = O.trace_rays(case["points"], case["normals"], case["incident"], du, de, case["target_idx"], case["targets"], res)
+    assert (ic.cpu() - rref[1]).abs().max() <= 2e-3 and (ot.cpu() - rref[2]).abs().max() <= 2e-3
+    (flux * wgt.to(dev)).sum().backward()
+    assert (pc.grad.cpu() - gp).abs().max() <= 5e-4 * gp.abs().max()
+    assert (nc.grad.cpu() - gn).abs().max() <= 5e-4 * gn.abs().max()
