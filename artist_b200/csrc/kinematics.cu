@@ -294,60 +294,59 @@ __device__ inline void normalize3(float* v, float eps) {
     v[0] /= n; v[1] /= n; v[2] /= n;
 }
 
-// The alignment loop proper.  State per heliostat (motor positions, last loss) is kept in global
-// scratch so one CTA can serve any n; the all-heliostats convergence rule needs a CTA-wide vote
-// per iteration, which is why this runs as a single CTA (n is a few thousand at most).
-__global__ void __launch_bounds__(1024) kinematics_align_loop_kernel(const ab200_kinematics_args k,
-                                                                     const float* __restrict__ incident,
-                                                                     const float* __restrict__ aim, int max_iter, float min_eps,
-                                                                     float* __restrict__ out, float* __restrict__ motor_io,
-                                                                     float* __restrict__ last_loss /* [n] scratch */) {
-    __shared__ int any_open;
-    for (int i = threadIdx.x; i < k.n; i += blockDim.x) { motor_io[(size_t)i * 2] = 0.f; motor_io[(size_t)i * 2 + 1] = 0.f; }
-    __syncthreads();
-    for (int it = 0; it < max_iter; ++it) {
-        if (threadIdx.x == 0) any_open = 0;
-        __syncthreads();
-        // phase 1: forward kinematics, loss, convergence vote
-        for (int i = threadIdx.x; i < k.n; i += blockDim.x) {
-            float th[2];
-            joint_angles(k, i, motor_io, th, nullptr, nullptr, nullptr);
-            M4 F[kFactors];
-            build_factors(F, k, i, th);
-            const M4 o = raw_orientation(F);
-            const M4 fin = m4_mul(o, F[10]);
-            for (int q = 0; q < 16; ++q) out[(size_t)i * 16 + q] = fin.m[q];
-            const float cn[4] = {-o.m[1], -o.m[5], -o.m[9], -o.m[13]};
-            float wr[3] = {aim[(size_t)i * 4] - o.m[3], aim[(size_t)i * 4 + 1] - o.m[7], aim[(size_t)i * 4 + 2] - o.m[11]};
-            normalize3(wr, 1e-8f);
-            float wn[3] = {-incident[(size_t)i * 4] + wr[0], -incident[(size_t)i * 4 + 1] + wr[1], -incident[(size_t)i * 4 + 2] + wr[2]};
-            normalize3(wn, 1e-8f);
-            const float loss = (fabsf(wn[0] - cn[0]) + fabsf(wn[1] - cn[1]) + fabsf(wn[2] - cn[2]) + fabsf(cn[3])) / 4.0f;
-            if (it == 0 || !(fabsf(last_loss[i] - loss) <= min_eps)) any_open = 1;
-            last_loss[i] = loss;
-        }
-        __syncthreads();
-        if (it > 0 && any_open == 0) break;  // torch.all(eps <= min_eps): stop, keep this iteration's orientations
-        // phase 2: inverse kinematics towards the desired normal
-        for (int i = threadIdx.x; i < k.n; i += blockDim.x) {
-            // recompute the desired normal from the orientation written in phase 1 (raw = fin * offset^-1 is
-            // avoided by recomputing the forward chain; n is tiny)
-            float th[2];
-            joint_angles(k, i, motor_io, th, nullptr, nullptr, nullptr);
-            M4 F[kFactors];
-            build_factors(F, k, i, th);
-            const M4 o = raw_orientation(F);
-            float wr[3] = {aim[(size_t)i * 4] - o.m[3], aim[(size_t)i * 4 + 1] - o.m[7], aim[(size_t)i * 4 + 2] - o.m[11]};
-            normalize3(wr, 1e-8f);
-            float wn[3] = {-incident[(size_t)i * 4] + wr[0], -incident[(size_t)i * 4 + 1] + wr[1], -incident[(size_t)i * 4 + 2] + wr[2]};
-            normalize3(wn, 1e-8f);
-            float mo[2];
-            motor_from_normal(k, i, wn, mo);
-            motor_io[(size_t)i * 2] = mo[0];
-            motor_io[(size_t)i * 2 + 1] = mo[1];
-        }
-        __syncthreads();
+// The alignment loop: per iteration two small kernels (forward kinematics + convergence vote, then inverse
+// kinematics), one thread per heliostat.  The reference stops when ALL heliostats converged
+// (kinematics_rigid_body.py:621-625); the vote lives in device memory (`flags`), so there is no host sync:
+// later launches simply return once `done` is set.
+//   scratch layout (floats): [0,n) last loss | [n,4n) desired normal | then 8 ints: open[0..5], done
+struct AlignFlags {
+    int open[6];
+    int done;
+    int pad;
+};
+
+__global__ void kin_align_forward_kernel(const ab200_kinematics_args k, const float* __restrict__ incident,
+                                         const float* __restrict__ aim, int it, float min_eps, float* __restrict__ out,
+                                         float* __restrict__ motor_io, float* __restrict__ scratch) {
+    AlignFlags* fl = reinterpret_cast<AlignFlags*>(scratch + (size_t)4 * k.n);
+    if (fl->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k.n) return;
+    if (it == 0) { motor_io[(size_t)i * 2] = 0.f; motor_io[(size_t)i * 2 + 1] = 0.f; }
+    float th[2];
+    joint_angles(k, i, motor_io, th, nullptr, nullptr, nullptr);
+    M4 F[kFactors];
+    build_factors(F, k, i, th);
+    const M4 o = raw_orientation(F);
+    const M4 fin = m4_mul(o, F[10]);
+    for (int q = 0; q < 16; ++q) out[(size_t)i * 16 + q] = fin.m[q];
+    const float cn[4] = {-o.m[1], -o.m[5], -o.m[9], -o.m[13]};   // O (0,-1,0,0)
+    float wr[3] = {aim[(size_t)i * 4] - o.m[3], aim[(size_t)i * 4 + 1] - o.m[7], aim[(size_t)i * 4 + 2] - o.m[11]};
+    normalize3(wr, 1e-8f);
+    float wn[3] = {-incident[(size_t)i * 4] + wr[0], -incident[(size_t)i * 4 + 1] + wr[1], -incident[(size_t)i * 4 + 2] + wr[2]};
+    normalize3(wn, 1e-8f);
+    const float loss = (fabsf(wn[0] - cn[0]) + fabsf(wn[1] - cn[1]) + fabsf(wn[2] - cn[2]) + fabsf(cn[3])) / 4.0f;
+    if (it == 0 || !(fabsf(scratch[i] - loss) <= min_eps)) fl->open[it] = 1;   // benign race: everybody writes 1
+    scratch[i] = loss;
+    scratch[(size_t)k.n + 3 * i] = wn[0]; scratch[(size_t)k.n + 3 * i + 1] = wn[1]; scratch[(size_t)k.n + 3 * i + 2] = wn[2];
+}
+
+__global__ void kin_align_inverse_kernel(const ab200_kinematics_args k, int it, float* __restrict__ motor_io,
+                                         float* __restrict__ scratch) {
+    AlignFlags* fl = reinterpret_cast<AlignFlags*>(scratch + (size_t)4 * k.n);
+    if (fl->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it > 0 && fl->open[it] == 0) {   // torch.all(eps <= min_eps): stop, keep this iteration's orientations
+        __syncthreads();                 // every thread of the block has read the vote before it is overwritten
+        if (i == 0) fl->done = 1;
+        return;
     }
+    if (i >= k.n) return;
+    const float wn[3] = {scratch[(size_t)k.n + 3 * i], scratch[(size_t)k.n + 3 * i + 1], scratch[(size_t)k.n + 3 * i + 2]};
+    float mo[2];
+    motor_from_normal(k, i, wn, mo);
+    motor_io[(size_t)i * 2] = mo[0];
+    motor_io[(size_t)i * 2 + 1] = mo[1];
 }
 
 // ---- apply orientation to the surface (align) --------------------------------------------------
@@ -513,9 +512,15 @@ extern "C" int32_t ab200_kinematics_align_incident(const ab200_kinematics_args* 
     AB200_REQUIRE(incident && aim && orientations && motor_positions && scratch, AB200_EINVAL, "NULL pointer");
     AB200_REQUIRE(max_iterations >= 1, AB200_EINVAL, "max_iterations < 1");
     if (k->n == 0) return AB200_OK;
-    kinematics_align_loop_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(*k, incident, aim, max_iterations, min_eps,
-                                                                                    orientations, motor_positions, scratch);
-    note_launch();
+    AB200_REQUIRE(max_iterations <= 6, AB200_ELIMIT, "max_iterations > 6");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    AB200_CUDA_TRY(cudaMemsetAsync(scratch + (size_t)4 * k->n, 0, sizeof(AlignFlags), st));
+    const int blocks = (k->n + 63) / 64;
+    for (int it = 0; it < max_iterations; ++it) {
+        kin_align_forward_kernel<<<blocks, 64, 0, st>>>(*k, incident, aim, it, min_eps, orientations, motor_positions, scratch);
+        kin_align_inverse_kernel<<<blocks, 64, 0, st>>>(*k, it, motor_positions, scratch);
+        note_launch(2);
+    }
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }

@@ -392,7 +392,7 @@ def kinematics_align_incident(incident, aim_points, rot_dev, trans_dev, act_opt,
         n = incident.shape[0]
         out = torch.empty(n, 4, 4, device=incident.device)
         motor = torch.empty(n, 2, device=incident.device)
-        scratch = torch.empty(max(n, 1), device=incident.device)
+        scratch = torch.empty(4 * n + 8, device=incident.device)
         k = _kin_args(positions, trans_dev, rot_dev, act_non_opt, act_opt_c, offset, linear)
         _lib.call("ab200_kinematics_align_incident", C.byref(k), _p(incident), _p(aim_points), int(max_iterations),
                   float(min_eps), _p(out), _p(motor), _p(scratch), _stream())

@@ -212,11 +212,11 @@ int32_t ab200_kinematics_bwd(const ab200_kinematics_args* args, const float* mot
 
 /* incident_ray_directions_to_orientations (:540-634): writes orientations [n,4,4] and the final
  * motor positions [n,2].  The reference stops iterating when ALL heliostats converged; the same
- * batch-wide rule is applied on the device (no host sync). */
+ * batch-wide rule is applied on the device (no host sync); max_iterations <= 6. */
 int32_t ab200_kinematics_align_incident(const ab200_kinematics_args* args, const float* incident /* [n,4] */,
                                         const float* aim_points /* [n,4] */, int32_t max_iterations,
                                         float min_eps, float* orientations, float* motor_positions,
-                                        float* scratch /* [n] floats (last-iteration loss) */, void* stream);
+                                        float* scratch /* [4n + 8] floats of working storage */, void* stream);
 
 /*
  * ab200_align_fwd / _bwd - HeliostatGroupRigidBody.align_surfaces_with_* tail
