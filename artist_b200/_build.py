@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libartist_b200.so")
-SOURCES = ["trace.cu", "nurbs.cu", "kinematics.cu"]
+SOURCES = ["trace.cu", "nurbs.cu", "kinematics.cu", "blocking.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

@@ -29,8 +29,9 @@ class Targets(C.Structure):
 
 class Blockers(C.Structure):
     _fields_ = [
-        ("n_blockers", C.c_int32), ("corners", c_float_p), ("spans", c_float_p), ("normals", c_float_p),
-        ("sample_to_blocker", c_int_p), ("softness", C.c_float), ("epsilon", C.c_float),
+        ("n_blockers", C.c_int32), ("max_candidates", C.c_int32), ("prims", c_float_p), ("cand_idx", c_int_p),
+        ("cand_count", c_int_p), ("softness", C.c_float), ("alpha", C.c_float), ("ray_origin_offset", C.c_float),
+        ("epsilon", C.c_float), ("cull_angle", C.c_float),
     ]
 
 
@@ -50,7 +51,7 @@ class TraceArgs(C.Structure):
 
 class TraceBwdArgs(C.Structure):
     _fields_ = [("fwd", TraceArgs), ("grad_flux", c_float_p), ("grad_flux_stride", C.c_int64),
-                ("grad_points", c_float_p), ("grad_normals", c_float_p)]
+                ("grad_points", c_float_p), ("grad_normals", c_float_p), ("grad_prims", c_float_p)]
 
 
 class NurbsArgs(C.Structure):
@@ -101,6 +102,9 @@ EXPORTS = {
     "ab200_align_bwd": ([c_float_p, c_float_p, c_float_p, c_int_p, C.c_int32, C.c_int32, c_float_p, c_float_p,
                          c_float_p, c_float_p, c_float_p, C.c_void_p], C.c_int32),
     "ab200_trace_host": ([C.POINTER(HostTraceArgs), C.c_void_p], C.c_int32),
+    "ab200_blocking_pack": ([c_float_p, c_float_p, c_float_p, C.c_int32, C.c_float, c_float_p, C.c_void_p], C.c_int32),
+    "ab200_blocking_candidates": ([c_float_p, C.c_int32, c_int_p, c_float_p, c_float_p, C.c_int32, C.c_float, C.c_int32,
+                                   c_int_p, c_int_p, c_int_p, C.c_void_p], C.c_int32),
     "ab200_abi_version": ([], C.c_int32),
     "ab200_kernel_launch_count": ([], C.c_int64),
     "ab200_error_string": ([C.c_int32], C.c_char_p),

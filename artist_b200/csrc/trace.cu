@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <cstring>
 #include "trace_device.cuh"
+#include "blocking_device.cuh"
 
 namespace ab200 {
 
@@ -166,6 +167,9 @@ struct FwdCtx {
     int e0, u0, ww, wwm1, whm1;  // window origin, row pitch, (width-1), (height-1); an empty window has wwm1 = whm1 = 0
     int wh;
     int* fb_box;         // shared: bounding box (output rows/cols) of the taps that took the global path
+    const BlockPrim* blk; // shared: candidate blocking primitives of this sample
+    int n_blk;
+    BlockParams bp;
 };
 
 // The per-ray loop of one CTA, specialised on the target type and on whether the exact constant-divisor quotient
@@ -183,10 +187,10 @@ __device__ __forceinline__ bool angles_regular(float u, float e) {
 }
 __device__ __forceinline__ bool cosine_regular(float a) { return !(a < 0.0f) || (a < -1e-18f && a > -1e18f); }
 
-template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR>
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR, bool BLK>
 __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h, int p_begin,
                                          int p_end, float i0, float i1, float i2, int& cnt_lam_out, int& cnt_int_out,
-                                         bool& fell_back_out) {
+                                         int& cnt_blk_out, bool& fell_back_out) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
     const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
@@ -196,12 +200,13 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
     unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
     const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
     const float fxs = prm.fx_scale;
-    int cnt_lam = 0, cnt_int = 0;
+    int cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
     bool fell_back = false;
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
         PointCtx pc;
         make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         const float2* dp = dist + p;
         float2 d_next = __ldcs(dp);
         for (int r = 0; r < R; ++r) {
@@ -214,8 +219,13 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
             Hit hit;
             if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
             if (ONLY_IRREGULAR && point_regular(pc) && angles_regular<TRIG>(d.x, d.y) && cosine_regular(hit.a)) continue;
+            float blocked = 0.0f;
+            if (BLK) {
+                if (bmask) blocked = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                cnt_blk += (blocked < 1e-3f);
+            }
             // intensities = lambert * (1 - blocked) * (1 - extinction) * reflectivity   (:482-487); lambert * 1 is exact
-            const float inten = smul(smul(hit.lam, ome), refl);
+            const float inten = BLK ? smul(smul(smul(hit.lam, ssub(1.0f, blocked)), ome), refl) : smul(smul(hit.lam, ome), refl);
             if (DBG) {
                 const size_t q = ((size_t)h * R + r) * P + p;
                 if (prm.a.dbg_be) prm.a.dbg_be[q] = hit.be;
@@ -268,15 +278,16 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
             }
         }
     }
-    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; fell_back_out = fell_back;
+    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; cnt_blk_out = cnt_blk; fell_back_out = fell_back;
 }
 
 // Branch-free fast loop for planar targets: polynomial (or table) trig, range-guarded exact divisions, everything
 // predicated; irregular rays are only counted (n_irregular) and left to the generic loop.
-template <int THREADS, int TRIG, bool DBG, bool FP32ACC>
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
 __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h,
                                                      int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
-                                                     int& cnt_int_out, bool& fell_back_out, int& n_irregular_out) {
+                                                     int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
+                                                     int& n_irregular_out) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
     const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
@@ -287,13 +298,14 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
     const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
     const float fxs = prm.fx_scale;
     const float e_lim = (float)E, u_lim = (float)U;
-    int cnt_lam = 0, cnt_int = 0, n_irr = 0;
+    int cnt_lam = 0, cnt_int = 0, cnt_blk = 0, n_irr = 0;
     bool fell_back = false;
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
         PointCtx pc;
         make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
         if (!point_regular(pc)) { n_irr += R; continue; }
+        const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         const float2* dp = dist + p;
         float2 d_next = __ldcs(dp);
 #pragma unroll kRayUnroll
@@ -322,7 +334,12 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
             const float bu0 = smul(const_div(tu, T.h, T.rh), T.um1);
             const bool valid = ff && (0.0f <= be0) && (be0 <= T.em1) && (0.0f <= bu0) && (bu0 <= T.um1);
             const float lam = valid ? smul(mag, -a) : 0.0f;
-            const float inten = smul(smul(lam, ome), refl);
+            float blocked = 0.0f;
+            if (BLK) {
+                if (bmask) blocked = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                cnt_blk += (blocked < 1e-3f);
+            }
+            const float inten = BLK ? smul(smul(smul(lam, ssub(1.0f, blocked)), ome), refl) : smul(smul(lam, ome), refl);
             const float be = ssub(T.em1, valid ? be0 : 0.0f);
             const float bu = valid ? bu0 : 0.0f;
             if (DBG) {
@@ -379,10 +396,10 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
             }
         }
     }
-    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; fell_back_out = fell_back; n_irregular_out = n_irr;
+    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; cnt_blk_out = cnt_blk; fell_back_out = fell_back; n_irregular_out = n_irr;
 }
 
-template <int THREADS, int TRIG, bool DBG, bool FP32ACC>
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_fwd_kernel(const TraceParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -391,9 +408,10 @@ trace_fwd_kernel(const TraceParams prm) {
     __shared__ TargetCtx T_sh;
     __shared__ Window win_sh;
     __shared__ float red[6 * 32];
-    __shared__ int cnt_sh[2];
+    __shared__ int cnt_sh[3];
     __shared__ int fallback_sh;
-    __shared__ int fb_box[4];   // output rows / columns touched by global-path taps: row min, row max, col min, col max
+    __shared__ int fb_box[4];
+    __shared__ BlockPrim blk_sh[kMaxBlockCandidates];   // output rows / columns touched by global-path taps: row min, row max, col min, col max
 
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
@@ -405,7 +423,7 @@ trace_fwd_kernel(const TraceParams prm) {
 
     if (tid == 0) {
         load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
-        cnt_sh[0] = 0; cnt_sh[1] = 0; fallback_sh = 0;
+        cnt_sh[0] = 0; cnt_sh[1] = 0; cnt_sh[2] = 0; fallback_sh = 0;
         fb_box[0] = 1 << 30; fb_box[1] = -1; fb_box[2] = 1 << 30; fb_box[3] = -1;
     }
     __syncthreads();
@@ -426,30 +444,43 @@ trace_fwd_kernel(const TraceParams prm) {
     fc.e0 = W.e0; fc.u0 = W.u0; fc.ww = W.ww; fc.wh = W.wh;
     fc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; fc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
     fc.fb_box = fb_box;
+    fc.blk = blk_sh;
+    fc.n_blk = 0;
+    if (BLK && prm.a.blockers.n_blockers > 0) {
+        const ab200_blockers& B = prm.a.blockers;
+        fc.n_blk = min(B.cand_count[h], kMaxBlockCandidates);
+        fc.bp.softness = B.softness; fc.bp.alpha = B.alpha; fc.bp.offset = B.ray_origin_offset; fc.bp.epsilon = B.epsilon;
+        fc.bp.cull_angle = B.cull_angle;
+        for (int i = tid; i < fc.n_blk * 16; i += THREADS)
+            reinterpret_cast<float*>(blk_sh)[i] = B.prims[(size_t)B.cand_idx[(size_t)h * B.max_candidates + i / 16] * 16 + (i % 16)];
+        __syncthreads();
+    }
 
-    int cnt_lam = 0, cnt_int = 0;
+    int cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
     bool fell_back = false;
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
-        fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back, n_irr);
+        fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
         if (__syncthreads_or(n_irr != 0)) {   // never with physical inputs: the generic loop picks up the skipped rays
-            int c1 = 0, c2 = 0;
+            int c1 = 0, c2 = 0, c3 = 0;
             bool fb = false;
-            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, c1, c2, fb);
-            cnt_lam += c1; cnt_int += c2; fell_back = fell_back || fb;
+            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb);
+            cnt_lam += c1; cnt_int += c2; cnt_blk += c3; fell_back = fell_back || fb;
         }
     } else if (T.planar) {
-        fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
     } else {
-        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, fell_back);
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
     }
 
     // ---- epilogue: counters, window flush -----------------------------------------------------
     cnt_lam = warp_sum(cnt_lam);
     cnt_int = warp_sum(cnt_int);
+    cnt_blk = warp_sum(cnt_blk);
     if ((tid & 31) == 0) {
         if (cnt_lam) atomicAdd(&cnt_sh[0], cnt_lam);
         if (cnt_int) atomicAdd(&cnt_sh[1], cnt_int);
+        if (cnt_blk) atomicAdd(&cnt_sh[2], cnt_blk);
     }
     if (!FP32ACC && fell_back) fallback_sh = 1;
     if (prm.a.stats && tid == 0) {
@@ -466,10 +497,11 @@ trace_fwd_kernel(const TraceParams prm) {
             const float rp = (float)(R * P);
             prm.a.on_target[h] = sdiv((float)cnt_sh[0], rp);
             prm.a.intercept[h] = sdiv((float)cnt_sh[1], rp);
-            prm.a.blocking[h] = 1.0f;  // (blocked < 1e-3).sum() / (R*P) with blocked == 0
+            prm.a.blocking[h] = BLK ? sdiv((float)cnt_sh[2], rp) : 1.0f;  // (blocked < 1e-3).sum() / (R*P)
         } else {
             atomicAdd(reinterpret_cast<int*>(prm.a.on_target) + h, cnt_sh[0]);
             atomicAdd(reinterpret_cast<int*>(prm.a.intercept) + h, cnt_sh[1]);
+            atomicAdd(reinterpret_cast<int*>(prm.a.blocking) + h, BLK ? cnt_sh[2] : (p_end - p_begin) * R);
         }
     }
 
@@ -530,9 +562,10 @@ __global__ void finalize_split_kernel(const TraceParams prm) {
         const float rp = (float)(prm.a.n_rays * prm.a.n_points);
         const int c0 = reinterpret_cast<int*>(prm.a.on_target)[h];
         const int c1 = reinterpret_cast<int*>(prm.a.intercept)[h];
+        const int c2 = reinterpret_cast<int*>(prm.a.blocking)[h];
         prm.a.on_target[h] = sdiv((float)c0, rp);
         prm.a.intercept[h] = sdiv((float)c1, rp);
-        prm.a.blocking[h] = 1.0f;
+        prm.a.blocking[h] = sdiv((float)c2, rp);
     }
 }
 
@@ -543,9 +576,10 @@ __global__ void finalize_split_fp32_kernel(const TraceParams prm) {
     const float rp = (float)(prm.a.n_rays * prm.a.n_points);
     const int c0 = reinterpret_cast<int*>(prm.a.on_target)[h];
     const int c1 = reinterpret_cast<int*>(prm.a.intercept)[h];
+    const int c2 = reinterpret_cast<int*>(prm.a.blocking)[h];
     prm.a.on_target[h] = sdiv((float)c0, rp);
     prm.a.intercept[h] = sdiv((float)c1, rp);
-    prm.a.blocking[h] = 1.0f;
+    prm.a.blocking[h] = sdiv((float)c2, rp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -555,9 +589,14 @@ struct BwdCtx {
     const float* win_g;  // shared-memory window of the bitmap gradient
     const float* gf;     // this sample's [U,E] gradient in global memory
     int e0, u0, ww, wwm1, whm1;
+    const BlockPrim* blk; // shared: candidate blocking primitives of this sample
+    const int* blk_rows;  // shared: their rows in the primitive table
+    int n_blk;
+    BlockParams bp;
+    float* grad_prims;
 };
 
-template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR>
+template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR, bool BLK>
 __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, int h, int p_begin,
                                          int p_end, float i0, float i1, float i2, float* __restrict__ grad_points,
                                          float* __restrict__ grad_normals) {
@@ -567,8 +606,8 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
     const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
     const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
     const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
-    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
-    const float k_or = ome * refl;
+    const float mag = prm.a.ray_magnitude;
+    const float k_or = prm.a.one_minus_extinction * prm.a.reflectivity;
     const float k_int = mag * k_or;                 // d intensity / d lambert-cosine
     const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
 
@@ -578,7 +617,9 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
         make_point(pc, T, i0, i1, i2, o4, n4);
         float go0 = 0.f, go1 = 0.f, go2 = 0.f;   // planar: grad origin (world); cylindrical: grad origin (cylinder frame)
         float gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;   // grad preferred reflection direction
+        float gow0 = 0.f, gow1 = 0.f, gow2 = 0.f;  // grad origin through the blocking term (always world frame)
         bool touched = false;
+        const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         const float2* dp = dist + p;
         float2 d_next = __ldcs(dp);
         for (int r = 0; r < R; ++r) {
@@ -607,8 +648,18 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
                 const float* row_lo = row_hi + E;
                 g1 = __ldg(row_hi); g2 = __ldg(row_hi + 1); g3 = __ldg(row_lo + 1); g4 = __ldg(row_lo);
             }
-            const float inten = hit.lam * k_or;
-            const float g_int = sp.whu * (sp.wle * g1 + sp.whe * g2) + sp.wlu * (sp.whe * g3 + sp.wle * g4);
+            const float g_int0 = sp.whu * (sp.wle * g1 + sp.whe * g2) + sp.wlu * (sp.whe * g3 + sp.wle * g4);
+            float gdb0 = 0.f, gdb1 = 0.f, gdb2 = 0.f;
+            float unblocked = 1.0f;
+            if (BLK && bmask) {   // intensity = lambert * (1 - blocked) * k_or
+                const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
+                                                    -g_int0 * hit.lam * k_or, bc.grad_prims);
+                unblocked = 1.0f - bb.blocked;
+                gow0 += bb.go0; gow1 += bb.go1; gow2 += bb.go2;
+                gdb0 = bb.gd0; gdb1 = bb.gd1; gdb2 = bb.gd2;
+            }
+            const float g_int = g_int0 * unblocked;
+            const float inten = hit.lam * k_or * unblocked;
             const float g_be = inten * (sp.whu * (g2 - g1) + sp.wlu * (g3 - g4));
             const float g_bu = inten * (sp.wle * (g1 - g4) + sp.whe * (g2 - g3));
             float gdx, gdy, gdz;
@@ -652,6 +703,7 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
                 gdy = T.uy * gdlx + T.n1 * gdly + T.ax1 * gdlz;
                 gdz = T.uz * gdlx + T.n2 * gdly + T.ax2 * gdlz;
             }
+            gdx += gdb0; gdy += gdb1; gdz += gdb2;
             // d = M r  ->  grad r += M^T grad d
             gr0 += s.cu * gdx + s.m10 * gdy + s.m20 * gdz;
             gr1 += -s.su * gdx + s.m11 * gdy + s.m21 * gdz;
@@ -664,6 +716,7 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
             gp1 = T.uy * go0 + T.n1 * go1 + T.ax1 * go2;
             gp2 = T.uz * go0 + T.n2 * go1 + T.ax2 * go2;
         }
+        gp0 += gow0; gp1 += gow1; gp2 += gow2;
         // r = i - 2 (i.n) n   ->   grad n = -2 [ (i.n) grad r + (grad r . n) i ]
         const float grn = gr0 * n4.x + gr1 * n4.y + gr2 * n4.z;
         const float gn0 = -2.0f * (pc.dot * gr0 + grn * i0);
@@ -685,7 +738,7 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
 }
 
 // Branch-light fast loop for planar targets (see fwd_rays_planar_fast).
-template <int THREADS, int TRIG>
+template <int THREADS, int TRIG, bool BLK>
 __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, int h,
                                                      int p_begin, int p_end, float i0, float i1, float i2,
                                                      float* __restrict__ grad_points, float* __restrict__ grad_normals,
@@ -709,6 +762,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
         make_point(pc, T, i0, i1, i2, o4, n4);
         float go0 = 0.f, go1 = 0.f, go2 = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
         if (point_regular(pc)) {
+            const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
             const float2* dp = dist + p;
             float2 d_next = __ldcs(dp);
 #pragma unroll kRayUnroll
@@ -751,8 +805,17 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
                     const float* row_lo = row_hi + E;
                     g1 = __ldg(row_hi); g2 = __ldg(row_hi + 1); g3 = __ldg(row_lo + 1); g4 = __ldg(row_lo);
                 }
-                const float inten = -a * k_lam;
-                const float g_int = whu * fmaf(wle, g1, whe * g2) + wlu * fmaf(whe, g3, wle * g4);
+                float g_int = whu * fmaf(wle, g1, whe * g2) + wlu * fmaf(whe, g3, wle * g4);
+                float inten = -a * k_lam;
+                float gdb0 = 0.f, gdb1 = 0.f, gdb2 = 0.f;
+                if (BLK && bmask) {   // intensity = lambert * (1 - blocked) * k_or  (rare: only shadowed points get here)
+                    const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
+                                                        -g_int * inten, bc.grad_prims);
+                    go0 += bb.go0; go1 += bb.go1; go2 += bb.go2;
+                    gdb0 = bb.gd0; gdb1 = bb.gd1; gdb2 = bb.gd2;
+                    g_int *= 1.0f - bb.blocked;
+                    inten *= 1.0f - bb.blocked;
+                }
                 const float gX = -k_e * inten * fmaf(whu, g2 - g1, wlu * (g3 - g4));   // d/dX through be = (E-1) - te/w*(E-1)
                 const float gZ = k_u * inten * fmaf(wle, g1 - g4, whe * (g2 - g3));
                 const float gt = fmaf(gX, s.dx, gZ * s.dz);
@@ -761,7 +824,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
                 go0 += fmaf(-gnum, T.n0, gX);
                 go1 = fmaf(-gnum, T.n1, go1);
                 go2 += fmaf(-gnum, T.n2, gZ);
-                const float gdx = fmaf(gX, t, g_a * T.n0), gdy = g_a * T.n1, gdz = fmaf(gZ, t, g_a * T.n2);
+                const float gdx = fmaf(gX, t, g_a * T.n0) + gdb0, gdy = g_a * T.n1 + gdb1, gdz = fmaf(gZ, t, g_a * T.n2) + gdb2;
                 gr0 += fmaf(s.cu, gdx, fmaf(s.m10, gdy, s.m20 * gdz));
                 gr1 += fmaf(-s.su, gdx, fmaf(s.m11, gdy, s.m21 * gdz));
                 gr2 += fmaf(-s.se, gdy, s.ce * gdz);
@@ -779,15 +842,17 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
     n_irregular_out = n_irr;
 }
 
-template <int THREADS, int TRIG>
+template <int THREADS, int TRIG, bool BLK>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
-                 float* __restrict__ grad_points, float* __restrict__ grad_normals) {
+                 float* __restrict__ grad_points, float* __restrict__ grad_normals, float* __restrict__ grad_prims) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* win_g = reinterpret_cast<float*>(smem_raw);
     __shared__ TargetCtx T_sh;
     __shared__ Window win_sh;
     __shared__ float red[6 * 32];
+    __shared__ BlockPrim blk_sh[BLK ? kMaxBlockCandidates : 1];
+    __shared__ int blk_rows_sh[BLK ? kMaxBlockCandidates : 1];
 
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
@@ -817,15 +882,26 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     BwdCtx bc;
     bc.win_g = win_g; bc.gf = gf; bc.e0 = W.e0; bc.u0 = W.u0; bc.ww = W.ww;
     bc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; bc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
+    bc.blk = blk_sh; bc.blk_rows = blk_rows_sh; bc.n_blk = 0; bc.grad_prims = grad_prims;
+    if (BLK && prm.a.blockers.n_blockers > 0) {
+        const ab200_blockers& B = prm.a.blockers;
+        bc.n_blk = min(B.cand_count[h], kMaxBlockCandidates);
+        bc.bp.softness = B.softness; bc.bp.alpha = B.alpha; bc.bp.offset = B.ray_origin_offset; bc.bp.epsilon = B.epsilon;
+        bc.bp.cull_angle = B.cull_angle;
+        for (int i = tid; i < bc.n_blk; i += THREADS) blk_rows_sh[i] = B.cand_idx[(size_t)h * B.max_candidates + i];
+        for (int i = tid; i < bc.n_blk * 16; i += THREADS)
+            reinterpret_cast<float*>(blk_sh)[i] = B.prims[(size_t)B.cand_idx[(size_t)h * B.max_candidates + i / 16] * 16 + (i % 16)];
+        __syncthreads();
+    }
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
-        bwd_rays_planar_fast<THREADS, TRIG>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, n_irr);
+        bwd_rays_planar_fast<THREADS, TRIG, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, n_irr);
         if (__syncthreads_or(n_irr != 0))   // never with physical inputs (each thread re-reads only its own points)
-            bwd_rays<THREADS, TRIG, true, false, true>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+            bwd_rays<THREADS, TRIG, true, false, true, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
     } else if (T.planar) {
-        bwd_rays<THREADS, TRIG, true, false, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+        bwd_rays<THREADS, TRIG, true, false, false, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
     } else {
-        bwd_rays<THREADS, TRIG, false, false, false>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+        bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
     }
 }
 
@@ -844,7 +920,9 @@ static int32_t validate(const ab200_trace_args* a) {
     AB200_REQUIRE(a->trig_mode != AB200_TRIG_TABLE || a->trig, AB200_EINVAL, "trig_mode TABLE needs args->trig");
     AB200_REQUIRE(a->trig_mode >= 0 && a->trig_mode <= 2, AB200_EINVAL, "bad trig_mode %d", a->trig_mode);
     AB200_REQUIRE(a->targets.n_planar + a->targets.n_cyl > 0, AB200_EINVAL, "no target areas");
-    AB200_REQUIRE(a->blockers.n_blockers == 0, AB200_EINVAL, "blocking is not supported by this build");
+    AB200_REQUIRE(a->blockers.n_blockers == 0 || (a->blockers.prims && a->blockers.cand_idx && a->blockers.cand_count &&
+                                                   a->blockers.max_candidates >= 1 && a->blockers.max_candidates <= kMaxBlockCandidates),
+                  AB200_EINVAL, "blocking needs prims, cand_idx, cand_count and 1 <= max_candidates <= %d", kMaxBlockCandidates);
     return AB200_OK;
 }
 
@@ -852,11 +930,20 @@ struct LaunchPlan {
     int threads, split, pts_per_chunk, smem_bytes;
 };
 
+// dynamic shared memory available to one CTA next to the kernels' static shared data (target, window, reduction
+// scratch, 64 blocking primitives: < 6 KB)
+static int max_window_bytes() {
+    int dev = 0, optin = 227 * 1024;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return optin - 6 * 1024;
+}
+
 static LaunchPlan make_plan(int n_local, int n_points, int max_threads_large) {
     LaunchPlan pl;
     const int sms = sm_count();
     if (n_local >= 2 * sms) {
-        pl.threads = max_threads_large; pl.split = 1; pl.smem_bytes = AB200_WIN_KB * 1024;
+        pl.threads = max_threads_large; pl.split = 1;
+        pl.smem_bytes = AB200_WIN_KB * 1024 < max_window_bytes() ? AB200_WIN_KB * 1024 : max_window_bytes();
     } else {
         pl.threads = 512;
         const int want = (4 * sms + (n_local > 0 ? n_local : 1) - 1) / (n_local > 0 ? n_local : 1);
@@ -890,16 +977,19 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
 template <int THREADS, int TRIG>
 static cudaError_t launch_fwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, bool dbg, bool fp32acc) {
     const int grid = prm.a.n_local * pl.split;
-#define AB200_LAUNCH_FWD(DBG, ACC)                                                                           \
+#define AB200_LAUNCH_FWD(DBG, ACC, BLK)                                                                      \
     do {                                                                                                     \
-        auto kern = trace_fwd_kernel<THREADS, TRIG, DBG, ACC>;                                               \
+        auto kern = trace_fwd_kernel<THREADS, TRIG, DBG, ACC, BLK>;                                          \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes); \
         if (e != cudaSuccess) return e;                                                                      \
         kern<<<grid, THREADS, pl.smem_bytes, st>>>(prm);                                                     \
         note_launch();                                                                                       \
     } while (0)
-    if (dbg) { if (fp32acc) AB200_LAUNCH_FWD(true, true); else AB200_LAUNCH_FWD(true, false); }
-    else     { if (fp32acc) AB200_LAUNCH_FWD(false, true); else AB200_LAUNCH_FWD(false, false); }
+    if (prm.a.blockers.n_blockers > 0) {   // blocking: production variant only
+        if (dbg || fp32acc) return cudaErrorNotSupported;
+        AB200_LAUNCH_FWD(false, false, true);
+    } else if (dbg) { if (fp32acc) AB200_LAUNCH_FWD(true, true, false); else AB200_LAUNCH_FWD(true, false, false); }
+    else     { if (fp32acc) AB200_LAUNCH_FWD(false, true, false); else AB200_LAUNCH_FWD(false, false, false); }
 #undef AB200_LAUNCH_FWD
     return cudaGetLastError();
 }
@@ -915,22 +1005,29 @@ static cudaError_t launch_fwd_trig(const TraceParams& prm, const LaunchPlan& pl,
 
 template <int THREADS, int TRIG>
 static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                              long long gstride, float* gpts, float* gnrm) {
-    auto kern = trace_bwd_kernel<THREADS, TRIG>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
-    if (e != cudaSuccess) return e;
-    kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm);
+                              long long gstride, float* gpts, float* gnrm, float* gprims) {
+    if (prm.a.blockers.n_blockers > 0) {
+        auto kern = trace_bwd_kernel<THREADS, TRIG, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+        if (e != cudaSuccess) return e;
+        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims);
+    } else {
+        auto kern = trace_bwd_kernel<THREADS, TRIG, false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+        if (e != cudaSuccess) return e;
+        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims);
+    }
     note_launch();
     return cudaGetLastError();
 }
 
 template <int THREADS>
 static cudaError_t launch_bwd_trig(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                                   long long gstride, float* gpts, float* gnrm) {
+                                   long long gstride, float* gpts, float* gnrm, float* gprims) {
     switch (prm.a.trig_mode) {
-        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gstride, gpts, gnrm);
-        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gstride, gpts, gnrm);
-        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gstride, gpts, gnrm);
+        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims);
+        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims);
+        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims);
     }
 }
 
@@ -990,8 +1087,8 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
     fill_params(prm, a, pl);
     const long long gstride = b->grad_flux_stride >= 0 ? b->grad_flux_stride : (long long)a->res_u * a->res_e;
     cudaError_t e = (pl.threads == kBwdThreadsLarge)
-                        ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals)
-                        : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals);
+                        ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims)
+                        : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_bwd launch failed: %s", cudaGetErrorString(e));
     return AB200_OK;
 }

@@ -90,6 +90,24 @@ class TraceOptions:
     fp32_accumulate: bool = False
 
 
+@dataclass
+class BlockingInputs:
+    """Rectangle primitives of ALL heliostats (``artist/raytracing/blocking.py:123-209``) + what the candidate search
+    needs per active sample.  ``corners/spans/normals`` may require grad (gradients flow to the blockers' geometry)."""
+
+    corners: torch.Tensor            # [H,4,>=3]
+    spans: torch.Tensor              # [H,2,>=3]
+    normals: torch.Tensor            # [H,>=3]
+    sample_to_blocker: torch.Tensor  # [N] int32: primitive row of each active sample's own heliostat
+    aim_points: torch.Tensor         # [N,4]
+    target_radius: torch.Tensor      # [N]
+    softness: float = 1000.0
+    alpha: float = 100.0
+    ray_origin_offset: float = 0.05
+    epsilon: float = 1e-12
+    max_candidates: int = 64
+
+
 def pack_distortions(distortions_u: torch.Tensor, distortions_e: torch.Tensor) -> torch.Tensor:
     """Return the interleaved ``[N,R,P,2]`` (u,e) buffer the kernels stream.
 
@@ -106,7 +124,7 @@ def pack_distortions(distortions_u: torch.Tensor, distortions_e: torch.Tensor) -
 
 
 def _trace_args(points, normals, incident, distortions, trig, target_idx, targets: TargetTensors, opt: TraceOptions,
-                local_rows, flux, intercept, on_target, blocking, dbg=None) -> _lib.TraceArgs:
+                local_rows, flux, intercept, on_target, blocking, dbg=None, blk=None) -> _lib.TraceArgs:
     n, p, _ = points.shape
     r = distortions.shape[1]
     a = _lib.TraceArgs()
@@ -118,7 +136,13 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
     a.points, a.normals, a.incident = _p(points), _p(normals), _p(incident)
     a.distortions, a.trig, a.target_idx = _p(distortions), _p(trig), _p(target_idx)
     a.targets = targets.struct()
-    a.blockers = _lib.Blockers(0, None, None, None, None, 1000.0, 1e-12)
+    if blk is None:
+        a.blockers = _lib.Blockers(0, 0, None, None, None, 1000.0, 100.0, 0.05, 1e-12, 0.0)
+    else:
+        bi, prims, cand_idx, cand_count = blk
+        a.blockers = _lib.Blockers(int(prims.shape[0]), int(bi.max_candidates), _p(prims), _p(cand_idx), _p(cand_count),
+                                   float(bi.softness), float(bi.alpha), float(bi.ray_origin_offset), float(bi.epsilon),
+                                   6.0 * float(opt.scatter_sigma))
     a.ray_magnitude = float(opt.ray_magnitude)
     a.one_minus_extinction = float(1 - opt.ray_extinction_factor)
     a.reflectivity = float(opt.mirror_reflectivity)
@@ -135,9 +159,35 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
 trace_stats: torch.Tensor | None = None  # set to a zeroed int64[4] CUDA tensor to collect window diagnostics
 
 
+last_blocking_overflow: torch.Tensor | None = None  # int32[1]: samples whose candidate list overflowed (should stay 0)
+
+
+def _prepare_blocking(bi: BlockingInputs, opt: TraceOptions, n: int, dev):
+    """Pack the primitives and build the per-sample candidate lists (two small kernels)."""
+    global last_blocking_overflow
+    corners = _f32(bi.corners.detach()[..., :3], "blocking corners")
+    spans = _f32(bi.spans.detach()[..., :3], "blocking spans")
+    normals = _f32(bi.normals.detach()[..., :3], "blocking normals")
+    h = corners.shape[0]
+    prims = torch.empty(h, 16, device=dev)
+    _lib.call("ab200_blocking_pack", _p(corners), _p(spans), _p(normals), h, float(bi.epsilon), _p(prims), _stream())
+    cand_idx = torch.empty(n, bi.max_candidates, dtype=torch.int32, device=dev)
+    cand_count = torch.empty(n, dtype=torch.int32, device=dev)
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+    owner = _i32(bi.sample_to_blocker, "sample_to_blocker")
+    aim = _f32(bi.aim_points.detach(), "aim_points")
+    radius = _f32(bi.target_radius.detach(), "target_radius")
+    spread = 6.0 * float(opt.scatter_sigma) if opt.scatter_sigma > 0 else 0.02
+    _lib.call("ab200_blocking_candidates", _p(prims), h, _p(owner), _p(aim), _p(radius), n, spread, int(bi.max_candidates),
+              _p(cand_idx), _p(cand_count), _p(overflow), _stream())
+    last_blocking_overflow = overflow
+    return prims, cand_idx, cand_count
+
+
 class _TraceFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt):
+    def forward(ctx, points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, bi, b_corners,
+                b_spans, b_normals):
         points, normals, incident = _f32(points, "points"), _f32(normals, "normals"), _f32(incident, "incident")
         distortions = _f32(distortions, "distortions")
         target_idx = _i32(target_idx, "target_area_indices")
@@ -147,17 +197,24 @@ class _TraceFn(torch.autograd.Function):
         intercept = torch.empty(n, device=dev)
         on_target = torch.empty(n, device=dev)
         blocking = torch.empty(n, device=dev)
+        blk = None
+        if bi is not None:
+            blk = (bi, *_prepare_blocking(bi, opt, n, dev))
         args = _trace_args(points, normals, incident, distortions, trig, target_idx, targets, opt, local_rows,
-                           flux, intercept, on_target, blocking)
+                           flux, intercept, on_target, blocking, blk=blk)
         _lib.call("ab200_trace_fwd", C.byref(args), _stream())
-        ctx.save_for_backward(points, normals, incident, distortions, trig, target_idx, local_rows)
-        ctx.targets, ctx.opt = targets, opt
+        ctx.save_for_backward(points, normals, incident, distortions, trig, target_idx, local_rows,
+                              *(blk[1:] if blk is not None else ()))
+        ctx.targets, ctx.opt, ctx.bi = targets, opt, bi
+        ctx.blocker_shapes = None if bi is None else (b_corners.shape, b_spans.shape, b_normals.shape)
         ctx.mark_non_differentiable(intercept, on_target, blocking)
         return flux, intercept, on_target, blocking
 
     @staticmethod
     def backward(ctx, g_flux, _gi, _go, _gb):
-        points, normals, incident, distortions, trig, target_idx, local_rows = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        points, normals, incident, distortions, trig, target_idx, local_rows = saved[:7]
+        blk = None if ctx.bi is None else (ctx.bi, *saved[7:10])
         if not g_flux.is_cuda:
             raise _lib.Ab200Error("grad_flux must be a CUDA tensor")
         u, e = g_flux.shape[1], g_flux.shape[2]
@@ -170,22 +227,40 @@ class _TraceFn(torch.autograd.Function):
         g_normals = torch.empty_like(normals)
         b = _lib.TraceBwdArgs()
         b.fwd = _trace_args(points, normals, incident, distortions, trig, target_idx, ctx.targets, ctx.opt, local_rows,
-                            None, None, None, None)
+                            None, None, None, None, blk=blk)
         b.grad_flux, b.grad_points, b.grad_normals = _p(g_flux), _p(g_points), _p(g_normals)
         b.grad_flux_stride = g_stride
+        g_corners = g_spans = g_bnormals = None
+        need_blockers = blk is not None and any(ctx.needs_input_grad[10:13])
+        g_prims = torch.zeros(blk[1].shape[0], 12, device=points.device) if need_blockers else None
+        b.grad_prims = _p(g_prims)
         _lib.call("ab200_trace_bwd", C.byref(b), _stream())
-        return g_points, g_normals, None, None, None, None, None, None, None
+        if need_blockers:
+            cs, ss, ns = ctx.blocker_shapes
+            g_corners = torch.zeros(cs, device=points.device)
+            g_corners[:, 0, :3] = g_prims[:, 0:3]
+            g_spans = torch.zeros(ss, device=points.device)
+            g_spans[:, 0, :3] = g_prims[:, 3:6]
+            g_spans[:, 1, :3] = g_prims[:, 6:9]
+            g_bnormals = torch.zeros(ns, device=points.device)
+            g_bnormals[:, :3] = g_prims[:, 9:12]
+        return g_points, g_normals, None, None, None, None, None, None, None, None, g_corners, g_spans, g_bnormals
 
 
 def trace(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,
-          local_rows: torch.Tensor | None = None, trig: torch.Tensor | None = None):
+          local_rows: torch.Tensor | None = None, trig: torch.Tensor | None = None,
+          blocking: BlockingInputs | None = None):
     """Fused forward trace -> ``(flux[N,U,E], intercept[N], on_target[N], blocking[N])``; differentiable
-    w.r.t. ``points`` and ``normals``."""
+    w.r.t. ``points`` and ``normals`` (and, with ``blocking``, the blockers' corners / spans / normals)."""
     if trig is not None:
         trig = _f32(trig, "trig")
     if local_rows is not None:
         local_rows = _i32(local_rows, "local_rows")
-    return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt)
+    if blocking is None:
+        return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, None,
+                              None, None, None)
+    return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, blocking,
+                          blocking.corners, blocking.spans, blocking.normals)
 
 
 def trace_debug(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,

@@ -1,5 +1,7 @@
 from __future__ import annotations
 
+import math
+
 import torch
 
 from .. import ops
@@ -65,18 +67,6 @@ class HeliostatRayTracer:
         self._local_rows = None if len(rows) == n else torch.tensor(rows, dtype=torch.int32, device=device)
         self._targets = ops.TargetTensors.from_solar_tower(scenario.solar_tower, device)
 
-        if self.blocking_active:
-            groups = scenario.heliostat_field.heliostat_groups
-            self.blocking_heliostat_surfaces = torch.cat([g.surface_points for g in groups])
-            active = []
-            for g in groups:
-                surfaces = g.surface_points + g.positions.unsqueeze(1)
-                mask = g.active_heliostats_mask.bool()
-                if mask.any():
-                    surfaces[mask] = g.active_surface_points
-                active.append(surfaces)
-            self.blocking_heliostat_surfaces_active = torch.cat(active)
-
         if dni is not None:
             # heliostat area from the canting vectors of the first heliostat (:185-203)
             canting_norm = (torch.norm(heliostat_group.canting[0], dim=1)[0])[:2]
@@ -99,9 +89,6 @@ class HeliostatRayTracer:
         group = self.heliostat_group
         assert torch.equal(group.active_heliostats_mask, active_heliostats_mask), (
             "Some heliostats were not aligned and cannot be raytraced.")
-        if self.blocking_active:
-            raise NotImplementedError(
-                "blocking_active=True is not built yet in artist_b200 (SURVEY.md 8f-1); pass blocking_active=False")
         group._reflection_inputs = (incident_ray_directions, group.active_surface_normals)
         sigma = getattr(self.light_source, "scatter_sigma", 0.0)
         opt = ops.TraceOptions(
@@ -109,8 +96,75 @@ class HeliostatRayTracer:
             res_u=int(self.bitmap_resolution[indices.unbatched_bitmap_u]),
             ray_magnitude=float(self.ray_magnitude), ray_extinction_factor=ray_extinction_factor,
             mirror_reflectivity=mirror_reflectivity, scatter_sigma=sigma)
+        blocking = self._blocking_inputs(target_area_indices) if self.blocking_active else None
         return ops.trace(group.active_surface_points, group.active_surface_normals, incident_ray_directions,
-                         self._packed, target_area_indices, self._targets, opt, local_rows=self._local_rows)
+                         self._packed, target_area_indices, self._targets, opt, local_rows=self._local_rows,
+                         blocking=blocking)
+
+    # ---- blocking (artist/raytracing/blocking.py, heliostat_ray_tracer.py:159-183,292-301,445-480) -----------------
+    @staticmethod
+    def _corner_rows(number_of_points: int) -> list[int]:
+        """The four fixed surface-point indices the reference uses as rectangle corners (``blocking.py:176-193``;
+        assumes four equal square facets): lower left, upper left, upper right, lower right."""
+        q = int(math.sqrt(number_of_points / 4))
+        return [number_of_points // 2, q - 1, number_of_points // 2 - 1, number_of_points - q]
+
+    def _blocker_corners(self) -> tuple[torch.Tensor, torch.Tensor]:
+        """Corner points ``[H_all,4,4]`` of every heliostat of every group (aligned where a group is active,
+        horizontal at its position otherwise - ``:170-183``) and, for this tracer's group, the primitive row of each
+        active sample.  Only the 4 corner points per heliostat are gathered; the reference concatenates all surfaces."""
+        corners, owner, offset = [], None, 0
+        for g in self.scenario.heliostat_field.heliostat_groups:
+            rows = torch.tensor(self._corner_rows(g.surface_points.shape[1]), device=g.surface_points.device)
+            c = g.surface_points.index_select(1, rows) + g.positions.unsqueeze(1)
+            mask = g.active_heliostats_mask
+            if bool((mask > 0).any()):
+                active_rows = getattr(g, "_active_rows", None)
+                if active_rows is None:     # all-ones mask: sample i is heliostat i
+                    active_rows = torch.arange(g.number_of_heliostats, device=c.device)
+                aligned = g.active_surface_points.index_select(1, rows)
+                # a heliostat activated several times contributes the geometry of its last sample
+                c = c.index_copy(0, active_rows.long(), aligned)
+                if g is self.heliostat_group:
+                    owner = (active_rows + offset).to(torch.int32)
+            corners.append(c)
+            offset += g.number_of_heliostats
+        return torch.cat(corners), owner
+
+    def _blocking_inputs(self, target_area_indices: torch.Tensor) -> ops.BlockingInputs:
+        corners, owner = self._blocker_corners()
+        spans = torch.stack([corners[:, 1] - corners[:, 0], corners[:, 3] - corners[:, 0]], dim=1)
+        normals = torch.nn.functional.normalize(torch.linalg.cross(spans[:, 0, :3], spans[:, 1, :3], dim=-1), dim=-1)
+        tower = self.scenario.solar_tower
+        aim = tower.get_centers_of_target_areas(target_area_indices)
+        planar, cyl = tower.target_areas[0], tower.target_areas[1]
+        n_planar = planar.number_of_target_areas
+        idx = target_area_indices.long()
+        radius = torch.zeros(idx.shape[0], device=aim.device)
+        if n_planar > 0:
+            pr = 0.5 * torch.linalg.norm(planar.dimensions.to(aim.device).float(), dim=1)
+            radius = torch.where(idx < n_planar, pr[idx.clamp(max=n_planar - 1)], radius)
+        if cyl.number_of_target_areas > 0:
+            cr = 1.5 * torch.maximum(cyl.radii.to(aim.device).float(), 0.5 * cyl.heights.to(aim.device).float())
+            radius = torch.where(idx < n_planar, radius, cr[(idx - n_planar).clamp(min=0)])
+        return ops.BlockingInputs(corners=corners, spans=spans, normals=normals, sample_to_blocker=owner, aim_points=aim,
+                                  target_radius=radius)
+
+    @property
+    def blocking_heliostat_surfaces(self) -> torch.Tensor:
+        return torch.cat([g.surface_points for g in self.scenario.heliostat_field.heliostat_groups])
+
+    @property
+    def blocking_heliostat_surfaces_active(self) -> torch.Tensor:
+        out = []
+        for g in self.scenario.heliostat_field.heliostat_groups:
+            surfaces = g.surface_points + g.positions.unsqueeze(1)
+            mask = g.active_heliostats_mask.bool()
+            if mask.any():
+                surfaces = surfaces.clone()
+                surfaces[mask] = g.active_surface_points
+            out.append(surfaces)
+        return torch.cat(out)
 
     def get_bitmaps_per_target(self, bitmaps_per_heliostat: torch.Tensor, target_area_indices: torch.Tensor,
                                device: torch.device | None = None) -> torch.Tensor:

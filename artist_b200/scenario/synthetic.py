@@ -78,7 +78,9 @@ def planar_control_points(cu: int, cv: int, canting: torch.Tensor) -> torch.Tens
 
 def synthetic_field_tensors(n_heliostats: int, control_points: tuple[int, int] = (10, 10),
                             degrees: tuple[int, int] = (3, 3), surface_bump: float = 0.0,
-                            seed: int = 0, with_cylinder: bool = True) -> dict:
+                            seed: int = 0, with_cylinder: bool = True, pitch: float = 5.0,
+                            first_row_north: float = 30.0,
+                            planar_center: tuple[float, float, float] = (0.0, 0.0, 50.0)) -> dict:
     """Plain CPU tensors describing the synthetic field.
 
     ``surface_bump`` > 0 perturbs the control-point heights (metres, deterministic by ``seed``)
@@ -88,8 +90,8 @@ def synthetic_field_tensors(n_heliostats: int, control_points: tuple[int, int] =
     s = max(1, math.ceil(math.sqrt(n)))
     idx = torch.arange(n)
     positions = torch.zeros(n, 4)
-    positions[:, 0] = ((idx % s).float() - s / 2) * 5.0
-    positions[:, 1] = 30.0 + torch.div(idx, s, rounding_mode="floor").float() * 5.0
+    positions[:, 0] = ((idx % s).float() - s / 2) * pitch
+    positions[:, 1] = first_row_north + torch.div(idx, s, rounding_mode="floor").float() * pitch
     positions[:, 2] = 1.7
     positions[:, 3] = 1.0
     tr, cant = aa39_facets()
@@ -115,7 +117,7 @@ def synthetic_field_tensors(n_heliostats: int, control_points: tuple[int, int] =
         actuator_non_optimizable=non_opt,
         actuator_optimizable=opt,
         planar_names=["receiver_plane"],
-        planar_centers=torch.tensor([[0.0, 0.0, 50.0, 1.0]]),
+        planar_centers=torch.tensor([[planar_center[0], planar_center[1], planar_center[2], 1.0]]),
         planar_normals=torch.tensor([[0.0, 1.0, 0.0, 0.0]]),
         planar_dimensions=torch.tensor([[8.0, 8.0]]),
     )

@@ -57,15 +57,20 @@ typedef struct ab200_targets {
     const float* cyl_opening;    /* [n_cyl] opening angles (rad) */
 } ab200_targets;
 
-/* Blocking rectangles of ALL heliostats of the scenario (artist/raytracing/blocking.py:123-209). */
+/* Blocking (artist/raytracing/blocking.py): rectangle primitives of ALL heliostats of the scenario, packed by
+ * ab200_blocking_pack, and per active sample the ordered candidate list built by ab200_blocking_candidates (it
+ * replaces the per-batch LBVH filter :832-995).  n_blockers == 0 switches blocking off. */
 typedef struct ab200_blockers {
-    int32_t n_blockers;          /* 0 = blocking off */
-    const float* corners;        /* [H,4,3] corner points (lower-left, upper-left, upper-right, lower-right) */
-    const float* spans;          /* [H,2,3] */
-    const float* normals;        /* [H,3] */
-    const int32_t* sample_to_blocker; /* [N] global heliostat index of each active sample (self-hit removal) */
-    float softness;              /* 1000 */
-    float epsilon;               /* 1e-12 */
+    int32_t n_blockers;            /* H */
+    int32_t max_candidates;        /* row length of cand_idx (<= 64) */
+    const float* prims;            /* [H,16]: corner0(3) span_u(3) span_v(3) normal(3) |u|^2 |v|^2 u.v det_safe */
+    const int32_t* cand_idx;       /* [N,max_candidates] candidate primitive rows per active sample */
+    const int32_t* cand_count;     /* [N] */
+    float softness;                /* 1000 */
+    float alpha;                   /* 100 */
+    float ray_origin_offset;       /* 0.05 */
+    float epsilon;                 /* 1e-12 */
+    float cull_angle;              /* bound on the scatter angle for the per-point candidate cull (rad); <= 0 disables it */
 } ab200_blockers;
 
 /*
@@ -129,6 +134,8 @@ typedef struct ab200_trace_bwd_args {
                                  (e.g. the loss is taken on the per-target sum) - no [N,U,E] expansion is materialised */
     float* grad_points;       /* out [N,P,4] (w component 0) */
     float* grad_normals;      /* out [N,P,4] (w component 0) */
+    float* grad_prims;        /* blocking only, may be NULL: [H,12] d/d(corner0, span_u, span_v, normal), ACCUMULATED with
+                                 float atomics (caller zeroes it) */
 } ab200_trace_bwd_args;
 
 int32_t ab200_trace_bwd(const ab200_trace_bwd_args* args, void* stream);
@@ -255,6 +262,17 @@ typedef struct ab200_host_trace_args {
 } ab200_host_trace_args;
 
 int32_t ab200_trace_host(const ab200_host_trace_args* args, void* stream);
+
+/* pack the blocking primitives (corners [H,4,3], spans [H,2,3], normals [H,3] -> prims [H,16]) */
+int32_t ab200_blocking_pack(const float* corners, const float* spans, const float* normals, int32_t n_prims, float epsilon,
+                            float* prims, void* stream);
+/* candidate lists: primitives whose bounding sphere touches the tapered capsule heliostat -> aim point
+ * (radius from the heliostat's half diagonal to target_radius + spread_angle * distance); `overflow` (int, caller
+ * zeroes) counts samples with more than max_candidates candidates. */
+int32_t ab200_blocking_candidates(const float* prims, int32_t n_prims, const int32_t* sample_to_blocker,
+                                  const float* aim_points /* [N,4] */, const float* target_radius /* [N] */,
+                                  int32_t n_samples, float spread_angle, int32_t max_candidates, int32_t* cand_idx,
+                                  int32_t* cand_count, int32_t* overflow, void* stream);
 
 /* misc */
 int32_t ab200_abi_version(void);

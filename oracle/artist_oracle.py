@@ -304,12 +304,12 @@ def bilinear_splatting(be: torch.Tensor, bu: torch.Tensor, inten: torch.Tensor, 
 def blocking_primitives(aligned_surface_points: torch.Tensor):
     """Rectangle per heliostat from 4 fixed corner point indices (assumes 4 square facets, 2x2).
 
-    ``blocking.py:176-209``: corners = points[P/2], [P-sqrt(P/4)], [P/2-1], [sqrt(P/4)-1];
+    ``blocking.py:176-209``: corners 0..3 = points[P/2], [sqrt(P/4)-1], [P/2-1], [P-sqrt(P/4)];
     spans u = c1-c0, v = c3-c0; normal = normalize(u x v).
     """
     p = aligned_surface_points.shape[1]
     q = int(math.sqrt(p / 4))
-    idx = torch.tensor([p // 2, p - q, p // 2 - 1, q - 1], device=aligned_surface_points.device)
+    idx = torch.tensor([p // 2, q - 1, p // 2 - 1, p - q], device=aligned_surface_points.device)
     corners = aligned_surface_points[:, idx, :3]
     span_u = corners[:, 1] - corners[:, 0]
     span_v = corners[:, 3] - corners[:, 0]
@@ -317,11 +317,57 @@ def blocking_primitives(aligned_surface_points: torch.Tensor):
     return corners, torch.stack([span_u, span_v], dim=1), normals
 
 
-def soft_ray_blocking_mask(origins, dirs, corners, spans, normals, distances_to_target,
-                           epsilon: float = 1e-12, softness: float = 1000.0):
-    """Soft differentiable ray/rectangle blocking with Beer-Lambert accumulation
-    (``blocking.py:212-354``).  Filled in by ``tests/golden`` parity once blocking is built."""
-    raise NotImplementedError("blocking oracle not built yet (SURVEY.md §8f-1)")
+def soft_ray_blocking_mask(origins, dirs, corners, spans, normals, epsilon: float = 1e-12, softness: float = 1000.0,
+                           alpha: float = 100.0, ray_origin_offset: float = 0.05):
+    """Soft differentiable ray/rectangle blocking with Beer-Lambert accumulation (``blocking.py:289-354``).
+
+    ``origins [B,P,>=3]``, ``dirs [B,R,P,>=3]``, primitives ``corners [K,4,>=3]``, ``spans [K,2,>=3]``,
+    ``normals [K,>=3]`` -> ``blocked [B,R,P]`` in [0, 1).
+    """
+    o = origins[:, None, :, None, :3]
+    d = dirs[:, :, :, None, :3]
+    c0 = corners[None, None, None, :, 0, :3]
+    su = spans[None, None, None, :, 0, :3]
+    sv = spans[None, None, None, :, 1, :3]
+    nn = normals[None, None, None, :, :3]
+    den = torch.sum(d * nn, dim=-1)
+    den = torch.where(den.abs() < epsilon, torch.where(den >= 0, epsilon, -epsilon), den)
+    t = torch.sum((c0 - o) * nn, dim=-1) / den
+    front = torch.sigmoid(softness * (t - ray_origin_offset))
+    off = (o + t[..., None] * d) - c0
+    uu, vv, uv = torch.sum(su * su, dim=-1), torch.sum(sv * sv, dim=-1), torch.sum(su * sv, dim=-1)
+    pu, pv = torch.sum(off * su, dim=-1), torch.sum(off * sv, dim=-1)
+    det = uu * vv - uv * uv
+    det = torch.where(det.abs() < epsilon, torch.sign(det) * epsilon, det)
+    u = (pu * vv - pv * uv) / det
+    v = (pv * uu - pu * uv) / det
+    inside = (torch.sigmoid(softness * u) * torch.sigmoid(softness * (1 - u))
+              * torch.sigmoid(softness * v) * torch.sigmoid(softness * (1 - v)))
+    sigma = (inside * front).clamp(0.0, 1.0)
+    return 1.0 - torch.exp(-(alpha * torch.sum(sigma, dim=-1)))
+
+
+@torch.no_grad()
+def blocking_filter(origins, dirs, corners, ray_owner, t_target):
+    """The SET of primitives whose axis-aligned box is hit by any ray of the batch before the ray reaches its
+    target, self-hits removed - what the reference's LBVH traversal returns (``blocking.py:832-995``); brute force
+    over primitives here.  ``origins [B,P,>=3]``, ``dirs [B,R,P,>=3]``, ``ray_owner [B]``, ``t_target [B,R,P]``."""
+    b, r, p = dirs.shape[:3]
+    o = origins[:, None, :, :3].expand(-1, r, -1, -1).reshape(-1, 3)
+    inv = 1.0 / (dirs[..., :3].reshape(-1, 3) + 1e-12)
+    tt = t_target.reshape(-1)
+    owner = ray_owner.repeat_interleave(r * p)
+    c3 = corners[..., :3]
+    keep = []
+    for k in range(c3.shape[0]):
+        lo, hi = c3[k].min(dim=0).values, c3[k].max(dim=0).values
+        d0, d1 = (lo - o) * inv, (hi - o) * inv
+        entry = torch.minimum(d0, d1).amax(dim=-1)
+        exit_ = torch.maximum(d0, d1).amin(dim=-1)
+        hit = (exit_ >= entry) & (exit_ > 1e-6) & (entry <= tt) & (owner != k)
+        if hit.any():
+            keep.append(k)
+    return torch.tensor(keep, dtype=torch.long)
 
 
 # --------------------------------------------------------------------------------------
@@ -332,8 +378,10 @@ def soft_ray_blocking_mask(origins, dirs, corners, spans, normals, distances_to_
 def trace_rays(points, normals, incident, dist_u, dist_e, target_idx, targets: Targets,
                resolution=(256, 256), ray_magnitude: float = 1.0, ray_extinction_factor: float = 0.0,
                mirror_reflectivity: float = 0.935, sample_indices: list[int] | None = None,
-               batch_size: int = 100):
-    """Full planar/cylindrical trace without blocking.
+               batch_size: int = 100, blocking: dict | None = None):
+    """Full planar/cylindrical trace; ``blocking = dict(corners[H,4,3+], spans[H,2,3+], normals[H,3+],
+    sample_to_blocker[N])`` switches on the blocking branch of ``heliostat_ray_tracer.py:445-480`` (per-batch
+    primitive filter + soft mask), ``None`` = ``blocking_active=False``.
 
     Returns ``(flux[N,U,E], intercept[N], on_target[N], blocking[N])`` like the reference
     (``:508``) except that rows of samples not in ``sample_indices`` are ZERO instead of
@@ -372,6 +420,11 @@ def trace_rays(points, normals, incident, dist_u, dist_e, target_idx, targets: T
                 targets.cyl_axes, targets.cyl_radii, targets.cyl_heights, targets.cyl_opening_angles,
                 tb[~planar] - targets.n_planar, res)
         blocked = torch.zeros_like(be)
+        if blocking is not None:
+            keep = blocking_filter(points[b], dirs, blocking["corners"], blocking["sample_to_blocker"][b], tt)
+            if keep.numel() > 0:
+                blocked = soft_ray_blocking_mask(points[b], dirs, blocking["corners"][keep], blocking["spans"][keep],
+                                                 blocking["normals"][keep])
         inten = lam * (1 - blocked) * (1 - ray_extinction_factor) * mirror_reflectivity
         flux[b] = bilinear_splatting(be, bu, inten, res)
         rp = r * p

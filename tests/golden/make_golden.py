@@ -73,6 +73,30 @@ def trace_case(ideal: bool, seed: int):
         flux=flux.clone(), intercept=ic.clone(), on_target=ot.clone(), blocking=bl.clone(), per_target=per_target.clone())
 
 
+def blocking_case():
+    """3x3 heliostats at 3.4 m pitch aiming at a low target: the reference with blocking_active=True (two batch sizes)."""
+    from artist.raytracing import blocking as ref_blocking
+    from artist.raytracing.heliostat_ray_tracer import HeliostatRayTracer
+
+    n, rays, ppf, res = 9, 4, (10, 10), (48, 48)
+    ft = synthetic_field_tensors(n, control_points=(6, 6), surface_bump=0.001, pitch=3.4, planar_center=(0.0, 0.0, 6.0))
+    scenario, group, _ = build_reference_scenario(ft, rays, ppf)
+    mask, tidx, inc = scenario.index_mapping(group, single_incident_ray_direction=torch.tensor([0.0, 0.8, -0.6, 0.0]), device=CPU)
+    group.activate_heliostats(mask, device=CPU)
+    aim = scenario.solar_tower.get_centers_of_target_areas(tidx, device=CPU)
+    group.align_surfaces_with_incident_ray_directions(aim, inc, mask, device=CPU)
+    out = dict(field={k: v for k, v in ft.items() if isinstance(v, torch.Tensor)}, rays=rays, res=res, target_idx=tidx,
+               incident=inc, aligned_points=group.active_surface_points.clone(), aligned_normals=group.active_surface_normals.clone())
+    for bs in (100, 4):
+        tracer = HeliostatRayTracer(scenario, group, blocking_active=True, batch_size=bs, random_seed=7, bitmap_resolution=torch.tensor(res))
+        flux, ic, ot, bl = tracer.trace_rays(inc, mask, tidx, device=CPU)
+        out[f"batch{bs}"] = dict(flux=flux.clone(), intercept=ic.clone(), on_target=ot.clone(), blocking=bl.clone())
+    c, s, nn = ref_blocking.create_blocking_primitives_rectangles_by_index(tracer.blocking_heliostat_surfaces_active, device=CPU)
+    out.update(corners=c.clone(), spans=s.clone(), normals=nn.clone(), dist_u=tracer.distortions_dataset.distortions_u.clone(),
+               dist_e=tracer.distortions_dataset.distortions_e.clone())
+    return out
+
+
 def nurbs_case(degrees, cps, ppf, canting: bool, seed: int):
     from artist.nurbs.surfaces import NURBSSurfaces
     from artist.nurbs.utils import create_nurbs_evaluation_grid
@@ -98,7 +122,7 @@ def main() -> None:
     from artist.raytracing.sampling import RestrictedDistributedSampler
     from artist.scene.sun import Sun
 
-    out = {"trace_linear": trace_case(False, 1), "trace_ideal": trace_case(True, 2),
+    out = {"trace_linear": trace_case(False, 1), "trace_ideal": trace_case(True, 2), "blocking": blocking_case(),
            "nurbs": [nurbs_case((3, 3), (6, 7), (7, 5), True, 1), nurbs_case((3, 3), (10, 10), (9, 9), False, 2),
                      nurbs_case((2, 3), (5, 6), (6, 6), True, 3)]}
     samplers = {}

@@ -106,5 +106,6 @@ def test_motor_position_gradients_and_mask_assertion():
     assert torch.isfinite(motor.grad).all() and motor.grad.abs().max() > 0
     with pytest.raises(AssertionError, match="not aligned"):
         tracer.trace_rays(inc, torch.zeros_like(mask), tidx)
-    with pytest.raises(NotImplementedError):
-        HeliostatRayTracer(scenario, group, blocking_active=True).trace_rays(inc, mask, tidx)
+    blocked = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor([64, 64]))
+    fb, _, _, bl = blocked.trace_rays(inc, mask, tidx)      # default blocking_active=True works (no shadowing here)
+    assert torch.equal(fb, flux) and (bl == 1).all()

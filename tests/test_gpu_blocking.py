@@ -1,0 +1,96 @@
+"""-m gpu: blocking (soft ray/rectangle occlusion) fused into the trace kernels vs the oracle, which reproduces the
+reference's per-batch LBVH filter + soft mask bit for bit (tests/test_oracle_golden.py::test_blocking_*)."""
+import pytest
+import torch
+
+from oracle import artist_oracle as O
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _scene(n=9, ppf=(10, 10), rays=4, seed=0):
+    """3x3 heliostats at 3.4 m pitch aiming at a target 6 m above ground: the back rows are heavily shadowed."""
+    from artist_b200 import build_synthetic_scenario, synthetic_field_tensors
+
+    ft = synthetic_field_tensors(n, control_points=(6, 6), surface_bump=0.001, pitch=3.4, planar_center=(0.0, 0.0, 6.0), seed=seed)
+    scenario, group = build_synthetic_scenario(n, number_of_rays=rays, points_per_facet=ppf, device=DEV, field_tensors=ft)
+    mask, tidx, inc = scenario.index_mapping(group, single_incident_ray_direction=torch.tensor([0.0, 0.8, -0.6, 0.0]))
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_incident_ray_directions(scenario.solar_tower.get_centers_of_target_areas(tidx), inc, mask)
+    return ft, scenario, group, mask, tidx, inc
+
+
+def _oracle_blocking(points_cpu, n):
+    c, s, nn = O.blocking_primitives(points_cpu)
+    return dict(corners=c, spans=s, normals=nn, sample_to_blocker=torch.arange(n))
+
+
+@pytest.mark.parametrize("res", [(48, 48), (128, 96)])
+def test_blocked_flux_and_factors_match_oracle(res):
+    from artist_b200 import HeliostatRayTracer, ops
+
+    ft, scenario, group, mask, tidx, inc = _scene()
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor(res))
+    flux, ic, ot, bl = tracer.trace_rays(inc, mask, tidx)
+    assert int(ops.last_blocking_overflow.item()) == 0
+    pts, nrm = group.active_surface_points.cpu(), group.active_surface_normals.cpu()
+    tg = cases.targets_from(ft)
+    du, de = tracer.distortions_dataset.distortions_u.cpu(), tracer.distortions_dataset.distortions_e.cpu()
+    ref, ric, rot, rbl = O.trace_rays(pts, nrm, inc.cpu(), du, de, tidx.cpu(), tg, res, blocking=_oracle_blocking(pts, 9))
+    unblocked, *_ = O.trace_rays(pts, nrm, inc.cpu(), du, de, tidx.cpu(), tg, res)
+    assert rbl.min() < 0.5 and (unblocked.sum() - ref.sum()) > 0.2 * unblocked.sum(), "scene must be strongly shadowed"
+    assert (flux.cpu() - ref).abs().max() <= 2e-4 * ref.max()
+    assert (bl.cpu() - rbl).abs().max() <= 2.5e-3        # a few rays sit on the 1e-3 threshold of the soft mask
+    assert (ic.cpu() - ric).abs().max() <= 2.5e-3 and (ot.cpu() - rot).abs().max() <= 1e-6
+    # blocking switched off gives the unshadowed flux
+    plain = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor(res))
+    f0, *_ = plain.trace_rays(inc, mask, tidx)
+    assert (f0.cpu() - unblocked).abs().max() <= 1e-4 * unblocked.max()
+
+
+def test_blocking_gradients_match_oracle_autograd():
+    """Gradients w.r.t. the traced surfaces (ray origins / directions through the soft mask) and w.r.t. the blockers'
+    geometry (their corner points are rows of the same aligned surfaces) vs autograd of the oracle."""
+    from artist_b200 import HeliostatRayTracer
+
+    res = (48, 48)
+    ft, scenario, group, mask, tidx, inc = _scene(rays=6)
+    pts_leaf = group.active_surface_points.detach().clone().requires_grad_(True)
+    nrm_leaf = group.active_surface_normals.detach().clone().requires_grad_(True)
+    group.active_surface_points, group.active_surface_normals = pts_leaf, nrm_leaf
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor(res))
+    flux, *_ = tracer.trace_rays(inc, mask, tidx)
+    torch.manual_seed(2)
+    wgt = torch.rand(9, res[1], res[0])
+    (flux * wgt.to(DEV)).sum().backward()
+    p = pts_leaf.detach().cpu().requires_grad_(True)
+    n = nrm_leaf.detach().cpu().requires_grad_(True)
+    c, s, nn = O.blocking_primitives(p)
+    blk = dict(corners=c, spans=s, normals=nn, sample_to_blocker=torch.arange(9))
+    tg = cases.targets_from(ft)
+    ref, *_ = O.trace_rays(p, n, inc.cpu(), tracer.distortions_dataset.distortions_u.cpu(),
+                           tracer.distortions_dataset.distortions_e.cpu(), tidx.cpu(), tg, res, blocking=blk)
+    (ref * wgt).sum().backward()
+    for got, want, name in ((pts_leaf.grad.cpu(), p.grad, "points"), (nrm_leaf.grad.cpu(), n.grad, "normals")):
+        scale = want.abs().max()
+        err = (got - want).abs().max() / scale
+        assert err <= 2e-3, f"grad {name}: {err:.3e}"
+    # the corner rows carry the blocker-geometry gradient: compare them separately (they are tiny next to the rest)
+    rows = torch.tensor(HeliostatRayTracer._corner_rows(p.shape[1]))
+    gc, wc = pts_leaf.grad.cpu()[:, rows], p.grad[:, rows]
+    assert (gc - wc).abs().max() <= 5e-3 * wc.abs().max()
+
+
+def test_distant_heliostats_do_not_block():
+    """The benchmark-style field (5 m pitch, 50 m high target) has no shadowing: blocking on == blocking off."""
+    from artist_b200 import HeliostatRayTracer, build_synthetic_scenario
+
+    scenario, group = build_synthetic_scenario(16, number_of_rays=4, points_per_facet=(10, 10), device=DEV)
+    mask, tidx, inc = scenario.index_mapping(group)
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_incident_ray_directions(scenario.solar_tower.get_centers_of_target_areas(tidx), inc, mask)
+    a = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor([64, 64])).trace_rays(inc, mask, tidx)
+    b = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor([64, 64])).trace_rays(inc, mask, tidx)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], torch.ones_like(a[3]))

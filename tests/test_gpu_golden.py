@@ -85,3 +85,25 @@ def test_nurbs_against_reference_fixture(golden):
         ((pts * g["weight_points"].to(DEV)).sum() + (nrm * g["weight_normals"].to(DEV)).sum()).backward()
         scale = g["grad_control_points"].abs().max()
         assert (cp.grad.cpu() - g["grad_control_points"]).abs().max() <= 2e-5 * scale
+
+
+def test_blocking_against_reference_fixture(golden):
+    """The fused blocking path vs the flux the REAL reference produced with blocking_active=True."""
+    from artist_b200 import ops
+
+    g = golden["blocking"]
+    res = g["res"]
+    n = g["aligned_points"].shape[0]
+    opt = ops.TraceOptions(res_e=res[0], res_u=res[1], trig_mode=1, scatter_sigma=2.09e-3)
+    trig = torch.stack([torch.cos(g["dist_u"]), torch.sin(g["dist_u"]), torch.cos(g["dist_e"]), torch.sin(g["dist_e"])], -1)
+    f = g["field"]
+    aim = f["planar_centers"][g["target_idx"].long()].to(DEV)
+    bi = ops.BlockingInputs(corners=g["corners"].to(DEV), spans=g["spans"].to(DEV), normals=g["normals"].to(DEV),
+                            sample_to_blocker=torch.arange(n, dtype=torch.int32, device=DEV), aim_points=aim,
+                            target_radius=torch.full((n,), 6.0, device=DEV))
+    flux, ic, ot, bl = ops.trace(g["aligned_points"].to(DEV), g["aligned_normals"].to(DEV), g["incident"].to(DEV),
+                                 ops.pack_distortions(g["dist_u"].to(DEV), g["dist_e"].to(DEV)), g["target_idx"].to(DEV),
+                                 _targets(f), opt, trig=trig.contiguous().to(DEV), blocking=bi)
+    want = g["batch100"]
+    assert (flux.cpu() - want["flux"]).abs().max() <= 2e-4 * want["flux"].max()
+    assert (bl.cpu() - want["blocking"]).abs().max() <= 2.5e-3 and torch.equal(ot.cpu(), want["on_target"])

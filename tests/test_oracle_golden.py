@@ -79,3 +79,19 @@ def test_sampler_and_sun(golden):
     du, de = O.sun_distortions(3, 5, 2, 7)
     assert torch.equal(du, s["u"]) and torch.equal(de, s["e"])
     assert torch.equal(torch.rand(3), s["next_rand"]), "global RNG side effect of get_distortions must match"
+
+
+@pytest.mark.parametrize("batch_size", [100, 4])
+def test_blocking_trace_bit_exact(golden, batch_size):
+    """blocking_active=True: per-batch primitive filter (the LBVH's result set) + soft mask, bit for bit."""
+    g = golden["blocking"]
+    tg = _targets(g["field"])
+    c, s, n = O.blocking_primitives(g["aligned_points"])
+    assert torch.equal(c, g["corners"][..., :3]) and torch.equal(s, g["spans"][..., :3]) and torch.equal(n, g["normals"][..., :3])
+    blk = dict(corners=g["corners"], spans=g["spans"], normals=g["normals"], sample_to_blocker=torch.arange(9))
+    flux, ic, ot, bl = O.trace_rays(g["aligned_points"], g["aligned_normals"], g["incident"], g["dist_u"], g["dist_e"],
+                                    g["target_idx"], tg, g["res"], batch_size=batch_size, blocking=blk)
+    want = g[f"batch{batch_size}"]
+    assert torch.equal(flux, want["flux"]) and torch.equal(bl, want["blocking"])
+    assert torch.equal(ic, want["intercept"]) and torch.equal(ot, want["on_target"])
+    assert want["blocking"].min() < 0.2, "fixture must contain real shadowing"
