@@ -43,6 +43,7 @@ struct TraceParams {
     float fx_scale;     // fixed-point scale (counts per unit of flux)
     float fx_inv;       // 1 / fx_scale (signed)
     float sigma;        // scatter sigma used for the window margin
+    PackedIdentities ident;  // 1, -0, -1 as run-time values (see common.cuh, packed arithmetic)
 };
 
 // Window of the bitmap held in shared memory, in (iu, ie) index space.
@@ -59,6 +60,9 @@ constexpr int kWindowSampleStride = 8;
 #endif
 #ifndef AB200_WIN_KB
 #define AB200_WIN_KB 224   // shared-memory bitmap window per CTA in the one-CTA-per-sample mode
+#endif
+#ifndef AB200_PACKED_RAYS
+#define AB200_PACKED_RAYS 1     // fast loops process two rays per iteration with fp32x2 (FFMA2) arithmetic
 #endif
 #ifndef AB200_RAY_UNROLL
 #define AB200_RAY_UNROLL 1
@@ -399,6 +403,169 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
     cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; cnt_blk_out = cnt_blk; fell_back_out = fell_back; n_irregular_out = n_irr;
 }
 
+// Packed variant of the fast loop: two rays of a point per iteration in fp32x2 registers (FFMA2), which halves the
+// issue slots of the floating-point part.  Per element the operations and roundings are exactly those of the scalar
+// loop (strict products/sums are identity-FMAs, see common.cuh), so the results are bit-identical to it.
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
+__device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h,
+                                                      int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
+                                                      int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
+                                                      int& n_irregular_out) {
+    const int tid = threadIdx.x;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
+    const Packed K(prm.ident);
+    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
+    const float fxs = prm.fx_scale;
+    const float e_lim = (float)E, u_lim = (float)U;
+    int cnt_lam = 0, cnt_int = 0, cnt_blk = 0, n_irr = 0;
+    bool fell_back = false;
+
+    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+        PointCtx pc;
+        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        if (!point_regular(pc)) { n_irr += R; continue; }
+        const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
+        const float2* dp = dist + p;
+        float2 da = __ldcs(dp), db = (R > 1) ? __ldcs(dp + P) : make_float2(0.f, 0.f);
+        for (int r = 0; r < R; r += 2) {
+            const bool two = (r + 1 < R);
+            const float2 d0 = da, d1 = db;
+            dp += 2 * (size_t)P;
+            if (r + 2 < R) da = __ldcs(dp);
+            if (r + 3 < R) db = __ldcs(dp + P);
+            float2 cu, su, ce, se;
+            if (TRIG == AB200_TRIG_TABLE) {
+                const float4 ta = __ldg(trig + (size_t)r * P + p);
+                const float4 tb = two ? __ldg(trig + (size_t)(r + 1) * P + p) : ta;
+                cu = make_float2(ta.x, tb.x); su = make_float2(ta.y, tb.y); ce = make_float2(ta.z, tb.z); se = make_float2(ta.w, tb.w);
+            } else {
+                sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
+                sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
+            }
+            // scatter: d = M(e,u) r   ((-su) * r1 == su * (-r1), (-se) * r2 == se * (-r2) exactly)
+            const float2 m10 = K.mul(ce, su), m11 = K.mul(ce, cu), m20 = K.mul(se, su), m21 = K.mul(se, cu);
+            const float2 dx = K.add(K.mul(cu, bc2(pc.r0)), K.mul(su, bc2(-pc.r1)));
+            const float2 dy = K.add(K.add(K.mul(m10, bc2(pc.r0)), K.mul(m11, bc2(pc.r1))), K.mul(se, bc2(-pc.r2)));
+            const float2 dz = K.add(K.add(K.mul(m20, bc2(pc.r0)), K.mul(m21, bc2(pc.r1))), K.mul(ce, bc2(pc.r2)));
+            const float2 a = K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
+            const bool reg0 = angles_regular<TRIG>(d0.x, d0.y) && cosine_regular(a.x);
+            const bool reg1 = two && angles_regular<TRIG>(d1.x, d1.y) && cosine_regular(a.y);
+            n_irr += (!reg0) + (two && !reg1);
+            const float2 t = div_regular2(bc2(pc.num), a, K);
+            const float2 X = K.add(bc2(pc.o0), K.mul(dx, t));
+            const float2 Z = K.add(bc2(pc.o2), K.mul(dz, t));
+            const float2 te = K.sub(K.add(X, bc2(T.half_w)), bc2(T.c0));
+            const float2 tu = K.sub(K.add(Z, bc2(T.half_h)), bc2(T.c2));
+            // exact constant-divisor quotients (const_div): q0 = te*rw; r = te - q0*w; q = q0 + r*rw
+            const float2 qe0 = K.mul(te, bc2(T.rw)), qu0 = K.mul(tu, bc2(T.rh));
+            const float2 be0 = K.mul(pfma(pfma(qe0, bc2(-T.w), te), bc2(T.rw), qe0), bc2(T.em1));
+            const float2 bu0 = K.mul(pfma(pfma(qu0, bc2(-T.h), tu), bc2(T.rh), qu0), bc2(T.um1));
+            const bool valid0 = reg0 && (a.x < 0.0f) && (0.0f <= be0.x) && (be0.x <= T.em1) && (0.0f <= bu0.x) && (bu0.x <= T.um1);
+            const bool valid1 = reg1 && (a.y < 0.0f) && (0.0f <= be0.y) && (be0.y <= T.em1) && (0.0f <= bu0.y) && (bu0.y <= T.um1);
+            float2 lam = K.mul(a, bc2(-mag));                       // mag * (-a)
+            lam.x = valid0 ? lam.x : 0.0f; lam.y = valid1 ? lam.y : 0.0f;
+            float2 inten;
+            if (BLK) {
+                float2 blocked = make_float2(0.f, 0.f);
+                if (bmask) {
+                    if (reg0) blocked.x = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.x, dy.x, dz.x);
+                    if (reg1) blocked.y = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.y, dy.y, dz.y);
+                }
+                cnt_blk += (reg0 && blocked.x < 1e-3f) + (reg1 && blocked.y < 1e-3f);
+                inten = K.mul(K.mul(K.mul(lam, K.sub(K.one, blocked)), bc2(ome)), bc2(refl));
+            } else {
+                inten = K.mul(K.mul(lam, bc2(ome)), bc2(refl));
+            }
+            float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
+            if (DBG) {
+                const size_t q = ((size_t)h * R + r) * P + p;
+                if (reg0) {
+                    if (prm.a.dbg_be) prm.a.dbg_be[q] = valid0 ? be.x : T.em1;
+                    if (prm.a.dbg_bu) prm.a.dbg_bu[q] = valid0 ? bu.x : 0.0f;
+                    if (prm.a.dbg_t) prm.a.dbg_t[q] = valid0 ? t.x : 0.0f;
+                    if (prm.a.dbg_lambert) prm.a.dbg_lambert[q] = lam.x;
+                }
+                if (reg1) {
+                    if (prm.a.dbg_be) prm.a.dbg_be[q + P] = valid1 ? be.y : T.em1;
+                    if (prm.a.dbg_bu) prm.a.dbg_bu[q + P] = valid1 ? bu.y : 0.0f;
+                    if (prm.a.dbg_t) prm.a.dbg_t[q + P] = valid1 ? t.y : 0.0f;
+                    if (prm.a.dbg_lambert) prm.a.dbg_lambert[q + P] = lam.y;
+                }
+            }
+            cnt_lam += (lam.x > 0.0f) + (lam.y > 0.0f);
+            cnt_int += (inten.x > 0.0f) + (inten.y > 0.0f);
+            // splat weights (valid rays have 0 <= be <= E-1, 0 <= bu <= U-1).  floor() and the integer pixel index come
+            // from one round-down add of 2^23 (FMA pipe) instead of FRND + F2I (XU pipe): for 0 <= x < 2^23 the sum's
+            // low mantissa bits ARE floor(x).
+            const float kMagic = 8388608.0f;
+            const float2 me = make_float2(__fadd_rd(be.x, kMagic), __fadd_rd(be.y, kMagic));
+            const float2 mu = make_float2(__fadd_rd(bu.x, kMagic), __fadd_rd(bu.y, kMagic));
+            const float2 fe = K.sub(me, bc2(kMagic)), fu = K.sub(mu, bc2(kMagic));
+            const float2 fe1 = K.add(fe, K.one), fu1 = K.add(fu, K.one);
+            const float2 wle = K.sub(fe1, be), wlu = K.sub(fu1, bu), whe = K.sub(be, fe), whu = K.sub(bu, fu);
+            const bool go0 = valid0 && (fe1.x < e_lim) && (fu1.x < u_lim);
+            const bool go1 = valid1 && (fe1.y < e_lim) && (fu1.y < u_lim);
+            float2 v1, v2, v3, v4;   // tap values (fp32 accumulate) or 2^23 + round(scaled tap value) (fixed point)
+            if (FP32ACC) {
+                v1 = K.mul(K.mul(wle, whu), inten); v2 = K.mul(K.mul(whe, whu), inten);
+                v3 = K.mul(K.mul(whe, wlu), inten); v4 = K.mul(K.mul(wle, wlu), inten);
+            } else {
+                float2 sc = K.mul(inten, bc2(fxs));
+                sc.x = fabsf(sc.x); sc.y = fabsf(sc.y);
+                const float2 ahi = K.mul(whu, sc), alo = K.mul(wlu, sc);
+                v1 = pfma(wle, ahi, bc2(kMagic)); v2 = pfma(whe, ahi, bc2(kMagic));
+                v3 = pfma(whe, alo, bc2(kMagic)); v4 = pfma(wle, alo, bc2(kMagic));
+            }
+#pragma unroll
+            for (int lane = 0; lane < 2; ++lane) {
+                const bool go = lane ? go1 : go0;
+                if (!go) continue;
+                const int ie = (int)(__float_as_uint(lane ? me.y : me.x) & 0x007fffffu);
+                const int iu = (int)(__float_as_uint(lane ? mu.y : mu.x) & 0x007fffffu);
+                const int cex = ie - fc.e0, cux = iu - fc.u0;
+                const bool fast = ((unsigned)cex < (unsigned)fc.wwm1) && ((unsigned)cux < (unsigned)fc.whm1);
+                const float a1 = lane ? v1.y : v1.x, a2 = lane ? v2.y : v2.x, a3 = lane ? v3.y : v3.x, a4 = lane ? v4.y : v4.x;
+                if (FP32ACC) {
+                    if (fast) {
+                        float* b = fc.win_f + cux * fc.ww + cex;
+                        atomicAdd(b + fc.ww, a1); atomicAdd(b + fc.ww + 1, a2); atomicAdd(b + 1, a3); atomicAdd(b, a4);
+                    } else {
+                        float* row_hi = fc.out_f + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                        float* row_lo = row_hi + E;
+                        atomicAdd(row_hi, a1); atomicAdd(row_hi + 1, a2); atomicAdd(row_lo + 1, a3); atomicAdd(row_lo, a4);
+                    }
+                } else {
+                    const unsigned q1 = __float_as_uint(a1) & 0x007fffffu, q2 = __float_as_uint(a2) & 0x007fffffu;
+                    const unsigned q3 = __float_as_uint(a3) & 0x007fffffu, q4 = __float_as_uint(a4) & 0x007fffffu;
+                    if (fast) {
+                        unsigned* b = fc.win_u + cux * fc.ww + cex;
+                        atomicAdd(b + fc.ww, q1); atomicAdd(b + fc.ww + 1, q2); atomicAdd(b + 1, q3); atomicAdd(b, q4);
+                    } else {
+                        fell_back = true;
+                        atomicMin(fc.fb_box + 0, U - 2 - iu); atomicMax(fc.fb_box + 1, U - 1 - iu);
+                        atomicMin(fc.fb_box + 2, ie); atomicMax(fc.fb_box + 3, ie + 1);
+                        const bool e_in0 = (unsigned)cex < (unsigned)fc.ww, e_in1 = (unsigned)(cex + 1) < (unsigned)fc.ww;
+                        const bool u_in0 = (unsigned)cux < (unsigned)fc.wh, u_in1 = (unsigned)(cux + 1) < (unsigned)fc.wh;
+                        unsigned* g_hi = out_u + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                        unsigned* g_lo = g_hi + E;
+                        unsigned* b = fc.win_u + cux * fc.ww + cex;
+                        if (u_in1 && e_in0) atomicAdd(b + fc.ww, q1); else atomicAdd(g_hi, q1);
+                        if (u_in1 && e_in1) atomicAdd(b + fc.ww + 1, q2); else atomicAdd(g_hi + 1, q2);
+                        if (u_in0 && e_in1) atomicAdd(b + 1, q3); else atomicAdd(g_lo + 1, q3);
+                        if (u_in0 && e_in0) atomicAdd(b, q4); else atomicAdd(g_lo, q4);
+                    }
+                }
+            }
+        }
+    }
+    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; cnt_blk_out = cnt_blk; fell_back_out = fell_back; n_irregular_out = n_irr;
+}
+
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_fwd_kernel(const TraceParams prm) {
@@ -460,7 +627,11 @@ trace_fwd_kernel(const TraceParams prm) {
     bool fell_back = false;
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
+#if AB200_PACKED_RAYS
+        fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
+#else
         fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
+#endif
         if (__syncthreads_or(n_irr != 0)) {   // never with physical inputs: the generic loop picks up the skipped rays
             int c1 = 0, c2 = 0, c3 = 0;
             bool fb = false;
@@ -964,7 +1135,8 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
     const double imax = (k < 0 ? -k : k) * 1.01;   // |lambert cosine| <= 1 for unit vectors (+1% slack)
     const double rays = (double)a->n_points * (double)a->n_rays;
     if (imax > 0.0) {
-        const double s = (4294967295.0 - 2.0 * rays) / (rays * imax) * (1.0 - 1e-6);
+        double s = (4294967295.0 - 2.0 * rays) / (rays * imax) * (1.0 - 1e-6);
+        if (s * imax > 4194304.0) s = 4194304.0 / imax;   // one tap < 2^22: lets the packed loop round with a magic-number FMA
         prm.fx_scale = (float)s;
         prm.fx_inv = (float)((k < 0 ? -1.0 : 1.0) / (double)prm.fx_scale);
     } else {
@@ -972,6 +1144,7 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
         prm.fx_inv = 0.f;
     }
     prm.sigma = a->scatter_sigma > 0.f ? a->scatter_sigma : 2.5e-3f;
+    prm.ident.one = 1.0f; prm.ident.negzero = -0.0f; prm.ident.negone = -1.0f;
 }
 
 template <int THREADS, int TRIG>
