@@ -10,7 +10,7 @@ import os
 
 from ._build import LIB_PATH
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 TRIG_SINCOSF, TRIG_TABLE, TRIG_POLY = 0, 1, 2
 FLAG_FP32_ACCUM = 1
 
@@ -45,13 +45,14 @@ class TraceArgs(C.Structure):
         ("scatter_sigma", C.c_float), ("trig_mode", C.c_int32), ("flags", C.c_int32),
         ("flux", c_float_p), ("intercept", c_float_p), ("on_target", c_float_p), ("blocking", c_float_p),
         ("dbg_be", c_float_p), ("dbg_bu", c_float_p), ("dbg_t", c_float_p), ("dbg_lambert", c_float_p),
-        ("stats", C.c_void_p),
+        ("stats", C.c_void_p), ("orientations", c_float_p),
     ]
 
 
 class TraceBwdArgs(C.Structure):
     _fields_ = [("fwd", TraceArgs), ("grad_flux", c_float_p), ("grad_flux_stride", C.c_int64),
-                ("grad_points", c_float_p), ("grad_normals", c_float_p), ("grad_prims", c_float_p)]
+                ("grad_points", c_float_p), ("grad_normals", c_float_p), ("grad_prims", c_float_p),
+                ("grad_orientations", c_float_p)]
 
 
 class NurbsArgs(C.Structure):

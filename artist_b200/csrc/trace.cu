@@ -43,6 +43,7 @@ struct TraceParams {
     float fx_scale;     // fixed-point scale (counts per unit of flux)
     float fx_inv;       // 1 / fx_scale (signed)
     float sigma;        // scatter sigma used for the window margin
+    int self_zero;      // 1: every CTA clears the part of its bitmap row outside the window itself (no memset pass)
     PackedIdentities ident;  // 1, -0, -1 as run-time values (see common.cuh, packed arithmetic)
 };
 
@@ -77,12 +78,11 @@ constexpr int kRayUnroll = AB200_RAY_UNROLL;
 // the window (misses take the global path); it only decides how many rays take the fast path.
 // ---------------------------------------------------------------------------------------------
 template <int THREADS>
-__device__ void place_window(Window& win_out, const TraceParams& prm, const TargetCtx& T, int h, int p_begin, int p_end,
-                             float i0, float i1, float i2, float* red /* [6*32] */, Window* win_sh) {
+__device__ void place_window(Window& win_out, const TraceParams& prm, const TargetCtx& T, const PointSrc& src, int p_begin,
+                             int p_end, float i0, float i1, float i2, float* red /* [6*32] */, Window* win_sh) {
     const int tid = threadIdx.x;
-    const int P = prm.a.n_points;
-    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
     const float inf = __int_as_float(0x7f800000);
     float emin = inf, emax = -inf, umin = inf, umax = -inf, tmax = 0.f, cmin = inf;
     {
@@ -92,6 +92,8 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
         float4 oa = make_float4(0, 0, 0, 0), na = oa, ob = oa, nb = oa;
         if (has_a) { oa = __ldg(pts + pa); na = __ldg(nrm + pa); }
         if (has_b) { ob = __ldg(pts + pb); nb = __ldg(nrm + pb); }
+        orient_point(src, oa, na);
+        orient_point(src, ob, nb);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (!(k == 0 ? has_a : has_b)) continue;
@@ -107,7 +109,9 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
         }
         for (int p = pb + THREADS * kWindowSampleStride; p < p_end; p += THREADS * kWindowSampleStride) {  // very large P only
             PointCtx pc;
-            make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
             float be, bu, t, cosi;
             const bool ok = T.planar ? centre_planar(T, pc, be, bu, t, cosi) : centre_cylinder(T, pc, be, bu, t, cosi);
             if (ok && be == be && bu == bu && fabsf(be) < 1e6f && fabsf(bu) < 1e6f) {
@@ -192,13 +196,13 @@ __device__ __forceinline__ bool angles_regular(float u, float e) {
 __device__ __forceinline__ bool cosine_regular(float a) { return !(a < 0.0f) || (a < -1e-18f && a > -1e18f); }
 
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR, bool BLK>
-__device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h, int p_begin,
+__device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h, int p_begin,
                                          int p_end, float i0, float i1, float i2, int& cnt_lam_out, int& cnt_int_out,
                                          int& cnt_blk_out, bool& fell_back_out) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
-    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
     const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
     const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
     unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
@@ -209,7 +213,11 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
         PointCtx pc;
-        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        {
+            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
+        }
         const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         const float2* dp = dist + p;
         float2 d_next = __ldcs(dp);
@@ -288,14 +296,14 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
 // Branch-free fast loop for planar targets: polynomial (or table) trig, range-guarded exact divisions, everything
 // predicated; irregular rays are only counted (n_irregular) and left to the generic loop.
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
-__device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h,
+__device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h,
                                                      int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
                                                      int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
                                                      int& n_irregular_out) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
-    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
     const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
     const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
     unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
@@ -307,7 +315,11 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
         PointCtx pc;
-        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        {
+            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
+        }
         if (!point_regular(pc)) { n_irr += R; continue; }
         const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         const float2* dp = dist + p;
@@ -407,14 +419,14 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
 // issue slots of the floating-point part.  Per element the operations and roundings are exactly those of the scalar
 // loop (strict products/sums are identity-FMAs, see common.cuh), so the results are bit-identical to it.
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
-__device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, int h,
+__device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h,
                                                       int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
                                                       int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
                                                       int& n_irregular_out) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
-    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
     const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
     const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
     unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
@@ -427,7 +439,11 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
         PointCtx pc;
-        make_point(pc, T, i0, i1, i2, __ldg(pts + p), __ldg(nrm + p));
+        {
+            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
+        }
         if (!point_regular(pc)) { n_irr += R; continue; }
         const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         const float2* dp = dist + p;
@@ -578,7 +594,8 @@ trace_fwd_kernel(const TraceParams prm) {
     __shared__ int cnt_sh[3];
     __shared__ int fallback_sh;
     __shared__ int fb_box[4];
-    __shared__ BlockPrim blk_sh[kMaxBlockCandidates];   // output rows / columns touched by global-path taps: row min, row max, col min, col max
+    __shared__ BlockPrim blk_sh[kMaxBlockCandidates];
+    __shared__ float O_sh[16];
 
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
@@ -591,21 +608,49 @@ trace_fwd_kernel(const TraceParams prm) {
     if (tid == 0) {
         load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
         cnt_sh[0] = 0; cnt_sh[1] = 0; cnt_sh[2] = 0; fallback_sh = 0;
+        // output rows / columns touched by global-path taps: row min, row max, col min, col max
         fb_box[0] = 1 << 30; fb_box[1] = -1; fb_box[2] = 1 << 30; fb_box[3] = -1;
     }
+    if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
     __syncthreads();
+    PointSrc src;
+    src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    src.O = prm.a.orientations ? O_sh : nullptr;
     const TargetCtx T = T_sh;
     const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
                 i2 = __ldg(prm.a.incident + 4 * h + 2);
 
     Window W;
-    place_window<THREADS>(W, prm, T, h, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    place_window<THREADS>(W, prm, T, src, p_begin, p_end, i0, i1, i2, red, &win_sh);
     const int wcells = W.ww * W.wh;
     for (int i = tid; i < wcells; i += THREADS) win_u[i] = 0u;
-    __syncthreads();
-
     float* out_f = prm.a.flux + (size_t)h * U * E;
     unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
+    if (prm.self_zero) {
+        // clear the pixels the window flush will not overwrite (the global-path taps need zeros to add to); output
+        // rows of the window: [U - u0 - wh, U - 1 - u0], columns [e0, e0 + ww)
+        const int r_lo = U - W.u0 - W.wh, r_hi = U - 1 - W.u0, c_lo = W.e0, c_hi = W.e0 + W.ww;
+        if ((E & 3) == 0) {
+            const int e4 = E >> 2;
+            float4* o4 = reinterpret_cast<float4*>(out_f);
+            for (int i = tid; i < U * e4; i += THREADS) {
+                const int row = i / e4, c = (i - row * e4) << 2;
+                if (row < r_lo || row > r_hi || c + 4 <= c_lo || c >= c_hi) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (c + k < c_lo || c + k >= c_hi) out_f[(size_t)row * E + c + k] = 0.f;
+                }
+            }
+        } else {
+            for (int i = tid; i < U * E; i += THREADS) {
+                const int row = i / E, c = i - row * E;
+                if (row < r_lo || row > r_hi || c < c_lo || c >= c_hi) out_f[i] = 0.f;
+            }
+        }
+    }
+    __syncthreads();
+
     FwdCtx fc;
     fc.win_u = win_u; fc.win_f = win_f; fc.out_f = out_f;
     fc.e0 = W.e0; fc.u0 = W.u0; fc.ww = W.ww; fc.wh = W.wh;
@@ -628,20 +673,20 @@ trace_fwd_kernel(const TraceParams prm) {
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
-        fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
+        fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #else
-        fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
+        fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #endif
         if (__syncthreads_or(n_irr != 0)) {   // never with physical inputs: the generic loop picks up the skipped rays
             int c1 = 0, c2 = 0, c3 = 0;
             bool fb = false;
-            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb);
+            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb);
             cnt_lam += c1; cnt_int += c2; cnt_blk += c3; fell_back = fell_back || fb;
         }
     } else if (T.planar) {
-        fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
     } else {
-        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, BLK>(prm, T, fc, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
     }
 
     // ---- epilogue: counters, window flush -----------------------------------------------------
@@ -768,13 +813,13 @@ struct BwdCtx {
 };
 
 template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR, bool BLK>
-__device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, int h, int p_begin,
-                                         int p_end, float i0, float i1, float i2, float* __restrict__ grad_points,
-                                         float* __restrict__ grad_normals) {
+__device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, const PointSrc& src, int h,
+                                         int p_begin, int p_end, float i0, float i1, float i2, float* __restrict__ grad_points,
+                                         float* __restrict__ grad_normals, float* gori_acc) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
-    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
     const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
     const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
     const float mag = prm.a.ray_magnitude;
@@ -783,7 +828,9 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
     const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
-        const float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+        const float4 o_raw = __ldg(pts + p), n_raw = __ldg(nrm + p);
+        float4 o4 = o_raw, n4 = n_raw;
+        orient_point(src, o4, n4);
         PointCtx pc;
         make_point(pc, T, i0, i1, i2, o4, n4);
         float go0 = 0.f, go1 = 0.f, go2 = 0.f;   // planar: grad origin (world); cylindrical: grad origin (cylinder frame)
@@ -895,29 +942,32 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
         const float gn2 = -2.0f * (pc.dot * gr2 + grn * i2);
         float4* gpp = reinterpret_cast<float4*>(grad_points) + (size_t)h * P + p;
         float4* gnp = reinterpret_cast<float4*>(grad_normals) + (size_t)h * P + p;
+        float4 gp4 = make_float4(gp0, gp1, gp2, 0.f), gn4 = make_float4(gn0, gn1, gn2, 0.f);
         if (ONLY_IRREGULAR) {   // add to what the fast loop wrote for this point
             if (touched) {
+                orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
                 const float4 a4 = *gpp, b4 = *gnp;
-                *gpp = make_float4(a4.x + gp0, a4.y + gp1, a4.z + gp2, 0.f);
-                *gnp = make_float4(b4.x + gn0, b4.y + gn1, b4.z + gn2, 0.f);
+                *gpp = make_float4(a4.x + gp4.x, a4.y + gp4.y, a4.z + gp4.z, a4.w + gp4.w);
+                *gnp = make_float4(b4.x + gn4.x, b4.y + gn4.y, b4.z + gn4.z, b4.w + gn4.w);
             }
         } else {
-            *gpp = make_float4(gp0, gp1, gp2, 0.f);
-            *gnp = make_float4(gn0, gn1, gn2, 0.f);
+            orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
+            *gpp = gp4;
+            *gnp = gn4;
         }
     }
 }
 
 // Branch-light fast loop for planar targets (see fwd_rays_planar_fast).
 template <int THREADS, int TRIG, bool BLK>
-__device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, int h,
-                                                     int p_begin, int p_end, float i0, float i1, float i2,
-                                                     float* __restrict__ grad_points, float* __restrict__ grad_normals,
-                                                     int& n_irregular_out) {
+__device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc,
+                                                     const PointSrc& src, int h, int p_begin, int p_end, float i0, float i1,
+                                                     float i2, float* __restrict__ grad_points,
+                                                     float* __restrict__ grad_normals, float* gori_acc, int& n_irregular_out) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
-    const float4* pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
     const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
     const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
     const float mag = prm.a.ray_magnitude;
@@ -928,7 +978,9 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
     int n_irr = 0;
 
     for (int p = p_begin + tid; p < p_end; p += THREADS) {
-        const float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+        const float4 o_raw = __ldg(pts + p), n_raw = __ldg(nrm + p);
+        float4 o4 = o_raw, n4 = n_raw;
+        orient_point(src, o4, n4);
         PointCtx pc;
         make_point(pc, T, i0, i1, i2, o4, n4);
         float go0 = 0.f, go1 = 0.f, go2 = 0.f, gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;
@@ -1007,8 +1059,10 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
         const float gn0 = -2.0f * (pc.dot * gr0 + grn * i0);
         const float gn1 = -2.0f * (pc.dot * gr1 + grn * i1);
         const float gn2 = -2.0f * (pc.dot * gr2 + grn * i2);
-        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = make_float4(go0, go1, go2, 0.f);
-        reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = make_float4(gn0, gn1, gn2, 0.f);
+        float4 gp4 = make_float4(go0, go1, go2, 0.f), gn4 = make_float4(gn0, gn1, gn2, 0.f);
+        orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
+        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = gp4;
+        reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = gn4;
     }
     n_irregular_out = n_irr;
 }
@@ -1016,12 +1070,14 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
 template <int THREADS, int TRIG, bool BLK>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
-                 float* __restrict__ grad_points, float* __restrict__ grad_normals, float* __restrict__ grad_prims) {
+                 float* __restrict__ grad_points, float* __restrict__ grad_normals, float* __restrict__ grad_prims,
+                 float* __restrict__ grad_orientations) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* win_g = reinterpret_cast<float*>(smem_raw);
     __shared__ TargetCtx T_sh;
     __shared__ Window win_sh;
     __shared__ float red[6 * 32];
+    __shared__ float O_sh[16];
     __shared__ BlockPrim blk_sh[BLK ? kMaxBlockCandidates : 1];
     __shared__ int blk_rows_sh[BLK ? kMaxBlockCandidates : 1];
 
@@ -1034,13 +1090,22 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     const int p_end = min(P, p_begin + prm.pts_per_chunk);
 
     if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
+    if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
     __syncthreads();
     const TargetCtx T = T_sh;
     const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
                 i2 = __ldg(prm.a.incident + 4 * h + 2);
+    PointSrc src;
+    src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    src.O = prm.a.orientations ? O_sh : nullptr;
+    float gori[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) gori[q] = 0.f;
+    float* gori_acc = (grad_orientations && src.O) ? gori : nullptr;
 
     Window W;
-    place_window<THREADS>(W, prm, T, h, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    place_window<THREADS>(W, prm, T, src, p_begin, p_end, i0, i1, i2, red, &win_sh);
     const float* gf = grad_flux + (size_t)h * grad_stride;
     {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
         const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
@@ -1066,13 +1131,31 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     }
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
-        bwd_rays_planar_fast<THREADS, TRIG, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, n_irr);
+        bwd_rays_planar_fast<THREADS, TRIG, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
         if (__syncthreads_or(n_irr != 0))   // never with physical inputs (each thread re-reads only its own points)
-            bwd_rays<THREADS, TRIG, true, false, true, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+            bwd_rays<THREADS, TRIG, true, false, true, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
     } else if (T.planar) {
-        bwd_rays<THREADS, TRIG, true, false, false, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+        bwd_rays<THREADS, TRIG, true, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
     } else {
-        bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals);
+        bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
+    }
+    if (gori_acc) {
+        // dL/dO rows 0..2 of this sample: warp shuffle tree, then the warps' partial sums in index order (fixed order);
+        // the gradient window in shared memory is dead by now and serves as scratch
+        __syncthreads();
+        const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+            const float v = warp_sumf(gori[q]);
+            if (lane == 0) win_g[warp * 12 + q] = v;
+        }
+        __syncthreads();
+        if (tid < 12) {
+            float sum = 0.f;
+            for (int w = 0; w < nwarps; ++w) sum += win_g[w * 12 + tid];
+            float* dst = grad_orientations + (size_t)h * 16 + tid;
+            if (prm.split == 1) *dst = sum; else atomicAdd(dst, sum);   // caller zeroes the buffer (row 3 stays 0)
+        }
     }
 }
 
@@ -1145,6 +1228,7 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
     }
     prm.sigma = a->scatter_sigma > 0.f ? a->scatter_sigma : 2.5e-3f;
     prm.ident.one = 1.0f; prm.ident.negzero = -0.0f; prm.ident.negone = -1.0f;
+    prm.self_zero = 0;
 }
 
 template <int THREADS, int TRIG>
@@ -1178,17 +1262,17 @@ static cudaError_t launch_fwd_trig(const TraceParams& prm, const LaunchPlan& pl,
 
 template <int THREADS, int TRIG>
 static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                              long long gstride, float* gpts, float* gnrm, float* gprims) {
+                              long long gstride, float* gpts, float* gnrm, float* gprims, float* gori) {
     if (prm.a.blockers.n_blockers > 0) {
         auto kern = trace_bwd_kernel<THREADS, TRIG, true>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
         if (e != cudaSuccess) return e;
-        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims);
+        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori);
     } else {
         auto kern = trace_bwd_kernel<THREADS, TRIG, false>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
         if (e != cudaSuccess) return e;
-        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims);
+        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori);
     }
     note_launch();
     return cudaGetLastError();
@@ -1196,11 +1280,11 @@ static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cuda
 
 template <int THREADS>
 static cudaError_t launch_bwd_trig(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                                   long long gstride, float* gpts, float* gnrm, float* gprims) {
+                                   long long gstride, float* gpts, float* gnrm, float* gprims, float* gori) {
     switch (prm.a.trig_mode) {
-        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims);
-        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims);
-        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims);
+        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori);
+        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori);
+        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori);
     }
 }
 
@@ -1215,16 +1299,21 @@ extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t ue = (size_t)a->res_u * a->res_e;
     // rows not traced by this rank stay zero; traced rows are accumulated into / overwritten
-    AB200_CUDA_TRY(cudaMemsetAsync(a->flux, 0, (size_t)a->n_samples * ue * sizeof(float), st));
-    AB200_CUDA_TRY(cudaMemsetAsync(a->intercept, 0, (size_t)a->n_samples * sizeof(float), st));
-    AB200_CUDA_TRY(cudaMemsetAsync(a->on_target, 0, (size_t)a->n_samples * sizeof(float), st));
-    AB200_CUDA_TRY(cudaMemsetAsync(a->blocking, 0, (size_t)a->n_samples * sizeof(float), st));
-    if (a->n_local == 0 || a->n_samples == 0) return AB200_OK;
     const LaunchPlan pl = make_plan(a->n_local, a->n_points, kFwdThreadsLarge);
-    TraceParams prm;
-    fill_params(prm, a, pl);
     const bool dbg = a->dbg_be || a->dbg_bu || a->dbg_t || a->dbg_lambert;
     const bool fp32acc = (a->flags & AB200_FLAG_FP32_ACCUM) != 0;
+    // one CTA per sample and every sample traced here: each CTA clears its own bitmap row (no N*U*E memset pass)
+    const bool self_zero = pl.split == 1 && a->n_local == a->n_samples && !fp32acc && a->n_samples > 0;
+    if (!self_zero) {
+        AB200_CUDA_TRY(cudaMemsetAsync(a->flux, 0, (size_t)a->n_samples * ue * sizeof(float), st));
+        AB200_CUDA_TRY(cudaMemsetAsync(a->intercept, 0, (size_t)a->n_samples * sizeof(float), st));
+        AB200_CUDA_TRY(cudaMemsetAsync(a->on_target, 0, (size_t)a->n_samples * sizeof(float), st));
+        AB200_CUDA_TRY(cudaMemsetAsync(a->blocking, 0, (size_t)a->n_samples * sizeof(float), st));
+    }
+    if (a->n_local == 0 || a->n_samples == 0) return AB200_OK;
+    TraceParams prm;
+    fill_params(prm, a, pl);
+    prm.self_zero = self_zero ? 1 : 0;
     cudaError_t e = (pl.threads == kFwdThreadsLarge) ? launch_fwd_trig<kFwdThreadsLarge>(prm, pl, st, dbg, fp32acc)
                                                      : launch_fwd_trig<512>(prm, pl, st, dbg, fp32acc);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_fwd launch failed: %s", cudaGetErrorString(e));
@@ -1260,8 +1349,8 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
     fill_params(prm, a, pl);
     const long long gstride = b->grad_flux_stride >= 0 ? b->grad_flux_stride : (long long)a->res_u * a->res_e;
     cudaError_t e = (pl.threads == kBwdThreadsLarge)
-                        ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims)
-                        : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims);
+                        ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations)
+                        : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_bwd launch failed: %s", cudaGetErrorString(e));
     return AB200_OK;
 }

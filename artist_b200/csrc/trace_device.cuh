@@ -120,6 +120,51 @@ __device__ __forceinline__ void make_point(PointCtx& pc, const TargetCtx& T, flo
     }
 }
 
+// Where a CTA's surface points come from: already aligned [P] float4 rows, or - when the caller passes the sample's
+// orientation (ab200_trace_args::orientations) - the un-aligned rows, which are rotated here exactly as
+// ab200_align_fwd does (out_j = sum_k d_k * O[j][k] accumulated as an FMA chain over k, like the CPU GEMM of
+// heliostat_group_rigid_body.py:217-222), so the aligned [N,P,4] tensors never exist in HBM.
+struct PointSrc {
+    const float4* pts;
+    const float4* nrm;
+    const float* O;   // shared memory, row-major 4x4, or nullptr
+};
+
+__device__ __forceinline__ float4 apply_orientation(const float* O, const float4 d) {
+    float4 r;
+    r.x = fmaf(d.w, O[3], fmaf(d.z, O[2], fmaf(d.y, O[1], smul(d.x, O[0]))));
+    r.y = fmaf(d.w, O[7], fmaf(d.z, O[6], fmaf(d.y, O[5], smul(d.x, O[4]))));
+    r.z = fmaf(d.w, O[11], fmaf(d.z, O[10], fmaf(d.y, O[9], smul(d.x, O[8]))));
+    r.w = 0.f;   // the trace never reads the homogeneous component
+    return r;
+}
+
+__device__ __forceinline__ void orient_point(const PointSrc& s, float4& o, float4& n) {
+    if (s.O) { o = apply_orientation(s.O, o); n = apply_orientation(s.O, n); }
+}
+
+// Backward of orient_point for one surface point: (gp, gn) arrive as gradients w.r.t. the ALIGNED point / normal and
+// leave as gradients w.r.t. the un-aligned rows (g @ O); `acc` (12 registers, rows 0..2 of dL/dO, or nullptr) collects
+// sum_p g_j * d_k over the thread's points.  d, e are the un-aligned point / normal.
+__device__ __forceinline__ void orient_point_backward(const PointSrc& s, const float4 d, const float4 e, float4& gp,
+                                                      float4& gn, float* acc) {
+    if (!s.O) return;
+    if (acc) {
+        const float g[3] = {gp.x, gp.y, gp.z}, m[3] = {gn.x, gn.y, gn.z};
+        const float dd[4] = {d.x, d.y, d.z, d.w}, ee[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j * 4 + k] += g[j] * dd[k] + m[j] * ee[k];
+    }
+    const float* O = s.O;
+    const float4 a = gp, b = gn;
+    gp = make_float4(a.x * O[0] + a.y * O[4] + a.z * O[8], a.x * O[1] + a.y * O[5] + a.z * O[9],
+                     a.x * O[2] + a.y * O[6] + a.z * O[10], a.x * O[3] + a.y * O[7] + a.z * O[11]);
+    gn = make_float4(b.x * O[0] + b.y * O[4] + b.z * O[8], b.x * O[1] + b.y * O[5] + b.z * O[9],
+                     b.x * O[2] + b.y * O[6] + b.z * O[10], b.x * O[3] + b.y * O[7] + b.z * O[11]);
+}
+
 // Scatter: d = M(e,u) * r   (geometry/transforms.py:67-74, heliostat_ray_tracer.py:547-552)
 struct Scatter {
     float cu, su, ce, se;

@@ -28,13 +28,65 @@ class HeliostatGroup:
         self.kinematics = Kinematics()
         self.number_of_active_heliostats = 0
         self.active_heliostats_mask = torch.zeros(self.number_of_heliostats, device=device)
-        self.active_surface_points = surface_points
-        self.active_surface_normals = surface_normals
+        self._asp, self._asn, self._pending_alignment = surface_points, surface_normals, None
         self.active_canting = canting
         self.active_facet_translations = facet_translations
         self.active_nurbs_control_points = nurbs_control_points
         self._reflection_inputs = None
         self._active_rows = None
+
+    # ``active_surface_points`` / ``active_surface_normals`` after an alignment (``heliostat_group_rigid_body.py:217-222,
+    # 265-270``) are LAZY: ``align_surfaces_with_*`` only records (un-aligned rows, orientations) and the ray tracer
+    # consumes that pair directly (the rotation is fused into the trace kernels, ``ab200_trace_args::orientations``).
+    # Reading either attribute materialises both aligned ``[N,P,4]`` tensors once (``ab200_align_fwd``) - same values,
+    # same autograd graph as the eager reference.
+    @property
+    def active_surface_points(self) -> torch.Tensor:
+        if self._asp is None:
+            self._materialise_alignment()
+        return self._asp
+
+    @active_surface_points.setter
+    def active_surface_points(self, value: torch.Tensor) -> None:
+        if self._asn is None and self._pending_alignment is not None:
+            self._materialise_alignment()
+        self._asp = value
+        self._pending_alignment = None
+
+    @property
+    def active_surface_normals(self) -> torch.Tensor:
+        if self._asn is None:
+            self._materialise_alignment()
+        return self._asn
+
+    @active_surface_normals.setter
+    def active_surface_normals(self, value: torch.Tensor) -> None:
+        if self._asp is None and self._pending_alignment is not None:
+            self._materialise_alignment()
+        self._asn = value
+        self._pending_alignment = None
+
+    def _set_active_surface(self, points: torch.Tensor, normals: torch.Tensor) -> None:
+        self._asp, self._asn, self._pending_alignment = points, normals, None
+
+    def _set_pending_alignment(self, points: torch.Tensor, normals: torch.Tensor, orientations: torch.Tensor) -> None:
+        self._asp, self._asn, self._pending_alignment = None, None, (points, normals, orientations)
+
+    def _materialise_alignment(self) -> None:
+        from .. import ops
+
+        points, normals, orientations = self._pending_alignment
+        self._asp, self._asn = ops.align_surfaces(points, normals, orientations)
+
+    def _fused_alignment(self):
+        """``(points, normals, orientations)`` if the alignment has not been materialised, else None."""
+        if self._pending_alignment is not None and self._asp is None and self._asn is None:
+            return self._pending_alignment
+        return None
+
+    def _active_points_per_heliostat(self) -> int:
+        fused = self._fused_alignment()
+        return int((fused[0] if fused is not None else self.active_surface_points).shape[1])
 
     # The reference materialises ``preferred_reflection_directions`` ([N,P,4]) inside trace_rays; the fused
     # kernel never needs it in memory, so it is evaluated only if somebody reads the attribute.
@@ -42,8 +94,8 @@ class HeliostatGroup:
     def preferred_reflection_directions(self) -> torch.Tensor:
         if self._reflection_inputs is None:
             return torch.empty(self.number_of_heliostats, 4, device=self.positions.device)
-        incident, normals = self._reflection_inputs
-        incident = incident.unsqueeze(1)
+        incident = self._reflection_inputs.unsqueeze(1)
+        normals = self.active_surface_normals
         return incident - 2 * torch.sum(incident * normals, dim=-1, keepdim=True) * normals
 
     @preferred_reflection_directions.setter
@@ -84,8 +136,7 @@ class HeliostatGroup:
                                            active_heliostats_mask.long())
             self._active_rows = rows
             pick = lambda t: t.index_select(0, rows.to(t.device))
-        self.active_surface_points = pick(self.surface_points)
-        self.active_surface_normals = pick(self.surface_normals)
+        self._set_active_surface(pick(self.surface_points), pick(self.surface_normals))
         self.active_canting = pick(self.canting)
         self.active_facet_translations = pick(self.facet_translations)
         self.active_nurbs_control_points = pick(self.nurbs_control_points)

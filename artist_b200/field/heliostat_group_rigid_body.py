@@ -27,9 +27,9 @@ class HeliostatGroupRigidBody(HeliostatGroup):
             actuator_parameters_optimizable=actuator_parameters_optimizable, device=device)
 
     def _apply(self, orientations: torch.Tensor) -> None:
-        # points @ O^T, normals @ O^T in one pass (:217-222, :265-270)
-        self.active_surface_points, self.active_surface_normals = ops.align_surfaces(
-            self.active_surface_points, self.active_surface_normals, orientations)
+        # points @ O^T, normals @ O^T (:217-222, :265-270) - recorded, not executed: the ray tracer fuses the rotation
+        # into its kernels; reading active_surface_points / _normals materialises them (HeliostatGroup properties)
+        self._set_pending_alignment(self.active_surface_points, self.active_surface_normals, orientations)
 
     def align_surfaces_with_incident_ray_directions(self, aim_points, incident_ray_directions, active_heliostats_mask,
                                                     device=None) -> None:

@@ -124,7 +124,7 @@ def pack_distortions(distortions_u: torch.Tensor, distortions_e: torch.Tensor) -
 
 
 def _trace_args(points, normals, incident, distortions, trig, target_idx, targets: TargetTensors, opt: TraceOptions,
-                local_rows, flux, intercept, on_target, blocking, dbg=None, blk=None) -> _lib.TraceArgs:
+                local_rows, flux, intercept, on_target, blocking, dbg=None, blk=None, orientations=None) -> _lib.TraceArgs:
     n, p, _ = points.shape
     r = distortions.shape[1]
     a = _lib.TraceArgs()
@@ -153,6 +153,7 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
     if dbg is not None:
         a.dbg_be, a.dbg_bu, a.dbg_t, a.dbg_lambert = (_p(d) for d in dbg)
     a.stats = _p(trace_stats)
+    a.orientations = _p(orientations)
     return a
 
 
@@ -187,10 +188,14 @@ def _prepare_blocking(bi: BlockingInputs, opt: TraceOptions, n: int, dev):
 class _TraceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, bi, b_corners,
-                b_spans, b_normals):
+                b_spans, b_normals, orientations):
         points, normals, incident = _f32(points, "points"), _f32(normals, "normals"), _f32(incident, "incident")
         distortions = _f32(distortions, "distortions")
         target_idx = _i32(target_idx, "target_area_indices")
+        if orientations is not None:
+            orientations = _f32(orientations, "orientations")
+            if orientations.shape != (points.shape[0], 4, 4):
+                raise _lib.Ab200Error("orientations must be [N,4,4] with one matrix per row of points")
         n = points.shape[0]
         dev = points.device
         flux = torch.empty(n, opt.res_u, opt.res_e, device=dev)
@@ -201,9 +206,9 @@ class _TraceFn(torch.autograd.Function):
         if bi is not None:
             blk = (bi, *_prepare_blocking(bi, opt, n, dev))
         args = _trace_args(points, normals, incident, distortions, trig, target_idx, targets, opt, local_rows,
-                           flux, intercept, on_target, blocking, blk=blk)
+                           flux, intercept, on_target, blocking, blk=blk, orientations=orientations)
         _lib.call("ab200_trace_fwd", C.byref(args), _stream())
-        ctx.save_for_backward(points, normals, incident, distortions, trig, target_idx, local_rows,
+        ctx.save_for_backward(points, normals, incident, distortions, trig, target_idx, local_rows, orientations,
                               *(blk[1:] if blk is not None else ()))
         ctx.targets, ctx.opt, ctx.bi = targets, opt, bi
         ctx.blocker_shapes = None if bi is None else (b_corners.shape, b_spans.shape, b_normals.shape)
@@ -213,8 +218,8 @@ class _TraceFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_flux, _gi, _go, _gb):
         saved = ctx.saved_tensors
-        points, normals, incident, distortions, trig, target_idx, local_rows = saved[:7]
-        blk = None if ctx.bi is None else (ctx.bi, *saved[7:10])
+        points, normals, incident, distortions, trig, target_idx, local_rows, orientations = saved[:8]
+        blk = None if ctx.bi is None else (ctx.bi, *saved[8:11])
         if not g_flux.is_cuda:
             raise _lib.Ab200Error("grad_flux must be a CUDA tensor")
         u, e = g_flux.shape[1], g_flux.shape[2]
@@ -227,13 +232,17 @@ class _TraceFn(torch.autograd.Function):
         g_normals = torch.empty_like(normals)
         b = _lib.TraceBwdArgs()
         b.fwd = _trace_args(points, normals, incident, distortions, trig, target_idx, ctx.targets, ctx.opt, local_rows,
-                            None, None, None, None, blk=blk)
+                            None, None, None, None, blk=blk, orientations=orientations)
         b.grad_flux, b.grad_points, b.grad_normals = _p(g_flux), _p(g_points), _p(g_normals)
         b.grad_flux_stride = g_stride
         g_corners = g_spans = g_bnormals = None
         need_blockers = blk is not None and any(ctx.needs_input_grad[10:13])
         g_prims = torch.zeros(blk[1].shape[0], 12, device=points.device) if need_blockers else None
         b.grad_prims = _p(g_prims)
+        g_ori = None
+        if orientations is not None and ctx.needs_input_grad[13]:
+            g_ori = torch.zeros_like(orientations)
+        b.grad_orientations = _p(g_ori)
         _lib.call("ab200_trace_bwd", C.byref(b), _stream())
         if need_blockers:
             cs, ss, ns = ctx.blocker_shapes
@@ -244,23 +253,28 @@ class _TraceFn(torch.autograd.Function):
             g_spans[:, 1, :3] = g_prims[:, 6:9]
             g_bnormals = torch.zeros(ns, device=points.device)
             g_bnormals[:, :3] = g_prims[:, 9:12]
-        return g_points, g_normals, None, None, None, None, None, None, None, None, g_corners, g_spans, g_bnormals
+        return (g_points, g_normals, None, None, None, None, None, None, None, None, g_corners, g_spans, g_bnormals,
+                g_ori)
 
 
 def trace(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,
           local_rows: torch.Tensor | None = None, trig: torch.Tensor | None = None,
-          blocking: BlockingInputs | None = None):
+          blocking: BlockingInputs | None = None, orientations: torch.Tensor | None = None):
     """Fused forward trace -> ``(flux[N,U,E], intercept[N], on_target[N], blocking[N])``; differentiable
-    w.r.t. ``points`` and ``normals`` (and, with ``blocking``, the blockers' corners / spans / normals)."""
+    w.r.t. ``points`` and ``normals`` (and, with ``blocking``, the blockers' corners / spans / normals).
+
+    ``orientations`` ([N,4,4], optional) fuses the alignment ``rows @ O^T`` into the kernels: ``points`` / ``normals``
+    are then the UN-aligned rows, the aligned tensors never exist in HBM, and the flux is differentiable w.r.t. the
+    orientations too (``ab200_trace_args::orientations``)."""
     if trig is not None:
         trig = _f32(trig, "trig")
     if local_rows is not None:
         local_rows = _i32(local_rows, "local_rows")
     if blocking is None:
         return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, None,
-                              None, None, None)
+                              None, None, None, orientations)
     return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, blocking,
-                          blocking.corners, blocking.spans, blocking.normals)
+                          blocking.corners, blocking.spans, blocking.normals, orientations)
 
 
 def trace_debug(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,
@@ -287,22 +301,48 @@ class _PerTargetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, bitmaps, target_idx, n_targets):
         bitmaps = _f32(bitmaps, "bitmaps_per_heliostat")
+        target_idx_object = target_idx
         target_idx = _i32(target_idx, "target_area_indices")
         n, u, e = bitmaps.shape
         out = torch.empty(n_targets, u, e, device=bitmaps.device)
         _lib.call("ab200_bitmaps_per_target", _p(bitmaps), _p(target_idx), n, n_targets, u, e, _p(out), _stream())
         ctx.save_for_backward(target_idx)
         ctx.n = n
+        ctx.target_idx_object = target_idx_object
         return out
 
     @staticmethod
     def backward(ctx, g):
         (target_idx,) = ctx.saved_tensors
-        if g.shape[0] == 1:
-            # a single target: every sample sees the same [U,E] gradient - hand an expanded (stride-0) view to
-            # the trace backward, which reads it in place
-            return g.expand(ctx.n, -1, -1), None, None
+        # every sample aims at ONE target (the common case): all samples see the same [U,E] gradient - hand an
+        # expanded (stride-0) view to the trace backward, which reads it in place instead of an [N,U,E] gather
+        t = 0 if g.shape[0] == 1 else _uniform_target(ctx.target_idx_object)
+        if t is not None:
+            return g[t].expand(ctx.n, -1, -1), None, None
         return g.index_select(0, target_idx.long()), None, None
+
+
+_uniform_cache: dict = {}
+
+
+def _uniform_target(target_idx: torch.Tensor) -> int | None:
+    """The single target index all samples share, or None.  Costs one device->host read per distinct index tensor
+    OBJECT and version (id + weak reference, so a recycled address or an in-place update is never mistaken for a hit)."""
+    import weakref
+
+    hit = _uniform_cache.get(id(target_idx))
+    if hit is not None and hit[0]() is target_idx and hit[1] == target_idx._version:
+        return hit[2]
+    if target_idx.numel() == 0:
+        result = None
+    else:
+        lo, hi = torch.aminmax(target_idx)
+        lo_hi = torch.stack([lo, hi]).tolist()
+        result = int(lo_hi[0]) if lo_hi[0] == lo_hi[1] else None
+    if len(_uniform_cache) > 64:
+        _uniform_cache.clear()
+    _uniform_cache[id(target_idx)] = (weakref.ref(target_idx), target_idx._version, result)
+    return result
 
 
 def bitmaps_per_target(bitmaps, target_idx, n_targets: int):

@@ -51,7 +51,7 @@ class HeliostatRayTracer:
         self.light_source = scenario.light_sources.light_source_list[0]
         self.distortions_dataset = DistortionsDataset(
             light_source=self.light_source,
-            number_of_points_per_heliostat=heliostat_group.active_surface_points.shape[1],
+            number_of_points_per_heliostat=heliostat_group._active_points_per_heliostat(),
             number_of_active_heliostats=heliostat_group.number_of_active_heliostats, random_seed=random_seed)
         self.distortions_sampler = RestrictedDistributedSampler(
             number_of_samples=len(self.distortions_dataset),
@@ -59,7 +59,7 @@ class HeliostatRayTracer:
             world_size=world_size, rank=rank)
         self.distortions_loader = _BatchLoader(self.distortions_dataset, self.distortions_sampler, batch_size)
         self.bitmap_resolution = bitmap_resolution
-        device = heliostat_group.active_surface_points.device
+        device = heliostat_group.surface_points.device
         self._device = device
         self._packed = ops.pack_distortions(self.distortions_dataset.distortions_u, self.distortions_dataset.distortions_e)
         n = len(self.distortions_dataset)
@@ -89,7 +89,7 @@ class HeliostatRayTracer:
         group = self.heliostat_group
         assert torch.equal(group.active_heliostats_mask, active_heliostats_mask), (
             "Some heliostats were not aligned and cannot be raytraced.")
-        group._reflection_inputs = (incident_ray_directions, group.active_surface_normals)
+        group._reflection_inputs = incident_ray_directions
         sigma = getattr(self.light_source, "scatter_sigma", 0.0)
         opt = ops.TraceOptions(
             res_e=int(self.bitmap_resolution[indices.unbatched_bitmap_e]),
@@ -97,9 +97,13 @@ class HeliostatRayTracer:
             ray_magnitude=float(self.ray_magnitude), ray_extinction_factor=ray_extinction_factor,
             mirror_reflectivity=mirror_reflectivity, scatter_sigma=sigma)
         blocking = self._blocking_inputs(target_area_indices) if self.blocking_active else None
-        return ops.trace(group.active_surface_points, group.active_surface_normals, incident_ray_directions,
-                         self._packed, target_area_indices, self._targets, opt, local_rows=self._local_rows,
-                         blocking=blocking)
+        fused = group._fused_alignment()
+        if fused is not None:   # alignment not materialised: the kernels rotate the un-aligned rows themselves
+            points, normals, orientations = fused
+        else:
+            points, normals, orientations = group.active_surface_points, group.active_surface_normals, None
+        return ops.trace(points, normals, incident_ray_directions, self._packed, target_area_indices, self._targets,
+                         opt, local_rows=self._local_rows, blocking=blocking, orientations=orientations)
 
     # ---- blocking (artist/raytracing/blocking.py, heliostat_ray_tracer.py:159-183,292-301,445-480) -----------------
     @staticmethod
@@ -122,7 +126,12 @@ class HeliostatRayTracer:
                 active_rows = getattr(g, "_active_rows", None)
                 if active_rows is None:     # all-ones mask: sample i is heliostat i
                     active_rows = torch.arange(g.number_of_heliostats, device=c.device)
-                aligned = g.active_surface_points.index_select(1, rows)
+                fused = g._fused_alignment()
+                if fused is not None:   # only the 4 corner rows are rotated; the full alignment stays lazy
+                    aligned, _ = ops.align_surfaces(fused[0].index_select(1, rows), fused[1].index_select(1, rows),
+                                                    fused[2])
+                else:
+                    aligned = g.active_surface_points.index_select(1, rows)
                 # a heliostat activated several times contributes the geometry of its last sample
                 c = c.index_copy(0, active_rows.long(), aligned)
                 if g is self.heliostat_group:

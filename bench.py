@@ -134,7 +134,7 @@ class Workload:
         g.align_surfaces_with_incident_ray_directions(self.aim, self.inc, self.mask)
         self.tracer = HeliostatRayTracer(self.scenario, g, blocking_active=False, random_seed=7 + rank,
                                          bitmap_resolution=torch.tensor(RES))
-        self.opt = torch.optim.Adam([self.cp], lr=1e-6)
+        self.opt = torch.optim.Adam([self.cp], lr=1e-6, fused=True)
         self.p = g.surface_points.shape[1]
         self.rays_per_step = n * self.p * RAYS
         # pinned host mirrors for the end-to-end leg

@@ -30,7 +30,7 @@ extern "C" {
 #define AB200_ECUDA (-2)    /* a CUDA runtime call or launch failed */
 #define AB200_ELIMIT (-3)   /* size beyond what the kernels support */
 
-#define AB200_ABI_VERSION 1
+#define AB200_ABI_VERSION 2
 
 /* trig source for the per-ray scatter rotation (artist/geometry/transforms.py:52-55) */
 #define AB200_TRIG_SINCOSF 0 /* libdevice sincosf (default) */
@@ -116,6 +116,11 @@ typedef struct ab200_trace_args {
     float* dbg_lambert;      /* [N,R,P] */
     int64_t* stats;          /* optional diagnostics (NULL to skip), accumulated: [0] threads that used the global fallback
                                 path, [1] sum of window cells, [2] CTAs */
+    const float* orientations; /* optional [N,4,4] (NULL = `points`/`normals` are already aligned): fuses
+                                HeliostatGroupRigidBody.align_surfaces_with_* (heliostat_group_rigid_body.py:217-222,
+                                265-270) into the trace - `points`/`normals` are then the UN-aligned active surface
+                                rows and every CTA applies `row @ O^T` itself (same FMA chain as ab200_align_fwd), so
+                                the aligned [N,P,4] tensors are never written to or re-read from HBM */
 } ab200_trace_args;
 
 int32_t ab200_trace_fwd(const ab200_trace_args* args, void* stream);
@@ -136,6 +141,8 @@ typedef struct ab200_trace_bwd_args {
     float* grad_normals;      /* out [N,P,4] (w component 0) */
     float* grad_prims;        /* blocking only, may be NULL: [H,12] d/d(corner0, span_u, span_v, normal), ACCUMULATED with
                                  float atomics (caller zeroes it) */
+    float* grad_orientations; /* fwd.orientations only, may be NULL: [N,4,4] dL/dO (caller zeroes it; row 3 stays 0).
+                                 With fwd.orientations set, grad_points / grad_normals are w.r.t. the UN-aligned rows. */
 } ab200_trace_bwd_args;
 
 int32_t ab200_trace_bwd(const ab200_trace_bwd_args* args, void* stream);

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(_lib.EXPORTS) == set(declared), "ctypes binding and header disagree"
-    assert _lib.lib().ab200_abi_version() == 1
+    assert _lib.lib().ab200_abi_version() == _lib.ABI_VERSION == 2
     assert _lib.lib().ab200_error_string(-1) == b"invalid argument"
 
 
@@ -59,7 +59,7 @@ def test_argument_validation_without_gpu():
     assert lib.ab200_trace_fwd(ctypes.byref(a), None) == -1
     assert b"abi_version" in lib.ab200_last_error_detail()
     n = _lib.NurbsArgs()
-    n.abi_version, n.n_surfaces, n.n_facets, n.n_eval, n.degree_u, n.degree_v = 1, 1, 1, 1, 5, 3
+    n.abi_version, n.n_surfaces, n.n_facets, n.n_eval, n.degree_u, n.degree_v = _lib.ABI_VERSION, 1, 1, 1, 5, 3
     assert lib.ab200_nurbs_fwd(ctypes.byref(n), None) == -1
     assert b"degree" in lib.ab200_last_error_detail()
 

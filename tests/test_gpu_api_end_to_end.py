@@ -109,3 +109,33 @@ def test_motor_position_gradients_and_mask_assertion():
     blocked = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor([64, 64]))
     fb, _, _, bl = blocked.trace_rays(inc, mask, tidx)      # default blocking_active=True works (no shadowing here)
     assert torch.equal(fb, flux) and (bl == 1).all()
+
+
+def test_lazy_alignment_fused_and_materialised_paths_agree():
+    """``align_surfaces_with_*`` only records the orientation; the tracer fuses the rotation into its kernels.
+    Reading ``active_surface_points`` materialises the aligned tensors: same flux bit for bit, and the aligned
+    tensors equal an explicit ``align_surfaces`` call."""
+    from artist_b200 import HeliostatRayTracer, build_synthetic_scenario, ops
+
+    scenario, group = build_synthetic_scenario(4, number_of_rays=5, points_per_facet=(10, 10), device=DEV)
+    mask, tidx, inc = scenario.index_mapping(group)
+    aim = scenario.solar_tower.get_centers_of_target_areas(tidx)
+    group.activate_heliostats(mask)
+    raw_p, raw_n = group.active_surface_points, group.active_surface_normals
+    group.align_surfaces_with_incident_ray_directions(aim, inc, mask)
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor([64, 64]))
+    pending = group._fused_alignment()
+    assert pending is not None and pending[0] is raw_p                     # nothing aligned in memory yet
+    fused = tracer.trace_rays(inc, mask, tidx)
+    assert group._fused_alignment() is not None
+    ap, an = ops.align_surfaces(raw_p, raw_n, pending[2])
+    assert torch.equal(group.active_surface_points, ap) and torch.equal(group.active_surface_normals, an)
+    assert group._fused_alignment() is None                                # materialised by the reads above
+    eager = tracer.trace_rays(inc, mask, tidx)
+    for a, b in zip(fused, eager):
+        assert torch.equal(a, b)
+    refl = group.preferred_reflection_directions
+    assert refl.shape == an.shape and torch.isfinite(refl).all()
+    # a fresh activation drops the recorded alignment without running it
+    group.activate_heliostats(mask)
+    assert group._fused_alignment() is None and group.active_surface_points is raw_p

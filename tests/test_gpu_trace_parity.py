@@ -183,3 +183,82 @@ def test_irregular_rays_take_the_generic_path():
     (flux * wgt.to(dev)).sum().backward()
     assert (pc.grad.cpu() - gp).abs().max() <= 5e-4 * gp.abs().max()
     assert (nc.grad.cpu() - gn).abs().max() <= 5e-4 * gn.abs().max()
+
+
+@pytest.mark.parametrize("pattern,n", [((0,), 4), ((1, 0), 5)])
+def test_fused_alignment_equals_align_then_trace(pattern, n):
+    """``orientations`` given: the kernels rotate the un-aligned rows themselves.  Forward bit-identical to
+    align_surfaces -> trace; gradients (un-aligned points / normals, orientations) equal to the two-step autograd
+    chain within fp32 summation-order noise."""
+    from artist_b200 import ops
+
+    case = cases.make_case(n=n, points_per_facet=(12, 12), rays=6, target_pattern=pattern)
+    res = (96, 96)
+    dev = torch.device("cuda:0")
+    opt = ops.TraceOptions(res_e=res[0], res_u=res[1], trig_mode=2, scatter_sigma=2.09e-3)
+    dist = ops.pack_distortions(case["dist_u"].to(dev), case["dist_e"].to(dev))
+    tg = _dev_targets(case["targets"], dev)
+    inc, tidx = case["incident"].to(dev), case["target_idx"].to(dev)
+    torch.manual_seed(3)
+    wgt = torch.rand(n, res[1], res[0], device=dev)
+
+    def leaves():
+        return (case["surface_points"].to(dev).requires_grad_(True), case["surface_normals"].to(dev).requires_grad_(True),
+                case["orientations"].to(dev).requires_grad_(True))
+
+    p1, n1, o1 = leaves()
+    ap, an = ops.align_surfaces(p1, n1, o1)
+    assert torch.equal(ap.detach().cpu(), case["points"])          # alignment itself is bit-exact vs the oracle
+    out1 = ops.trace(ap, an, inc, dist, tidx, tg, opt)
+    (out1[0] * wgt).sum().backward()
+    p2, n2, o2 = leaves()
+    out2 = ops.trace(p2, n2, inc, dist, tidx, tg, opt, orientations=o2)
+    (out2[0] * wgt).sum().backward()
+    for a, b in zip(out1, out2):
+        assert torch.equal(a, b)
+    for g1, g2, name in ((p1.grad, p2.grad, "points"), (n1.grad, n2.grad, "normals"), (o1.grad, o2.grad, "orientations")):
+        scale = g1.abs().max()
+        assert scale > 0, name
+        assert (g1 - g2).abs().max() <= 2e-5 * scale, f"{name}: {(g1 - g2).abs().max() / scale:.2e}"
+
+
+def test_one_cta_per_sample_mode_clears_its_own_bitmap():
+    """>= 2 x SM-count samples: one CTA per sample, no memset pass - every pixel outside the shared-memory window is
+    cleared by the CTA itself.  The output buffer is poisoned first; results must equal the split (memset) mode."""
+    from artist_b200 import ops
+
+    base = cases.make_case(n=4, points_per_facet=(8, 8), rays=3, target_pattern=(0, 1))
+    dev = torch.device("cuda:0")
+    reps = 80                                                    # 320 samples >= 2 * 148
+    rep = lambda x: x.to(dev).repeat(reps, *([1] * (x.dim() - 1))).contiguous()
+    pts, nrm, inc, tidx = rep(base["points"]), rep(base["normals"]), rep(base["incident"]), rep(base["target_idx"])
+    dist = ops.pack_distortions(rep(base["dist_u"]), rep(base["dist_e"]))
+    tg = _dev_targets(base["targets"], dev)
+    for res in ((64, 48), (50, 37)):                             # float4 and scalar clearing paths
+        opt = ops.TraceOptions(res_e=res[0], res_u=res[1], trig_mode=2, scatter_sigma=2.09e-3)
+        poison = torch.full((reps * 4 * res[0] * res[1] + 64,), float("nan"), device=dev)
+        del poison                                               # the caching allocator hands the block to `flux`
+        big = ops.trace(pts, nrm, inc, dist, tidx, tg, opt)
+        small = ops.trace(pts[:4], nrm[:4], inc[:4], dist[:4], tidx[:4], tg, opt)
+        assert torch.isfinite(big[0]).all()
+        for a, b in zip(big, small):
+            assert torch.equal(a[:4], b) and torch.equal(a[-4:], b)
+
+
+def test_per_target_backward_uniform_and_mixed_targets():
+    """get_bitmaps_per_target backward: with ONE shared target the trace backward reads a stride-0 view of the
+    [U,E] gradient; with mixed targets the gather path - both equal the dense autograd result."""
+    from artist_b200 import ops
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    flux = torch.rand(6, 16, 20, device=dev)
+    wgt = torch.rand(3, 16, 20, device=dev)
+    for tidx in (torch.tensor([1] * 6, device=dev), torch.tensor([0, 2, 2, 1, 0, 2], device=dev)):
+        f = flux.clone().requires_grad_(True)
+        (ops.bitmaps_per_target(f, tidx, 3) * wgt).sum().backward()
+        assert torch.equal(f.grad, wgt[tidx.long()])
+        tidx[0] = 2                                               # in-place update must not hit a stale cache entry
+        f = flux.clone().requires_grad_(True)
+        (ops.bitmaps_per_target(f, tidx, 3) * wgt).sum().backward()
+        assert torch.equal(f.grad, wgt[tidx.long()])
