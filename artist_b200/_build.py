@@ -12,6 +12,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libartist_b200.so")
+# tuning only: AB200_LIB points at a pre-built variant of the library (tools/build_variants.sh)
+LIB_OVERRIDE = os.environ.get("AB200_LIB")
 SOURCES = ["trace.cu", "nurbs.cu", "kinematics.cu", "blocking.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -42,6 +44,10 @@ def _source_digest() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if sources changed; return its path."""
+    if LIB_OVERRIDE:
+        if not os.path.exists(LIB_OVERRIDE):
+            raise RuntimeError(f"AB200_LIB={LIB_OVERRIDE} does not exist")
+        return LIB_OVERRIDE
     os.makedirs(LIB_DIR, exist_ok=True)
     stamp = os.path.join(LIB_DIR, "build.stamp")
     digest = _source_digest()

@@ -8,7 +8,9 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._build import LIB_PATH
+from ._build import LIB_OVERRIDE, LIB_PATH as _DEFAULT_LIB_PATH
+
+LIB_PATH = LIB_OVERRIDE or _DEFAULT_LIB_PATH
 
 ABI_VERSION = 2
 TRIG_SINCOSF, TRIG_TABLE, TRIG_POLY = 0, 1, 2

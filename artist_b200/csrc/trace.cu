@@ -43,6 +43,7 @@ struct TraceParams {
     float fx_scale;     // fixed-point scale (counts per unit of flux)
     float fx_inv;       // 1 / fx_scale (signed)
     float sigma;        // scatter sigma used for the window margin
+    int simple_counts;  // 1: magnitude, (1 - extinction), reflectivity >= 1e-6: lambert > 0 and intensity > 0 hold exactly for valid rays
     int self_zero;      // 1: every CTA clears the part of its bitmap row outside the window itself (no memset pass)
     PackedIdentities ident;  // 1, -0, -1 as run-time values (see common.cuh, packed arithmetic)
 };
@@ -57,7 +58,7 @@ constexpr int kWindowSampleStride = 8;
 #define AB200_FWD_THREADS 1024
 #endif
 #ifndef AB200_BWD_THREADS
-#define AB200_BWD_THREADS 1024
+#define AB200_BWD_THREADS 768
 #endif
 #ifndef AB200_WIN_KB
 #define AB200_WIN_KB 224   // shared-memory bitmap window per CTA in the one-CTA-per-sample mode
@@ -77,21 +78,33 @@ constexpr int kRayUnroll = AB200_RAY_UNROLL;
 // grown by ~4 sigma of the sun shape projected onto the target.  Correctness never depends on
 // the window (misses take the global path); it only decides how many rays take the fast path.
 // ---------------------------------------------------------------------------------------------
+// the (un-oriented) rows of the two window-sample points of a thread: loaded early, so that their DRAM latency
+// overlaps the CTA's other start-up loads (target constants, orientation, incident direction)
+struct WindowSamples {
+    float4 oa, na, ob, nb;
+};
 template <int THREADS>
-__device__ void place_window(Window& win_out, const TraceParams& prm, const TargetCtx& T, const PointSrc& src, int p_begin,
-                             int p_end, float i0, float i1, float i2, float* red /* [6*32] */, Window* win_sh) {
+__device__ __forceinline__ void load_window_samples(WindowSamples& ws, const float4* pts, const float4* nrm, int p_begin, int p_end) {
+    const int pa = p_begin + threadIdx.x * kWindowSampleStride, pb = pa + THREADS * kWindowSampleStride;
+    ws.oa = ws.na = ws.ob = ws.nb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pa < p_end) { ws.oa = __ldg(pts + pa); ws.na = __ldg(nrm + pa); }
+    if (pb < p_end) { ws.ob = __ldg(pts + pb); ws.nb = __ldg(nrm + pb); }
+}
+
+template <int THREADS>
+__device__ void place_window(Window& win_out, const TraceParams& prm, const TargetCtx& T, const PointSrc& src,
+                             const WindowSamples& ws, int p_begin, int p_end, float i0, float i1, float i2,
+                             float* red /* [6*32] */, Window* win_sh) {
     const int tid = threadIdx.x;
     const float4* pts = src.pts;
     const float4* nrm = src.nrm;
     const float inf = __int_as_float(0x7f800000);
     float emin = inf, emax = -inf, umin = inf, umax = -inf, tmax = 0.f, cmin = inf;
     {
-        // every kWindowSampleStride-th point; both candidate loads are issued before any math (latency overlap)
+        // every kWindowSampleStride-th point; the two candidate rows were loaded by the caller before its first barrier
         const int pa = p_begin + tid * kWindowSampleStride, pb = pa + THREADS * kWindowSampleStride;
         const bool has_a = pa < p_end, has_b = pb < p_end;
-        float4 oa = make_float4(0, 0, 0, 0), na = oa, ob = oa, nb = oa;
-        if (has_a) { oa = __ldg(pts + pa); na = __ldg(nrm + pa); }
-        if (has_b) { ob = __ldg(pts + pb); nb = __ldg(nrm + pb); }
+        float4 oa = ws.oa, na = ws.na, ob = ws.ob, nb = ws.nb;
         orient_point(src, oa, na);
         orient_point(src, ob, nb);
 #pragma unroll
@@ -415,9 +428,26 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
     cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; cnt_blk_out = cnt_blk; fell_back_out = fell_back; n_irregular_out = n_irr;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+// a in (-1e18, -1e-18), i.e. front-facing AND regular: ONE unsigned range test on the bit pattern
+// (bits(-1e-18f) = 0xA19392EF, bits(-1e18f) = 0xDD5E0B6B; negative floats order like their bit patterns)
+__device__ __forceinline__ bool front_regular(float a) {
+    return (__float_as_uint(a) - 0xA19392F0u) < (0xDD5E0B6Bu - 0xA19392F0u);
+}
+
 // Packed variant of the fast loop: two rays of a point per iteration in fp32x2 registers (FFMA2), which halves the
 // issue slots of the floating-point part.  Per element the operations and roundings are exactly those of the scalar
 // loop (strict products/sums are identity-FMAs, see common.cuh), so the results are bit-identical to it.
+// Preconditions (checked by the caller): R even; and - unless BLK - ray_magnitude, (1 - extinction) and reflectivity
+// all >= 1e-6, so that "lambert > 0" and "intensity > 0" hold exactly for the valid rays (the factor counters then
+// count valid rays instead of comparing two floats per ray).
+// Integer ALU work is kept off the half-rate pipe where possible: validity is an unsigned compare of bit patterns
+// (0 <= x <= lim  <=>  bits(x) <= bits(lim) once -0 is excluded, which the +0 addend of the last product does),
+// pixel indices come from the magic-number add, and the on-bitmap test is implied by the window test.
+// The distortion pair of the NEXT iteration (also across the thread's point boundary) is always in flight, and the
+// next point's rows are prefetched into L2 one point ahead, so a point start costs one L2 hit instead of two serial
+// DRAM round trips.
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
 __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h,
                                                       int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
@@ -433,28 +463,53 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     const Packed K(prm.ident);
     const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
     const float fxs = prm.fx_scale;
-    const float e_lim = (float)E, u_lim = (float)U;
-    int cnt_lam = 0, cnt_int = 0, cnt_blk = 0, n_irr = 0;
-    bool fell_back = false;
+    const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
+    const unsigned kMagicBits = 0x4B000000u;   // bits(2^23)
+    const unsigned bias_e = kMagicBits + (unsigned)fc.e0, bias_u = kMagicBits + (unsigned)fc.u0;
+    const unsigned win_base = (unsigned)__cvta_generic_to_shared(fc.win_u), row_bytes = (unsigned)fc.ww * 4u;
+    // factor counters: valid rays = R * (regular points) - cnt_bad; invalid rays are rare, so the bookkeeping (and the
+    // irregularity flag, which implies invalid) lives in a rarely taken branch
+    int cnt_bad = 0, n_reg_points = 0, cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
+    bool fell_back = false, any_irr = false;
+    // the next distortion pair of this thread: +2P inside a point, then over to the first pair of its next point
+    const int n_pairs = (R + 1) >> 1;
+    const long long step_inner = 2 * (long long)P, step_last = (long long)THREADS - (long long)(n_pairs - 1) * 2 * (long long)P;
 
-    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+    int p = p_begin + tid;
+    float2 da = make_float2(0.f, 0.f), db = da;
+    const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
+    if (p < p_end) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+    for (; p < p_end; p += THREADS) {
+        const int pn = p + THREADS;
+        const bool more = pn < p_end;
+        if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
         PointCtx pc;
         {
             float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
             orient_point(src, o4, n4);
             make_point(pc, T, i0, i1, i2, o4, n4);
         }
-        if (!point_regular(pc)) { n_irr += R; continue; }
+        if (!point_regular(pc)) {   // never with physical inputs: the generic loop re-traces the whole point
+            any_irr = true;
+            nx += THREADS;
+            if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+            continue;
+        }
         const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
-        const float2* dp = dist + p;
-        float2 da = __ldcs(dp), db = (R > 1) ? __ldcs(dp + P) : make_float2(0.f, 0.f);
+        ++n_reg_points;
         for (int r = 0; r < R; r += 2) {
-            const bool two = (r + 1 < R);
+            const bool two = (r + 1 < R);   // an odd R leaves the second lane of the last pair idle
             const float2 d0 = da, d1 = db;
-            dp += 2 * (size_t)P;
-            if (r + 2 < R) da = __ldcs(dp);
-            if (r + 3 < R) db = __ldcs(dp + P);
+            {
+                const bool inner = r + 2 < R;
+                nx += inner ? step_inner : step_last;
+                if (inner || more) {
+                    da = __ldcs(nx);
+                    if (inner ? (r + 3 < R) : (R > 1)) db = __ldcs(nx + P);
+                }
+            }
             float2 cu, su, ce, se;
+            bool ang0 = true, ang1 = true;
             if (TRIG == AB200_TRIG_TABLE) {
                 const float4 ta = __ldg(trig + (size_t)r * P + p);
                 const float4 tb = two ? __ldg(trig + (size_t)(r + 1) * P + p) : ta;
@@ -462,6 +517,8 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             } else {
                 sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
                 sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
+                ang0 = fmaxf(fabsf(d0.x), fabsf(d0.y)) <= 0.785f;
+                ang1 = fmaxf(fabsf(d1.x), fabsf(d1.y)) <= 0.785f;
             }
             // scatter: d = M(e,u) r   ((-su) * r1 == su * (-r1), (-se) * r2 == se * (-r2) exactly)
             const float2 m10 = K.mul(ce, su), m11 = K.mul(ce, cu), m20 = K.mul(se, su), m21 = K.mul(se, cu);
@@ -469,37 +526,47 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             const float2 dy = K.add(K.add(K.mul(m10, bc2(pc.r0)), K.mul(m11, bc2(pc.r1))), K.mul(se, bc2(-pc.r2)));
             const float2 dz = K.add(K.add(K.mul(m20, bc2(pc.r0)), K.mul(m21, bc2(pc.r1))), K.mul(ce, bc2(pc.r2)));
             const float2 a = K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
-            const bool reg0 = angles_regular<TRIG>(d0.x, d0.y) && cosine_regular(a.x);
-            const bool reg1 = two && angles_regular<TRIG>(d1.x, d1.y) && cosine_regular(a.y);
-            n_irr += (!reg0) + (two && !reg1);
+            // regular = angles in the polynomial's range and (a >= 0  or  a in (-1e18, -1e-18)); irregular rays are
+            // left to the generic loop (same predicate there: angles_regular && cosine_regular)
+            const bool fr0 = front_regular(a.x), fr1 = front_regular(a.y);
+            const bool front0 = ang0 && fr0, front1 = two && ang1 && fr1;   // regular and front-facing: may be valid
             const float2 t = div_regular2(bc2(pc.num), a, K);
             const float2 X = K.add(bc2(pc.o0), K.mul(dx, t));
             const float2 Z = K.add(bc2(pc.o2), K.mul(dz, t));
             const float2 te = K.sub(K.add(X, bc2(T.half_w)), bc2(T.c0));
             const float2 tu = K.sub(K.add(Z, bc2(T.half_h)), bc2(T.c2));
-            // exact constant-divisor quotients (const_div): q0 = te*rw; r = te - q0*w; q = q0 + r*rw
+            // exact constant-divisor quotients (const_div): q0 = te*rw; r = te - q0*w; q = q0 + r*rw.  The last
+            // product adds +0 instead of -0: identical except that a -0 product becomes +0 (same validity, see above)
             const float2 qe0 = K.mul(te, bc2(T.rw)), qu0 = K.mul(tu, bc2(T.rh));
-            const float2 be0 = K.mul(pfma(pfma(qe0, bc2(-T.w), te), bc2(T.rw), qe0), bc2(T.em1));
-            const float2 bu0 = K.mul(pfma(pfma(qu0, bc2(-T.h), tu), bc2(T.rh), qu0), bc2(T.um1));
-            const bool valid0 = reg0 && (a.x < 0.0f) && (0.0f <= be0.x) && (be0.x <= T.em1) && (0.0f <= bu0.x) && (bu0.x <= T.um1);
-            const bool valid1 = reg1 && (a.y < 0.0f) && (0.0f <= be0.y) && (be0.y <= T.em1) && (0.0f <= bu0.y) && (bu0.y <= T.um1);
+            const float2 be0 = pfma(pfma(pfma(qe0, bc2(-T.w), te), bc2(T.rw), qe0), bc2(T.em1), bc2(0.0f));
+            const float2 bu0 = pfma(pfma(pfma(qu0, bc2(-T.h), tu), bc2(T.rh), qu0), bc2(T.um1), bc2(0.0f));
+            const bool valid0 = front0 && (__float_as_uint(be0.x) <= em1_bits) && (__float_as_uint(bu0.x) <= um1_bits);
+            const bool valid1 = front1 && (__float_as_uint(be0.y) <= em1_bits) && (__float_as_uint(bu0.y) <= um1_bits);
             float2 lam = K.mul(a, bc2(-mag));                       // mag * (-a)
             lam.x = valid0 ? lam.x : 0.0f; lam.y = valid1 ? lam.y : 0.0f;
             float2 inten;
             if (BLK) {
                 float2 blocked = make_float2(0.f, 0.f);
+                const bool reg0 = ang0 && (fr0 || !(a.x < 0.0f)), reg1 = two && ang1 && (fr1 || !(a.y < 0.0f));
                 if (bmask) {
                     if (reg0) blocked.x = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.x, dy.x, dz.x);
                     if (reg1) blocked.y = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.y, dy.y, dz.y);
                 }
                 cnt_blk += (reg0 && blocked.x < 1e-3f) + (reg1 && blocked.y < 1e-3f);
                 inten = K.mul(K.mul(K.mul(lam, K.sub(K.one, blocked)), bc2(ome)), bc2(refl));
+                cnt_lam += (lam.x > 0.0f) + (lam.y > 0.0f);
+                cnt_int += (inten.x > 0.0f) + (inten.y > 0.0f);
             } else {
                 inten = K.mul(K.mul(lam, bc2(ome)), bc2(refl));
+            }
+            if (!(valid0 && valid1)) {   // rare
+                cnt_bad += (int)!valid0 + (int)(two && !valid1);
+                any_irr |= !ang0 || ((a.x < 0.0f) && !fr0) || (two && (!ang1 || ((a.y < 0.0f) && !fr1)));
             }
             float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
             if (DBG) {
                 const size_t q = ((size_t)h * R + r) * P + p;
+                const bool reg0 = ang0 && (fr0 || !(a.x < 0.0f)), reg1 = two && ang1 && (fr1 || !(a.y < 0.0f));
                 if (reg0) {
                     if (prm.a.dbg_be) prm.a.dbg_be[q] = valid0 ? be.x : T.em1;
                     if (prm.a.dbg_bu) prm.a.dbg_bu[q] = valid0 ? bu.x : 0.0f;
@@ -513,8 +580,6 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
                     if (prm.a.dbg_lambert) prm.a.dbg_lambert[q + P] = lam.y;
                 }
             }
-            cnt_lam += (lam.x > 0.0f) + (lam.y > 0.0f);
-            cnt_int += (inten.x > 0.0f) + (inten.y > 0.0f);
             // splat weights (valid rays have 0 <= be <= E-1, 0 <= bu <= U-1).  floor() and the integer pixel index come
             // from one round-down add of 2^23 (FMA pipe) instead of FRND + F2I (XU pipe): for 0 <= x < 2^23 the sum's
             // low mantissa bits ARE floor(x).
@@ -524,8 +589,6 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             const float2 fe = K.sub(me, bc2(kMagic)), fu = K.sub(mu, bc2(kMagic));
             const float2 fe1 = K.add(fe, K.one), fu1 = K.add(fu, K.one);
             const float2 wle = K.sub(fe1, be), wlu = K.sub(fu1, bu), whe = K.sub(be, fe), whu = K.sub(bu, fu);
-            const bool go0 = valid0 && (fe1.x < e_lim) && (fu1.x < u_lim);
-            const bool go1 = valid1 && (fe1.y < e_lim) && (fu1.y < u_lim);
             float2 v1, v2, v3, v4;   // tap values (fp32 accumulate) or 2^23 + round(scaled tap value) (fixed point)
             if (FP32ACC) {
                 v1 = K.mul(K.mul(wle, whu), inten); v2 = K.mul(K.mul(whe, whu), inten);
@@ -539,29 +602,34 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             }
 #pragma unroll
             for (int lane = 0; lane < 2; ++lane) {
-                const bool go = lane ? go1 : go0;
-                if (!go) continue;
-                const int ie = (int)(__float_as_uint(lane ? me.y : me.x) & 0x007fffffu);
-                const int iu = (int)(__float_as_uint(lane ? mu.y : mu.x) & 0x007fffffu);
-                const int cex = ie - fc.e0, cux = iu - fc.u0;
+                if (!(lane ? valid1 : valid0)) continue;
+                // a valid ray has me, mu in [2^23, 2^23 + 2^22): bits - bits(2^23) is the pixel index
+                const int cex = (int)(__float_as_uint(lane ? me.y : me.x) - bias_e);
+                const int cux = (int)(__float_as_uint(lane ? mu.y : mu.x) - bias_u);
+                const int ie = cex + fc.e0, iu = cux + fc.u0;   // only the slow paths need the absolute pixel index
+                // inside the window interior: implies ie + 1 < E and iu + 1 < U (the window lies on the bitmap)
                 const bool fast = ((unsigned)cex < (unsigned)fc.wwm1) && ((unsigned)cux < (unsigned)fc.whm1);
                 const float a1 = lane ? v1.y : v1.x, a2 = lane ? v2.y : v2.x, a3 = lane ? v3.y : v3.x, a4 = lane ? v4.y : v4.x;
                 if (FP32ACC) {
                     if (fast) {
                         float* b = fc.win_f + cux * fc.ww + cex;
                         atomicAdd(b + fc.ww, a1); atomicAdd(b + fc.ww + 1, a2); atomicAdd(b + 1, a3); atomicAdd(b, a4);
-                    } else {
+                    } else if (ie + 1 < E && iu + 1 < U) {
                         float* row_hi = fc.out_f + (size_t)(U - 1 - (iu + 1)) * E + ie;
                         float* row_lo = row_hi + E;
                         atomicAdd(row_hi, a1); atomicAdd(row_hi + 1, a2); atomicAdd(row_lo + 1, a3); atomicAdd(row_lo, a4);
                     }
                 } else {
-                    const unsigned q1 = __float_as_uint(a1) & 0x007fffffu, q2 = __float_as_uint(a2) & 0x007fffffu;
-                    const unsigned q3 = __float_as_uint(a3) & 0x007fffffu, q4 = __float_as_uint(a4) & 0x007fffffu;
+                    const unsigned q1 = __float_as_uint(a1) - kMagicBits, q2 = __float_as_uint(a2) - kMagicBits;
+                    const unsigned q3 = __float_as_uint(a3) - kMagicBits, q4 = __float_as_uint(a4) - kMagicBits;
                     if (fast) {
-                        unsigned* b = fc.win_u + cux * fc.ww + cex;
-                        atomicAdd(b + fc.ww, q1); atomicAdd(b + fc.ww + 1, q2); atomicAdd(b + 1, q3); atomicAdd(b, q4);
-                    } else {
+                        // 32-bit shared-window addresses + red.shared: no generic->shared conversion per tap
+                        const unsigned lo = win_base + (unsigned)(cux * fc.ww + cex) * 4u, hi = lo + row_bytes;
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hi), "r"(q1) : "memory");
+                        asm volatile("red.shared.add.u32 [%0+4], %1;" ::"r"(hi), "r"(q2) : "memory");
+                        asm volatile("red.shared.add.u32 [%0+4], %1;" ::"r"(lo), "r"(q3) : "memory");
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(lo), "r"(q4) : "memory");
+                    } else if (ie + 1 < E && iu + 1 < U) {
                         fell_back = true;
                         atomicMin(fc.fb_box + 0, U - 2 - iu); atomicMax(fc.fb_box + 1, U - 1 - iu);
                         atomicMin(fc.fb_box + 2, ie); atomicMax(fc.fb_box + 3, ie + 1);
@@ -579,7 +647,9 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             }
         }
     }
-    cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; cnt_blk_out = cnt_blk; fell_back_out = fell_back; n_irregular_out = n_irr;
+    const int cnt_valid = n_reg_points * R - cnt_bad;
+    cnt_lam_out = BLK ? cnt_lam : cnt_valid; cnt_int_out = BLK ? cnt_int : cnt_valid; cnt_blk_out = cnt_blk; fell_back_out = fell_back;
+    n_irregular_out = any_irr ? 1 : 0;
 }
 
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
@@ -605,6 +675,15 @@ trace_fwd_kernel(const TraceParams prm) {
     const int p_begin = chunk * prm.pts_per_chunk;
     const int p_end = min(P, p_begin + prm.pts_per_chunk);
 
+    // start-up loads, all issued before the first barrier so that their latencies overlap: target constants (thread
+    // 0), orientation (threads 32..47), incident direction and the window-sample rows (every thread); meanwhile the
+    // whole shared-memory window is cleared
+    const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
+    const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    WindowSamples ws;
+    load_window_samples<THREADS>(ws, pts_h, nrm_h, p_begin, p_end);
+    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
+                i2 = __ldg(prm.a.incident + 4 * h + 2);
     if (tid == 0) {
         load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
         cnt_sh[0] = 0; cnt_sh[1] = 0; cnt_sh[2] = 0; fallback_sh = 0;
@@ -612,40 +691,47 @@ trace_fwd_kernel(const TraceParams prm) {
         fb_box[0] = 1 << 30; fb_box[1] = -1; fb_box[2] = 1 << 30; fb_box[3] = -1;
     }
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
+    {
+        uint4* w4 = reinterpret_cast<uint4*>(smem_raw);
+        const int n4 = prm.win_cap >> 2;
+        for (int i = tid; i < n4; i += THREADS) w4[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = (n4 << 2) + tid; i < prm.win_cap; i += THREADS) win_u[i] = 0u;
+    }
     __syncthreads();
     PointSrc src;
-    src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    src.pts = pts_h;
+    src.nrm = nrm_h;
     src.O = prm.a.orientations ? O_sh : nullptr;
     const TargetCtx T = T_sh;
-    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
-                i2 = __ldg(prm.a.incident + 4 * h + 2);
 
     Window W;
-    place_window<THREADS>(W, prm, T, src, p_begin, p_end, i0, i1, i2, red, &win_sh);
-    const int wcells = W.ww * W.wh;
-    for (int i = tid; i < wcells; i += THREADS) win_u[i] = 0u;
+    place_window<THREADS>(W, prm, T, src, ws, p_begin, p_end, i0, i1, i2, red, &win_sh);
     float* out_f = prm.a.flux + (size_t)h * U * E;
     unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
     if (prm.self_zero) {
         // clear the pixels the window flush will not overwrite (the global-path taps need zeros to add to); output
         // rows of the window: [U - u0 - wh, U - 1 - u0], columns [e0, e0 + ww)
         const int r_lo = U - W.u0 - W.wh, r_hi = U - 1 - W.u0, c_lo = W.e0, c_hi = W.e0 + W.ww;
+        const int warp_z = tid >> 5, lane_z = tid & 31;
         if ((E & 3) == 0) {
             const int e4 = E >> 2;
-            float4* o4 = reinterpret_cast<float4*>(out_f);
-            for (int i = tid; i < U * e4; i += THREADS) {
-                const int row = i / e4, c = (i - row * e4) << 2;
-                if (row < r_lo || row > r_hi || c + 4 <= c_lo || c >= c_hi) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                else {
+            for (int row = warp_z; row < U; row += THREADS / 32) {
+                float4* o4 = reinterpret_cast<float4*>(out_f + (size_t)row * E);
+                const bool row_in = row >= r_lo && row <= r_hi;
+                for (int q = lane_z; q < e4; q += 32) {
+                    const int c = q << 2;
+                    if (!row_in || c + 4 <= c_lo || c >= c_hi) o4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) if (c + k < c_lo || c + k >= c_hi) out_f[(size_t)row * E + c + k] = 0.f;
+                        for (int k = 0; k < 4; ++k) if (c + k < c_lo || c + k >= c_hi) out_f[(size_t)row * E + c + k] = 0.f;
+                    }
                 }
             }
         } else {
-            for (int i = tid; i < U * E; i += THREADS) {
-                const int row = i / E, c = i - row * E;
-                if (row < r_lo || row > r_hi || c < c_lo || c >= c_hi) out_f[i] = 0.f;
+            for (int row = warp_z; row < U; row += THREADS / 32) {
+                const bool row_in = row >= r_lo && row <= r_hi;
+                for (int c = lane_z; c < E; c += 32)
+                    if (!row_in || c < c_lo || c >= c_hi) out_f[(size_t)row * E + c] = 0.f;
             }
         }
     }
@@ -670,7 +756,7 @@ trace_fwd_kernel(const TraceParams prm) {
 
     int cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
     bool fell_back = false;
-    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
+    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF && (BLK || prm.simple_counts)) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
         fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
@@ -742,13 +828,21 @@ trace_fwd_kernel(const TraceParams prm) {
         if (any_fb) {
             // rare: convert the integer taps that landed outside the window, in place
             const int r_lo = max(fb_box[0], 0), r_hi = min(fb_box[1], U - 1), c_lo = max(fb_box[2], 0), c_hi = min(fb_box[3], E - 1);
-            for (int row = r_lo + warp; row <= r_hi; row += nwarps) {
-                const int iu = U - 1 - row;
-                const bool row_in = (iu >= W.u0) && (iu < W.u0 + W.wh);
+            const int wr_lo = U - W.u0 - W.wh, wr_hi = U - 1 - W.u0;     // output rows of the window
+            constexpr int kRows = 4;                                     // independent L2 reads per thread and iteration
+            for (int row0 = r_lo + warp * kRows; row0 <= r_hi; row0 += nwarps * kRows) {
                 for (int c = c_lo + lane; c <= c_hi; c += 32) {
-                    if (row_in && c >= W.e0 && c < W.e0 + W.ww) continue;
-                    const unsigned q = __ldcg(out_u + (size_t)row * E + c);
-                    if (q) out_f[(size_t)row * E + c] = __uint2float_rn(q) * inv;
+                    const bool col_in = c >= W.e0 && c < W.e0 + W.ww;
+                    unsigned q[kRows];
+#pragma unroll
+                    for (int k = 0; k < kRows; ++k) {
+                        const int row = row0 + k;
+                        q[k] = 0u;
+                        if (row <= r_hi && !(col_in && row >= wr_lo && row <= wr_hi)) q[k] = __ldcg(out_u + (size_t)row * E + c);
+                    }
+#pragma unroll
+                    for (int k = 0; k < kRows; ++k)
+                        if (q[k]) out_f[(size_t)(row0 + k) * E + c] = __uint2float_rn(q[k]) * inv;
                 }
             }
         }
@@ -1067,6 +1161,203 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
     n_irregular_out = n_irr;
 }
 
+// Packed variant of the backward fast loop: two rays per iteration in fp32x2 registers.  The recomputation of the
+// ray (which decides the pixels) repeats the forward's strict operation sequence exactly; the gradient math behind it
+// is ordinary packed FMA arithmetic.  A pair with one dead lane (invalid / off-bitmap ray) zeroes that lane's inputs,
+// so it contributes exact zeros; a pair with two dead lanes is skipped.
+template <int THREADS, int TRIG, bool BLK>
+__device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc,
+                                                      const PointSrc& src, int h, int p_begin, int p_end, float i0, float i1,
+                                                      float i2, float* __restrict__ grad_points,
+                                                      float* __restrict__ grad_normals, float* gori_acc, int& n_irregular_out) {
+    const int tid = threadIdx.x;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    const Packed K(prm.ident);
+    const float mag = prm.a.ray_magnitude;
+    const float k_or = prm.a.one_minus_extinction * prm.a.reflectivity;
+    const float k_lam = mag * k_or;                         // intensity = k_lam * (-a)
+    const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
+    const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
+    const unsigned kMagicBits = 0x4B000000u;
+    const float kMagic = 8388608.0f;
+    const float2 zero2 = make_float2(0.f, 0.f);
+    const unsigned bias_e = kMagicBits + (unsigned)bc.e0, bias_u = kMagicBits + (unsigned)bc.u0;
+    bool any_irr = false;
+    const int n_pairs = (R + 1) >> 1;
+    const long long step_inner = 2 * (long long)P, step_last = (long long)THREADS - (long long)(n_pairs - 1) * 2 * (long long)P;
+
+    int p = p_begin + tid;
+    float2 da = zero2, db = zero2;
+    const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
+    if (p < p_end) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+    for (; p < p_end; p += THREADS) {
+        const int pn = p + THREADS;
+        const bool more = pn < p_end;
+        if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
+        PointCtx pc;
+        {
+            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
+        }
+        float2 go0 = zero2, go1 = zero2, go2 = zero2, gr0 = zero2, gr1 = zero2, gr2 = zero2;   // one partial sum per lane
+        if (point_regular(pc)) {
+            const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
+            for (int r = 0; r < R; r += 2) {
+                const bool two = (r + 1 < R);
+                const float2 d0 = da, d1 = db;
+                {
+                    const bool inner = r + 2 < R;
+                    nx += inner ? step_inner : step_last;
+                    if (inner || more) {
+                        da = __ldcs(nx);
+                        if (inner ? (r + 3 < R) : (R > 1)) db = __ldcs(nx + P);
+                    }
+                }
+                float2 cu, su, ce, se;
+                bool ang0 = true, ang1 = true;
+                if (TRIG == AB200_TRIG_TABLE) {
+                    const float4 ta = __ldg(trig + (size_t)r * P + p);
+                    const float4 tb = two ? __ldg(trig + (size_t)(r + 1) * P + p) : ta;
+                    cu = make_float2(ta.x, tb.x); su = make_float2(ta.y, tb.y); ce = make_float2(ta.z, tb.z); se = make_float2(ta.w, tb.w);
+                } else {
+                    sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
+                    sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
+                    ang0 = fmaxf(fabsf(d0.x), fabsf(d0.y)) <= 0.785f;
+                    ang1 = fmaxf(fabsf(d1.x), fabsf(d1.y)) <= 0.785f;
+                }
+                // ---- strict recomputation (same operations as fwd_rays_planar_fast2) ----
+                float2 dx, dz, a, dy_keep;
+                {
+                const float2 m10 = K.mul(ce, su), m11 = K.mul(ce, cu), m20 = K.mul(se, su), m21 = K.mul(se, cu);
+                dx = K.add(K.mul(cu, bc2(pc.r0)), K.mul(su, bc2(-pc.r1)));
+                const float2 dy = K.add(K.add(K.mul(m10, bc2(pc.r0)), K.mul(m11, bc2(pc.r1))), K.mul(se, bc2(-pc.r2)));
+                dz = K.add(K.add(K.mul(m20, bc2(pc.r0)), K.mul(m21, bc2(pc.r1))), K.mul(ce, bc2(pc.r2)));
+                a = K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
+                dy_keep = dy;
+                }
+                const bool fr0 = front_regular(a.x), fr1 = front_regular(a.y);
+                float2 rinv;
+                float2 t = div_regular2_r(bc2(pc.num), a, K, rinv);
+                const float2 X = K.add(bc2(pc.o0), K.mul(dx, t));
+                const float2 Z = K.add(bc2(pc.o2), K.mul(dz, t));
+                const float2 te = K.sub(K.add(X, bc2(T.half_w)), bc2(T.c0));
+                const float2 tu = K.sub(K.add(Z, bc2(T.half_h)), bc2(T.c2));
+                const float2 qe0 = K.mul(te, bc2(T.rw)), qu0 = K.mul(tu, bc2(T.rh));
+                const float2 be0 = pfma(pfma(pfma(qe0, bc2(-T.w), te), bc2(T.rw), qe0), bc2(T.em1), zero2);
+                const float2 bu0 = pfma(pfma(pfma(qu0, bc2(-T.h), tu), bc2(T.rh), qu0), bc2(T.um1), zero2);
+                const bool valid0 = ang0 && fr0 && (__float_as_uint(be0.x) <= em1_bits) && (__float_as_uint(bu0.x) <= um1_bits);
+                const bool valid1 = two && ang1 && fr1 && (__float_as_uint(be0.y) <= em1_bits) && (__float_as_uint(bu0.y) <= um1_bits);
+                const float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
+                const float2 me = make_float2(__fadd_rd(be.x, kMagic), __fadd_rd(be.y, kMagic));
+                const float2 mu = make_float2(__fadd_rd(bu.x, kMagic), __fadd_rd(bu.y, kMagic));
+                const int ie0 = (int)(__float_as_uint(me.x) - kMagicBits), iu0 = (int)(__float_as_uint(mu.x) - kMagicBits);
+                const int ie1 = (int)(__float_as_uint(me.y) - kMagicBits), iu1 = (int)(__float_as_uint(mu.y) - kMagicBits);
+                if (!(valid0 && valid1))   // rare; irregular implies invalid
+                    any_irr |= !ang0 || ((a.x < 0.0f) && !fr0) || (two && (!ang1 || ((a.y < 0.0f) && !fr1)));
+                // on the bitmap: ie + 1 < E and iu + 1 < U (the lower bounds hold for valid rays)
+                const bool live0 = valid0 && ((unsigned)ie0 < (unsigned)(E - 1)) && ((unsigned)iu0 < (unsigned)(U - 1));
+                const bool live1 = valid1 && ((unsigned)ie1 < (unsigned)(E - 1)) && ((unsigned)iu1 < (unsigned)(U - 1));
+                if (!(live0 || live1)) continue;
+                // fractional parts (exact); the low weights are 1 - high here - the last-bit difference to the forward's
+                // (ie + 1) - be only touches the gradient VALUE, never the pixel choice
+                float2 whe = K.sub(be, K.sub(me, bc2(kMagic))), whu = K.sub(bu, K.sub(mu, bc2(kMagic)));
+                // ---- gather the four gradient taps per live lane ----
+                float2 g1 = zero2, g2 = zero2, g3 = zero2, g4 = zero2;
+#pragma unroll
+                for (int lane = 0; lane < 2; ++lane) {
+                    if (!(lane ? live1 : live0)) continue;
+                    const int ie = lane ? ie1 : ie0, iu = lane ? iu1 : iu0;
+                    const int cex = (int)(__float_as_uint(lane ? me.y : me.x) - bias_e), cux = (int)(__float_as_uint(lane ? mu.y : mu.x) - bias_u);
+                    float t1, t2, t3, t4;
+                    if (((unsigned)cex < (unsigned)bc.wwm1) && ((unsigned)cux < (unsigned)bc.whm1)) {
+                        const float* b = bc.win_g + cux * bc.ww + cex;
+                        t1 = b[bc.ww]; t2 = b[bc.ww + 1]; t3 = b[1]; t4 = b[0];
+                    } else {
+                        const float* row_hi = bc.gf + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                        const float* row_lo = row_hi + E;
+                        t1 = __ldg(row_hi); t2 = __ldg(row_hi + 1); t3 = __ldg(row_lo + 1); t4 = __ldg(row_lo);
+                    }
+                    if (lane) { g1.y = t1; g2.y = t2; g3.y = t3; g4.y = t4; } else { g1.x = t1; g2.x = t2; g3.x = t3; g4.x = t4; }
+                }
+                float2 dead_scale = make_float2(1.f, 1.f);
+                if (!(live0 && live1)) {   // rare: silence the dead lane (its values may be anything, even NaN)
+                    if (!live0) {
+                        cu.x = su.x = ce.x = se.x = dx.x = dz.x = a.x = t.x = rinv.x = 0.f;
+                        whe.x = whu.x = 0.f; dead_scale.x = 0.f;
+                    } else {
+                        cu.y = su.y = ce.y = se.y = dx.y = dz.y = a.y = t.y = rinv.y = 0.f;
+                        whe.y = whu.y = 0.f; dead_scale.y = 0.f;
+                    }
+                }
+                // ---- gradient math (packed, FMA contraction allowed) ----
+                const float2 wle = lsub(dead_scale, whe), wlu = lsub(dead_scale, whu);   // 1 - high (0 on a dead lane)
+                float2 g_int = lfma(whu, lfma(wle, g1, lmul(whe, g2)), lmul(wlu, lfma(whe, g3, lmul(wle, g4))));
+                const float2 dgx = lfma(whu, lsub(g2, g1), lmul(wlu, lsub(g3, g4)));
+                const float2 dgz = lfma(wle, lsub(g1, g4), lmul(whe, lsub(g2, g3)));
+                float2 inten = lmul(a, bc2(-k_lam));
+                float2 gdb0 = zero2, gdb1 = zero2, gdb2 = zero2;
+                if (BLK && bmask) {   // intensity = lambert * (1 - blocked) * k_or  (rare: only shadowed points get here)
+                    float2 unblocked = make_float2(1.f, 1.f);
+#pragma unroll
+                    for (int lane = 0; lane < 2; ++lane) {
+                        if (!(lane ? live1 : live0)) continue;
+                        const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2,
+                                                            lane ? dx.y : dx.x, lane ? dy_keep.y : dy_keep.x, lane ? dz.y : dz.x,
+                                                            -(lane ? g_int.y : g_int.x) * (lane ? inten.y : inten.x), bc.grad_prims);
+                        if (lane) { go0.y += bb.go0; go1.y += bb.go1; go2.y += bb.go2; gdb0.y = bb.gd0; gdb1.y = bb.gd1; gdb2.y = bb.gd2; unblocked.y = 1.0f - bb.blocked; }
+                        else      { go0.x += bb.go0; go1.x += bb.go1; go2.x += bb.go2; gdb0.x = bb.gd0; gdb1.x = bb.gd1; gdb2.x = bb.gd2; unblocked.x = 1.0f - bb.blocked; }
+                    }
+                    g_int = lmul(g_int, unblocked);
+                    inten = lmul(inten, unblocked);
+                }
+                // d/dX through be = (E-1) - te/w*(E-1), d/dZ through bu = tu/h*(U-1)
+                const float2 gX = lmul(lmul(inten, bc2(-k_e)), dgx);
+                const float2 gZ = lmul(lmul(inten, bc2(k_u)), dgz);
+                const float2 gt = lfma(gX, dx, lmul(gZ, dz));
+                const float2 ngnum = lmul(gt, make_float2(-rinv.x, -rinv.y));        // -(gt / a):  t = num / a
+                const float2 g_a = lfma(ngnum, t, lmul(g_int, bc2(-k_lam)));         // lam = mag * (-a)
+                go0 = lfma(ngnum, bc2(T.n0), ladd(go0, gX));
+                go1 = lfma(ngnum, bc2(T.n1), go1);
+                go2 = lfma(ngnum, bc2(T.n2), ladd(go2, gZ));
+                float2 gdx = lfma(gX, t, lmul(g_a, bc2(T.n0))), gdy = lmul(g_a, bc2(T.n1)), gdz = lfma(gZ, t, lmul(g_a, bc2(T.n2)));
+                if (BLK) { gdx = ladd(gdx, gdb0); gdy = ladd(gdy, gdb1); gdz = ladd(gdz, gdb2); }
+                // d = M r  ->  grad r += M^T grad d
+                //   M^T = [cu, ce su, se su; -su, ce cu, se cu; 0, -se, ce]: grouped as ce * gdy + se * gdz and -se * gdy + ce * gdz
+                const float2 q = lfma(ce, gdy, lmul(se, gdz));
+                gr0 = lfma(cu, gdx, lfma(su, q, gr0));
+                gr1 = lfma(make_float2(-su.x, -su.y), gdx, lfma(cu, q, gr1));
+                gr2 = lfma(make_float2(-se.x, -se.y), gdy, lfma(ce, gdz, gr2));
+            }
+        } else {
+            any_irr = true;
+            nx += THREADS;
+            if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+        }
+        // the point's rows again (L1/L2 hit): cheaper than keeping 11 registers alive across the ray loop
+        const float4 o_raw = __ldg(pts + p), n_raw = __ldg(nrm + p);
+        float4 o4 = o_raw, n4 = n_raw;
+        orient_point(src, o4, n4);
+        const float dot_in = sadd(sadd(smul(i0, n4.x), smul(i1, n4.y)), smul(i2, n4.z));
+        const float s_go0 = go0.x + go0.y, s_go1 = go1.x + go1.y, s_go2 = go2.x + go2.y;
+        const float s_gr0 = gr0.x + gr0.y, s_gr1 = gr1.x + gr1.y, s_gr2 = gr2.x + gr2.y;
+        // r = i - 2 (i.n) n   ->   grad n = -2 [ (i.n) grad r + (grad r . n) i ]
+        const float grn = s_gr0 * n4.x + s_gr1 * n4.y + s_gr2 * n4.z;
+        const float gn0 = -2.0f * (dot_in * s_gr0 + grn * i0);
+        const float gn1 = -2.0f * (dot_in * s_gr1 + grn * i1);
+        const float gn2 = -2.0f * (dot_in * s_gr2 + grn * i2);
+        float4 gp4 = make_float4(s_go0, s_go1, s_go2, 0.f), gn4 = make_float4(gn0, gn1, gn2, 0.f);
+        orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
+        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = gp4;
+        reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = gn4;
+    }
+    n_irregular_out = any_irr ? 1 : 0;
+}
+
 template <int THREADS, int TRIG, bool BLK>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
@@ -1089,23 +1380,26 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     const int p_begin = chunk * prm.pts_per_chunk;
     const int p_end = min(P, p_begin + prm.pts_per_chunk);
 
-    if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
-    if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
-    __syncthreads();
-    const TargetCtx T = T_sh;
-    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
-                i2 = __ldg(prm.a.incident + 4 * h + 2);
+    // start-up loads issued together before the first barrier (see trace_fwd_kernel)
     PointSrc src;
     src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
     src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
     src.O = prm.a.orientations ? O_sh : nullptr;
+    WindowSamples ws;
+    load_window_samples<THREADS>(ws, src.pts, src.nrm, p_begin, p_end);
+    const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
+                i2 = __ldg(prm.a.incident + 4 * h + 2);
+    if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
+    if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
+    __syncthreads();
+    const TargetCtx T = T_sh;
     float gori[12];
 #pragma unroll
     for (int q = 0; q < 12; ++q) gori[q] = 0.f;
     float* gori_acc = (grad_orientations && src.O) ? gori : nullptr;
 
     Window W;
-    place_window<THREADS>(W, prm, T, src, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    place_window<THREADS>(W, prm, T, src, ws, p_begin, p_end, i0, i1, i2, red, &win_sh);
     const float* gf = grad_flux + (size_t)h * grad_stride;
     {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
         const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
@@ -1131,7 +1425,11 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     }
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
+#if AB200_PACKED_RAYS
+        bwd_rays_planar_fast2<THREADS, TRIG, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
+#else
         bwd_rays_planar_fast<THREADS, TRIG, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
+#endif
         if (__syncthreads_or(n_irr != 0))   // never with physical inputs (each thread re-reads only its own points)
             bwd_rays<THREADS, TRIG, true, false, true, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
     } else if (T.planar) {
@@ -1229,6 +1527,8 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
     prm.sigma = a->scatter_sigma > 0.f ? a->scatter_sigma : 2.5e-3f;
     prm.ident.one = 1.0f; prm.ident.negzero = -0.0f; prm.ident.negone = -1.0f;
     prm.self_zero = 0;
+    prm.simple_counts = (a->ray_magnitude >= 1e-6f && a->one_minus_extinction >= 1e-6f && a->reflectivity >= 1e-6f &&
+                         a->ray_magnitude <= 1e6f && a->one_minus_extinction <= 1e6f && a->reflectivity <= 1e6f) ? 1 : 0;
 }
 
 template <int THREADS, int TRIG>
