@@ -449,6 +449,14 @@ def nurbs_points_and_normals(control_points, evaluation_points, knots_u, knots_v
 # --------------------------------------------------------------------------------------------
 # kinematics
 # --------------------------------------------------------------------------------------------
+def _actuator_rows(act_non_opt: torch.Tensor) -> torch.Tensor:
+    """The kernels index the non-optimizable actuator parameters as ``[N,7,2]``; ideal actuators loaded from a
+    scenario file carry only the first four rows (``h5_scenario_parser.py:574-640``) - pad them with zeros."""
+    if act_non_opt.dim() == 3 and act_non_opt.shape[1] < 7:
+        act_non_opt = torch.nn.functional.pad(act_non_opt, (0, 0, 0, 7 - act_non_opt.shape[1]))
+    return act_non_opt
+
+
 def _kin_args(positions, trans_dev, rot_dev, act_non_opt, act_opt, offset, linear: bool):
     k = _lib.KinematicsArgs()
     k.abi_version = ABI_VERSION
@@ -463,7 +471,7 @@ class _KinematicsFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, motor, rot_dev, trans_dev, act_opt, positions, act_non_opt, offset, linear):
         motor, rot_dev, trans_dev = _f32(motor, "motor_positions"), _f32(rot_dev, "rotation_deviation"), _f32(trans_dev, "translation_deviation")
-        positions, act_non_opt, offset = _f32(positions, "positions"), _f32(act_non_opt, "actuator params"), _f32(offset, "offset")
+        positions, act_non_opt, offset = _f32(positions, "positions"), _f32(_actuator_rows(act_non_opt), "actuator params"), _f32(offset, "offset")
         has_opt = act_opt is not None and act_opt.numel() > 0
         act_opt_c = _f32(act_opt, "actuator_opt") if has_opt else None
         if linear and not has_opt:
@@ -501,7 +509,7 @@ def kinematics_align_incident(incident, aim_points, rot_dev, trans_dev, act_opt,
     with torch.no_grad():
         incident, aim_points = _f32(incident, "incident"), _f32(aim_points, "aim_points")
         rot_dev, trans_dev = _f32(rot_dev.detach(), "rotation_deviation"), _f32(trans_dev.detach(), "translation_deviation")
-        positions, act_non_opt, offset = _f32(positions, "positions"), _f32(act_non_opt, "actuator params"), _f32(offset, "offset")
+        positions, act_non_opt, offset = _f32(positions, "positions"), _f32(_actuator_rows(act_non_opt), "actuator params"), _f32(offset, "offset")
         has_opt = act_opt is not None and act_opt.numel() > 0
         act_opt_c = _f32(act_opt.detach(), "actuator_opt") if has_opt else None
         n = incident.shape[0]

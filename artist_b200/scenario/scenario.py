@@ -16,6 +16,82 @@ class Scenario:
         self.light_sources = light_sources
         self.heliostat_field = heliostat_field
 
+    # ---- HDF5 scenario files (``:84-259``) -----------------------------------------------------------------------
+    @staticmethod
+    def get_number_of_heliostat_groups_from_hdf5(scenario_path) -> int:
+        """``number_of_heliostat_groups`` of a scenario file (``:84-102``); read with the built-in HDF5 reader."""
+        from ..io import h5lite
+
+        with h5lite.File(scenario_path) as f:
+            return int(f["number_of_heliostat_groups"][()])
+
+    @classmethod
+    def load_scenario_from_hdf5(cls, scenario_file, number_of_surface_points_per_facet: torch.Tensor = torch.tensor([50, 50]),
+                                change_number_of_control_points_per_facet: torch.Tensor | None = None,
+                                device: torch.device | None = None) -> "Scenario":
+        """Load a scenario (``:105-259``).  ``scenario_file`` is an open ``artist_b200.io.File`` (or ``h5py.File``),
+        or a path.  Heliostats are grouped by ``"<kinematics>_<actuator>"`` type exactly as the reference does; each
+        group's surface points / normals are evaluated from its NURBS control nets by ``ab200_nurbs_fwd`` in one launch
+        (the reference evaluates every heliostat twice in a Python loop, ``heliostat_field.py:318-335``)."""
+        from ..field import (HeliostatField, HeliostatGroupRigidBody, SolarTower, TowerTargetAreasCylindrical,
+                             TowerTargetAreasPlanar)
+        from ..io import h5_scenario_parser, h5lite
+        from ..nurbs import NURBSSurfaces, create_nurbs_evaluation_grid, create_planar_nurbs_control_points
+        from ..scene import LightSourceArray, Sun
+
+        dev = get_device(device)
+        if isinstance(scenario_file, (str, bytes)) or hasattr(scenario_file, "__fspath__"):
+            with h5lite.File(scenario_file) as f:
+                parsed = h5_scenario_parser.parse_scenario(f)
+        else:
+            parsed = h5_scenario_parser.parse_scenario(scenario_file)
+        tg = parsed["targets"]
+        d = lambda t: t.to(dev)
+        planar = TowerTargetAreasPlanar(tg["planar_names"], d(tg["planar_centers"]), d(tg["planar_normals"]),
+                                        d(tg["planar_dimensions"]))
+        cyl = TowerTargetAreasCylindrical(tg["cyl_names"], d(tg["cyl_centers"]), d(tg["cyl_normals"]), d(tg["cyl_axes"]),
+                                          d(tg["cyl_radii"]), d(tg["cyl_heights"]), d(tg["cyl_opening_angles"]))
+        suns = [Sun(number_of_rays=ls["number_of_rays"], distribution_parameters=ls["distribution_parameters"], device=dev)
+                for ls in parsed["light_sources"]]
+        per_facet = [int(v) for v in number_of_surface_points_per_facet.tolist()]
+        grid = create_nurbs_evaluation_grid(torch.tensor(per_facet), device=dev)
+        groups = []
+        for key, g in parsed["groups"].items():
+            if g["kinematics_type"] != "rigid_body":
+                raise KeyError(f"heliostat group type {key} is not supported")
+            n, n_facets = len(g["names"]), g["canting"].shape[1]
+            control_points, canting = d(g["nurbs_control_points"]), d(g["canting"])
+            if change_number_of_control_points_per_facet is not None:
+                control_points = torch.stack([create_planar_nurbs_control_points(
+                    number_of_control_points=change_number_of_control_points_per_facet, canting=canting[i], device=dev)
+                    for i in range(n)])
+            # a flat control net (all heights 0: ideal surface) gets canted and translated, a fitted one already
+            # carries both (``artist/field/surface.py:99-120``) - decided per heliostat, evaluated in <= 2 launches
+            translations = d(g["facet_translations"])
+            flat = (control_points[..., 2] == 0).flatten(1).all(dim=1)
+            pts = torch.empty(n, n_facets, grid.shape[0], 4, device=dev)
+            nrm = torch.empty_like(pts)
+            with torch.no_grad():
+                for rows, cant in ((flat.nonzero().flatten(), True), ((~flat).nonzero().flatten(), False)):
+                    if rows.numel() == 0:
+                        continue
+                    surfaces = NURBSSurfaces(g["nurbs_degrees"], control_points[rows].contiguous(), device=dev)
+                    ev = grid[None, None].expand(rows.numel(), n_facets, -1, -1)
+                    a, b = surfaces.calculate_surface_points_and_normals(
+                        ev, canting[rows].contiguous() if cant else None, translations[rows].contiguous() if cant else None)
+                    pts[rows], nrm[rows] = a, b
+            groups.append(HeliostatGroupRigidBody(
+                names=g["names"], positions=d(g["positions"]), surface_points=pts.reshape(n, -1, 4),
+                surface_normals=nrm.reshape(n, -1, 4), canting=canting, facet_translations=translations,
+                initial_orientations=d(g["initial_orientations"]), nurbs_control_points=control_points,
+                nurbs_degrees=g["nurbs_degrees"], kinematics_translation_deviation_parameters=d(g["translation_deviations"]),
+                kinematics_rotation_deviation_parameters=d(g["rotation_deviations"]),
+                actuator_parameters_non_optimizable=d(g["actuator_non_optimizable"]),
+                actuator_parameters_optimizable=d(g["actuator_optimizable"]), device=dev))
+        return cls(power_plant_position=parsed["power_plant_position"].to(dev),
+                   solar_tower=SolarTower([planar, cyl], device=dev), light_sources=LightSourceArray(suns),
+                   heliostat_field=HeliostatField(groups, device=dev))
+
     def index_mapping(self, heliostat_group, string_mapping: list[tuple[str, str, torch.Tensor]] | None = None,
                       single_incident_ray_direction: torch.Tensor | None = None, single_target_area_index: int = 0,
                       device: torch.device | None = None) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
