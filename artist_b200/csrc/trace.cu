@@ -515,10 +515,16 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
                 const float4 tb = two ? __ldg(trig + (size_t)(r + 1) * P + p) : ta;
                 cu = make_float2(ta.x, tb.x); su = make_float2(ta.y, tb.y); ce = make_float2(ta.z, tb.z); se = make_float2(ta.w, tb.w);
             } else {
-                sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
-                sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
-                ang0 = fmaxf(fabsf(d0.x), fabsf(d0.y)) <= 0.785f;
-                ang1 = fmaxf(fabsf(d1.x), fabsf(d1.y)) <= 0.785f;
+                const float m0 = fmaxf(fabsf(d0.x), fabsf(d0.y)), m1 = fmaxf(fabsf(d1.x), fabsf(d1.y));
+                if (fmaxf(m0, m1) <= kTinyAngle) {   // always, for a physical sun shape (decided per PAIR, identically
+                    sincos_tiny2(make_float2(d0.x, d1.x), &su, &cu, K);   // in the forward and the backward kernel)
+                    sincos_tiny2(make_float2(d0.y, d1.y), &se, &ce, K);
+                } else {
+                    sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
+                    sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
+                    ang0 = m0 <= 0.785f;
+                    ang1 = m1 <= 0.785f;
+                }
             }
             // scatter: d = M(e,u) r   ((-su) * r1 == su * (-r1), (-se) * r2 == se * (-r2) exactly)
             const float2 m10 = K.mul(ce, su), m11 = K.mul(ce, cu), m20 = K.mul(se, su), m21 = K.mul(se, cu);
@@ -1225,10 +1231,16 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                     const float4 tb = two ? __ldg(trig + (size_t)(r + 1) * P + p) : ta;
                     cu = make_float2(ta.x, tb.x); su = make_float2(ta.y, tb.y); ce = make_float2(ta.z, tb.z); se = make_float2(ta.w, tb.w);
                 } else {
-                    sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
-                    sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
-                    ang0 = fmaxf(fabsf(d0.x), fabsf(d0.y)) <= 0.785f;
-                    ang1 = fmaxf(fabsf(d1.x), fabsf(d1.y)) <= 0.785f;
+                    const float m0 = fmaxf(fabsf(d0.x), fabsf(d0.y)), m1 = fmaxf(fabsf(d1.x), fabsf(d1.y));
+                    if (fmaxf(m0, m1) <= kTinyAngle) {   // always, for a physical sun shape (decided per PAIR, identically
+                        sincos_tiny2(make_float2(d0.x, d1.x), &su, &cu, K);   // in the forward and the backward kernel)
+                        sincos_tiny2(make_float2(d0.y, d1.y), &se, &ce, K);
+                    } else {
+                        sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
+                        sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
+                        ang0 = m0 <= 0.785f;
+                        ang1 = m1 <= 0.785f;
+                    }
                 }
                 // ---- strict recomputation (same operations as fwd_rays_planar_fast2) ----
                 float2 dx, dz, a, dy_keep;

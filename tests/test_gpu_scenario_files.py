@@ -72,6 +72,9 @@ def _check_trace(scenario, group, t):
     assert ((motor - t["motor_positions"]).abs() / t["motor_positions"].abs().clamp_min(1)).max() < 2e-4
     assert (group.active_surface_points[:, ::SAMPLE].cpu() - t["aligned_points_sample"]).abs().max() <= 2e-4
     assert (group.active_surface_normals[:, ::SAMPLE].cpu() - t["aligned_normals_sample"]).abs().max() <= 2e-5
+    print(f"   {t['name']}: motor rel diff {float(((motor - t['motor_positions']).abs() / t['motor_positions'].abs().clamp_min(1)).max()):.2e}, "
+          f"aligned points max diff {float((group.active_surface_points[:, ::SAMPLE].cpu() - t['aligned_points_sample']).abs().max()):.2e} m, "
+          f"normals {float((group.active_surface_normals[:, ::SAMPLE].cpu() - t['aligned_normals_sample']).abs().max()):.2e}")
     ref = _dense(t["flux"])
     assert flux.shape == ref.shape
     peak = ref.max()
