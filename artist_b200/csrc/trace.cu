@@ -465,6 +465,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     const float fxs = prm.fx_scale;
     const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
     const unsigned kMagicBits = 0x4B000000u;   // bits(2^23)
+    const bool axis_n = (T.n0 == 0.0f) && (T.n2 == 0.0f);
     const unsigned bias_e = kMagicBits + (unsigned)fc.e0, bias_u = kMagicBits + (unsigned)fc.u0;
     const unsigned win_base = (unsigned)__cvta_generic_to_shared(fc.win_u), row_bytes = (unsigned)fc.ww * 4u;
     // factor counters: valid rays = R * (regular points) - cnt_bad; invalid rays are rare, so the bookkeeping (and the
@@ -531,7 +532,10 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             const float2 dx = K.add(K.mul(cu, bc2(pc.r0)), K.mul(su, bc2(-pc.r1)));
             const float2 dy = K.add(K.add(K.mul(m10, bc2(pc.r0)), K.mul(m11, bc2(pc.r1))), K.mul(se, bc2(-pc.r2)));
             const float2 dz = K.add(K.add(K.mul(m20, bc2(pc.r0)), K.mul(m21, bc2(pc.r1))), K.mul(ce, bc2(pc.r2)));
-            const float2 a = K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
+            // a = d . n_t; for a target facing exactly +-north (n_e = n_u = 0, every scenario of the reference) the two
+            // zero products only add +-0, so the strict sum IS RN(dy * n_n) whenever it is non-zero (a == 0 is invalid anyway)
+            const float2 a = axis_n ? K.mul(dy, bc2(T.n1))
+                                    : K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
             // regular = angles in the polynomial's range and (a >= 0  or  a in (-1e18, -1e-18)); irregular rays are
             // left to the generic loop (same predicate there: angles_regular && cosine_regular)
             const bool fr0 = front_regular(a.x), fr1 = front_regular(a.y);
@@ -592,9 +596,10 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             const float kMagic = 8388608.0f;
             const float2 me = make_float2(__fadd_rd(be.x, kMagic), __fadd_rd(be.y, kMagic));
             const float2 mu = make_float2(__fadd_rd(bu.x, kMagic), __fadd_rd(bu.y, kMagic));
-            const float2 fe = K.sub(me, bc2(kMagic)), fu = K.sub(mu, bc2(kMagic));
-            const float2 fe1 = K.add(fe, K.one), fu1 = K.add(fu, K.one);
-            const float2 wle = K.sub(fe1, be), wlu = K.sub(fu1, bu), whe = K.sub(be, fe), whu = K.sub(bu, fu);
+            // high weights = fractional parts (exact); low weights = 1 - high, the same real number as the reference's
+            // (ie + 1) - be with its single rounding placed differently (<= 1 ulp of the weight, 1e-7 of a tap)
+            const float2 whe = K.sub(be, K.sub(me, bc2(kMagic))), whu = K.sub(bu, K.sub(mu, bc2(kMagic)));
+            const float2 wle = K.sub(K.one, whe), wlu = K.sub(K.one, whu);
             float2 v1, v2, v3, v4;   // tap values (fp32 accumulate) or 2^23 + round(scaled tap value) (fixed point)
             if (FP32ACC) {
                 v1 = K.mul(K.mul(wle, whu), inten); v2 = K.mul(K.mul(whe, whu), inten);
@@ -1189,6 +1194,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
     const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
     const unsigned kMagicBits = 0x4B000000u;
+    const bool axis_n = (T.n0 == 0.0f) && (T.n2 == 0.0f);
     const float kMagic = 8388608.0f;
     const float2 zero2 = make_float2(0.f, 0.f);
     const unsigned bias_e = kMagicBits + (unsigned)bc.e0, bias_u = kMagicBits + (unsigned)bc.u0;
@@ -1249,7 +1255,8 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                 dx = K.add(K.mul(cu, bc2(pc.r0)), K.mul(su, bc2(-pc.r1)));
                 const float2 dy = K.add(K.add(K.mul(m10, bc2(pc.r0)), K.mul(m11, bc2(pc.r1))), K.mul(se, bc2(-pc.r2)));
                 dz = K.add(K.add(K.mul(m20, bc2(pc.r0)), K.mul(m21, bc2(pc.r1))), K.mul(ce, bc2(pc.r2)));
-                a = K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
+                a = axis_n ? K.mul(dy, bc2(T.n1))
+                           : K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
                 dy_keep = dy;
                 }
                 const bool fr0 = front_regular(a.x), fr1 = front_regular(a.y);
