@@ -43,6 +43,19 @@ def bytes_per_ray(r: int, p: int, ue: int) -> tuple[float, float]:
     return 8 + 32 / r + 4 * ue / (r * p), 8 + 64 / r + 4 * ue / (r * p)
 
 
+def measured_traffic(kernel: str, rays_per_launch: int) -> float | None:
+    """DRAM bytes per launch of `kernel` from the committed ``ncu --set full`` capture (profiles/trace_traffic.json,
+    written by tools/ncu_traffic.py) - only if it was taken on the same workload size; else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "trace_traffic.json")) as fh:
+            t = json.load(fh)
+        if int(t["rays_per_launch"]) != int(rays_per_launch):
+            return None
+        return float(t["kernels"][kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_hbm() -> tuple[float, str]:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -281,6 +294,7 @@ def workload_config(gpus: int, note: str | None = None) -> dict:
         "bitmap": list(RES), "control_points": list(CONTROL_POINTS), "parallelism": f"heliostat-sharded x{gpus}, NCCL all-reduce of the [T,U,E] flux",
         "l2_policy": "inputs larger than L2 (2.9 GB of distortions/points/normals per step per GPU vs 126 MB L2)",
         "trig": "polynomial sin/cos (<= 1 ulp), FMA-free coordinate path", "accumulate": "fixed-point (deterministic)",
+        "alignment": "fused into the trace kernels (orientation applied per point; aligned [N,P,4] tensors never materialised)",
     }
     if note:
         cfg["note"] = note
@@ -360,7 +374,10 @@ def main() -> None:
             "gpu_launches": int(launches),
             "kernel_ms": {k: round(v, 4) for k, v in sorted(kern_ms.items())},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic(dom, wl.rays_per_step),
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, "
+                                         "profiles/trace_traffic.json)",
+                         "algorithmic_bytes_per_launch": wl.rays_per_step * bpr, "peak_source": peak_src,
                          "bytes_per_ray": bpr, "rays_per_launch": wl.rays_per_step,
                          "fwd_bwd_trace_frac": (wl.rays_per_step * (bf + bb) / ((kern_ms["ab200_trace_fwd"] + kern_ms["ab200_trace_bwd"]) * 1e-3) / 1e9) / peak},
             "clocks": clocks,
