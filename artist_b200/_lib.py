@@ -105,6 +105,12 @@ EXPORTS = {
     "ab200_align_bwd": ([c_float_p, c_float_p, c_float_p, c_int_p, C.c_int32, C.c_int32, c_float_p, c_float_p,
                          c_float_p, c_float_p, c_float_p, C.c_void_p], C.c_int32),
     "ab200_trace_host": ([C.POINTER(HostTraceArgs), C.c_void_p], C.c_int32),
+    "ab200_reflect": ([c_float_p, c_float_p, C.c_int32, C.c_int32, c_float_p, C.c_void_p], C.c_int32),
+    "ab200_line_intersections": ([c_float_p, c_float_p, c_float_p, C.POINTER(Targets), c_int_p, C.c_int32, C.c_int32,
+                                  C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p, c_float_p, c_float_p,
+                                  C.c_void_p], C.c_int32),
+    "ab200_bilinear_splatting": ([c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int64, C.c_int32, C.c_int32, c_float_p,
+                                  C.c_void_p], C.c_int32),
     "ab200_blocking_pack": ([c_float_p, c_float_p, c_float_p, C.c_int32, C.c_float, c_float_p, C.c_void_p], C.c_int32),
     "ab200_blocking_candidates": ([c_float_p, C.c_int32, c_int_p, c_float_p, c_float_p, C.c_int32, C.c_float, C.c_int32,
                                    c_int_p, c_int_p, c_int_p, C.c_void_p], C.c_int32),

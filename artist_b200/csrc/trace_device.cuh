@@ -98,16 +98,9 @@ struct PointCtx {
     float cc;           // cylindrical: ox^2 + oy^2 - r^2
 };
 
-__device__ __forceinline__ void make_point(PointCtx& pc, const TargetCtx& T, float i0, float i1, float i2,
-                                           const float4 o, const float4 n) {
+// origin-dependent, ray-independent terms (numerator of the plane distance / origin in the cylinder frame)
+__device__ __forceinline__ void make_origin(PointCtx& pc, const TargetCtx& T, const float4 o) {
     pc.o0 = o.x; pc.o1 = o.y; pc.o2 = o.z;
-    // dot over the 4 homogeneous components; incident.w * normal.w = 0 contributes +0
-    const float dot = sadd(sadd(smul(i0, n.x), smul(i1, n.y)), smul(i2, n.z));
-    pc.dot = dot;
-    const float two_dot = smul(2.0f, dot);
-    pc.r0 = ssub(i0, smul(two_dot, n.x));
-    pc.r1 = ssub(i1, smul(two_dot, n.y));
-    pc.r2 = ssub(i2, smul(two_dot, n.z));
     if (T.planar) {
         pc.num = sadd(sadd(smul(ssub(T.c0, o.x), T.n0), smul(ssub(T.c1, o.y), T.n1)), smul(ssub(T.c2, o.z), T.n2));
     } else {
@@ -118,6 +111,18 @@ __device__ __forceinline__ void make_point(PointCtx& pc, const TargetCtx& T, flo
         pc.oz = fmaf(q2, T.ax2, fmaf(q1, T.ax1, smul(q0, T.ax0)));
         pc.cc = ssub(sadd(smul(pc.ox, pc.ox), smul(pc.oy, pc.oy)), T.rad2);
     }
+}
+
+__device__ __forceinline__ void make_point(PointCtx& pc, const TargetCtx& T, float i0, float i1, float i2,
+                                           const float4 o, const float4 n) {
+    // dot over the 4 homogeneous components; incident.w * normal.w = 0 contributes +0
+    const float dot = sadd(sadd(smul(i0, n.x), smul(i1, n.y)), smul(i2, n.z));
+    pc.dot = dot;
+    const float two_dot = smul(2.0f, dot);
+    pc.r0 = ssub(i0, smul(two_dot, n.x));
+    pc.r1 = ssub(i1, smul(two_dot, n.y));
+    pc.r2 = ssub(i2, smul(two_dot, n.z));
+    make_origin(pc, T, o);
 }
 
 // Where a CTA's surface points come from: already aligned [P] float4 rows, or - when the caller passes the sample's

@@ -181,6 +181,15 @@ class HeliostatRayTracer:
         n_targets = int(self.scenario.solar_tower.number_of_target_areas_per_type.sum())
         return ops.bitmaps_per_target(bitmaps_per_heliostat, target_area_indices, n_targets)
 
+    def bilinear_splatting(self, bitmap_intersections_e: torch.Tensor, bitmap_intersections_u: torch.Tensor,
+                           absolute_intensities: torch.Tensor, device: torch.device | None = None) -> torch.Tensor:
+        """Stand-alone splat of materialised per-ray coordinates (``:610-778``); ``trace_rays`` splats inside its
+        fused kernel instead."""
+        from .geometry import bilinear_splatting
+
+        return bilinear_splatting(bitmap_intersections_e, bitmap_intersections_u, absolute_intensities,
+                                  self.bitmap_resolution)
+
     # The helper below exists for API parity; trace_rays does not go through it.
     def scatter_rays(self, distortion_u, distortion_e, original_ray_direction, device=None) -> Rays:
         """Scattered directions ``[B,R,P,4]`` around the preferred directions (``:510-561``)."""

@@ -251,6 +251,29 @@ int32_t ab200_align_bwd(const float* points, const float* normals, const float* 
                         float* grad_points, float* grad_normals, float* grad_orientations, void* stream);
 
 /*
+ * Stand-alone forms of the steps the reference exports as free functions (artist/raytracing/__init__.py:1-12) on the
+ * MATERIALISED per-ray tensors of its API; trace_rays never uses them (the fused kernels keep per-ray state in
+ * registers), they serve API parity and step-wise checks.  Forward only.
+ *   ab200_reflect              geometry.reflect, geometry.py:11-41: out = i - 2 (i.n) n over all 4 components;
+ *                              incident [N,4] (one direction per sample), normals / out [N,P,4]
+ *   ab200_line_intersections   geometry.line_plane_intersections :44-204 (cylindrical = 0) and
+ *                              line_cylinder_intersections :207-445 (cylindrical = 1; target_idx then counts within the
+ *                              cylindrical areas): ray_directions [N,R,P,4], ray_magnitudes [N,R,P], ray_origins [N,P,4],
+ *                              target_idx [N] or NULL (= area 0) -> bitmap coordinates e (flipped for planes) and u,
+ *                              intersection distances, Lambert-weighted intensities, each [N,R,P], zero where invalid
+ *   ab200_bilinear_splatting   HeliostatRayTracer.bilinear_splatting, heliostat_ray_tracer.py:610-778: be, bu,
+ *                              intensities [N,K] -> out [N,U,E] (zeroed here; fp32 atomics, row-flipped like the reference)
+ */
+int32_t ab200_reflect(const float* incident, const float* normals, int32_t n_samples, int32_t n_points, float* out,
+                      void* stream);
+int32_t ab200_line_intersections(const float* ray_directions, const float* ray_magnitudes, const float* ray_origins,
+                                 const ab200_targets* targets, const int32_t* target_idx, int32_t cylindrical,
+                                 int32_t n_samples, int32_t n_rays, int32_t n_points, int32_t res_e, int32_t res_u,
+                                 float* be, float* bu, float* distances, float* intensities, void* stream);
+int32_t ab200_bilinear_splatting(const float* be, const float* bu, const float* intensities, int32_t n_samples,
+                                 int64_t rays_per_sample, int32_t res_e, int32_t res_u, float* out, void* stream);
+
+/*
  * ab200_trace_host - end-to-end convenience entry with HOST buffers: uploads the per-call inputs
  * (incident directions, target indices, aligned points/normals if given on the host), traces,
  * and downloads the per-target bitmaps.  Device scratch is supplied by the caller.
