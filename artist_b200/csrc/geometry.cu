@@ -21,6 +21,25 @@ __global__ void __launch_bounds__(256) reflect_kernel(const float4* __restrict__
     }
 }
 
+// scatter (a9): d = M(e,u) r per ray, M from geometry/transforms.py:52-83 - the strict product/sum order of the fused
+// kernels (trace_device.cuh::scatter); trig = the kernels' polynomial / libdevice sincos (<= 1 ulp)
+__global__ void __launch_bounds__(256) scatter_kernel(const float* __restrict__ dist_u, const float* __restrict__ dist_e,
+                                                      const float4* __restrict__ reflected, int n_rays, int n_points,
+                                                      long long total, float4* __restrict__ out) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(k % n_points);
+        const long long b = k / ((long long)n_rays * n_points);
+        const float4 r = __ldg(reflected + b * n_points + p);
+        Scatter s;
+        sincos_poly(__ldg(dist_u + k), &s.su, &s.cu);
+        sincos_poly(__ldg(dist_e + k), &s.se, &s.ce);
+        PointCtx pc;
+        pc.r0 = r.x; pc.r1 = r.y; pc.r2 = r.z;
+        scatter(s, pc);
+        out[k] = make_float4(s.dx, s.dy, s.dz, r.w);
+    }
+}
+
 // one CTA row (blockIdx.y) per sample: the target constants are per sample
 template <bool PLANAR>
 __global__ void __launch_bounds__(256) intersections_kernel(const float4* __restrict__ dirs, const float* __restrict__ magnitudes,
@@ -85,6 +104,20 @@ extern "C" int32_t ab200_reflect(const float* incident, const float* normals, in
     const long long total = (long long)n_samples * n_points;
     reflect_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(incident), reinterpret_cast<const float4*>(normals), n_points, total,
+        reinterpret_cast<float4*>(out));
+    note_launch();
+    AB200_CUDA_TRY(cudaGetLastError());
+    return AB200_OK;
+}
+
+extern "C" int32_t ab200_scatter_rays(const float* distortions_u, const float* distortions_e, const float* reflected,
+                                      int32_t n_samples, int32_t n_rays, int32_t n_points, float* out, void* stream) {
+    AB200_REQUIRE(distortions_u && distortions_e && reflected && out, AB200_EINVAL, "NULL pointer");
+    AB200_REQUIRE(n_samples >= 0 && n_rays > 0 && n_points > 0, AB200_EINVAL, "bad sizes");
+    if (n_samples == 0) return AB200_OK;
+    const long long total = (long long)n_samples * n_rays * n_points;
+    scatter_kernel<<<blocks_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        distortions_u, distortions_e, reinterpret_cast<const float4*>(reflected), n_rays, n_points, total,
         reinterpret_cast<float4*>(out));
     note_launch();
     AB200_CUDA_TRY(cudaGetLastError());

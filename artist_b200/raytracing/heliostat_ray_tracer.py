@@ -4,7 +4,7 @@ import math
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
 from ..scene.rays import Rays
 from ..util import indices
 from .sampling import DistortionsDataset, RestrictedDistributedSampler
@@ -192,11 +192,11 @@ class HeliostatRayTracer:
 
     # The helper below exists for API parity; trace_rays does not go through it.
     def scatter_rays(self, distortion_u, distortion_e, original_ray_direction, device=None) -> Rays:
-        """Scattered directions ``[B,R,P,4]`` around the preferred directions (``:510-561``)."""
-        ce, se, cu, su = torch.cos(distortion_e), torch.sin(distortion_e), torch.cos(distortion_u), torch.sin(distortion_u)
-        r = original_ray_direction.unsqueeze(1)
-        dx = cu * r[..., 0] + (-su) * r[..., 1]
-        dy = (ce * su) * r[..., 0] + (ce * cu) * r[..., 1] + (-se) * r[..., 2]
-        dz = (se * su) * r[..., 0] + (se * cu) * r[..., 1] + ce * r[..., 2]
-        dirs = torch.stack([dx, dy, dz, r[..., 3].expand_as(dx)], dim=-1)
-        return Rays(dirs, torch.full(dirs.shape[:3], float(self.ray_magnitude), device=dirs.device))
+        """Scattered directions ``[B,R,P,4]`` around the preferred directions (``:510-561``) - ``ab200_scatter_rays``."""
+        du = ops._f32(distortion_u.detach(), "distortion_u")
+        de = ops._f32(distortion_e.detach(), "distortion_e")
+        refl = ops._f32(original_ray_direction.detach(), "original_ray_direction")
+        b, r, p = du.shape
+        dirs = torch.empty(b, r, p, 4, device=du.device)
+        _lib.call("ab200_scatter_rays", ops._p(du), ops._p(de), ops._p(refl), b, r, p, ops._p(dirs), ops._stream())
+        return Rays(dirs, torch.full((b, r, p), float(self.ray_magnitude), device=dirs.device))

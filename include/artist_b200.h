@@ -256,6 +256,9 @@ int32_t ab200_align_bwd(const float* points, const float* normals, const float* 
  * registers), they serve API parity and step-wise checks.  Forward only.
  *   ab200_reflect              geometry.reflect, geometry.py:11-41: out = i - 2 (i.n) n over all 4 components;
  *                              incident [N,4] (one direction per sample), normals / out [N,P,4]
+ *   ab200_scatter_rays         HeliostatRayTracer.scatter_rays, heliostat_ray_tracer.py:510-561 + transforms.
+ *                              rotate_distortions :7-83: distortions u, e [N,R,P], reflected directions [N,P,4] ->
+ *                              scattered directions [N,R,P,4]
  *   ab200_line_intersections   geometry.line_plane_intersections :44-204 (cylindrical = 0) and
  *                              line_cylinder_intersections :207-445 (cylindrical = 1; target_idx then counts within the
  *                              cylindrical areas): ray_directions [N,R,P,4], ray_magnitudes [N,R,P], ray_origins [N,P,4],
@@ -266,6 +269,8 @@ int32_t ab200_align_bwd(const float* points, const float* normals, const float* 
  */
 int32_t ab200_reflect(const float* incident, const float* normals, int32_t n_samples, int32_t n_points, float* out,
                       void* stream);
+int32_t ab200_scatter_rays(const float* distortions_u, const float* distortions_e, const float* reflected,
+                           int32_t n_samples, int32_t n_rays, int32_t n_points, float* out, void* stream);
 int32_t ab200_line_intersections(const float* ray_directions, const float* ray_magnitudes, const float* ray_origins,
                                  const ab200_targets* targets, const int32_t* target_idx, int32_t cylindrical,
                                  int32_t n_samples, int32_t n_rays, int32_t n_points, int32_t res_e, int32_t res_u,

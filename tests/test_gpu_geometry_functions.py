@@ -132,3 +132,20 @@ def test_step_functions_compose_to_trace_rays():
                                                       trig=cases.cpu_trig(case["dist_u"], case["dist_e"]).to(DEV))
     assert torch.equal(be, dbe) and torch.equal(bu, dbu) and torch.equal(t, dt) and torch.equal(lam, dlam)
     assert (flux - stepwise).abs().max() <= 1e-5 * flux.max()
+
+
+def test_scatter_rays_method_matches_the_oracle():
+    from artist_b200 import HeliostatRayTracer, build_synthetic_scenario
+
+    scenario, group = build_synthetic_scenario(2, number_of_rays=3, points_per_facet=(6, 6), device=DEV)
+    mask, tidx, inc = scenario.index_mapping(group)
+    group.activate_heliostats(mask)
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=False)
+    case = cases.make_case(n=3, points_per_facet=(7, 7), rays=4)
+    refl = O.reflect(case["incident"][:, None], case["normals"])
+    want = O.scatter_rays(case["dist_u"], case["dist_e"], refl)
+    rays = tracer.scatter_rays(case["dist_u"].to(DEV), case["dist_e"].to(DEV), refl.to(DEV), device=DEV)
+    assert rays.ray_directions.shape == want.shape and rays.ray_magnitudes.shape == want.shape[:3]
+    assert (rays.ray_magnitudes == 1.0).all()
+    # device trig is within an ulp of torch-CPU's: directions agree to 2e-7
+    assert (rays.ray_directions.cpu() - want).abs().max() <= 2e-7
