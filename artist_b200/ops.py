@@ -350,6 +350,64 @@ def bitmaps_per_target(bitmaps, target_idx, n_targets: int):
 
 
 # --------------------------------------------------------------------------------------------
+# flux post-processing: centre of mass, centre-of-mass crop (artist/flux/bitmap.py)
+# --------------------------------------------------------------------------------------------
+class _FluxCentreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bitmaps, normalised):
+        bitmaps = _f32(bitmaps, "bitmaps")
+        n, u, e = bitmaps.shape
+        moments = torch.empty(n, 3, device=bitmaps.device)
+        _lib.call("ab200_flux_moments", _p(bitmaps), n, u, e, 1 if normalised else 0, _p(moments), _stream())
+        ctx.save_for_backward(moments)
+        ctx.shape, ctx.normalised = (n, u, e), normalised
+        return moments[:, 1:].clone()
+
+    @staticmethod
+    def backward(ctx, g_centre):
+        (moments,) = ctx.saved_tensors
+        n, u, e = ctx.shape
+        g_centre = _f32(g_centre, "grad_centre")
+        g = torch.empty(n, u, e, device=moments.device)
+        _lib.call("ab200_flux_moments_bwd", _p(moments), _p(g_centre), n, u, e, 1 if ctx.normalised else 0, _p(g), _stream())
+        return g, None
+
+
+def flux_center_of_mass(bitmaps: torch.Tensor, normalised: bool = False) -> torch.Tensor:
+    """``[N,U,E]`` -> ``[N,2]`` (e, u) centre of mass in pixel units, or in the crop's normalised [-1,1] coordinates."""
+    return _FluxCentreFn.apply(bitmaps, normalised)
+
+
+class _FluxCropFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bitmaps, scale):
+        bitmaps, scale = _f32(bitmaps, "flux_distributions"), _f32(scale, "crop scale")
+        n, u, e = bitmaps.shape
+        moments = torch.empty(n, 3, device=bitmaps.device)
+        out = torch.empty_like(bitmaps)
+        _lib.call("ab200_flux_crop_fwd", _p(bitmaps), _p(scale), n, u, e, _p(moments), _p(out), _stream())
+        ctx.save_for_backward(bitmaps, scale, moments)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        bitmaps, scale, moments = ctx.saved_tensors
+        n, u, e = bitmaps.shape
+        g_out = _f32(g_out, "grad_cropped")
+        scratch = torch.empty(n, 2, device=bitmaps.device)
+        g_in = torch.empty_like(bitmaps)
+        _lib.call("ab200_flux_crop_bwd", _p(bitmaps), _p(scale), _p(moments), _p(g_out), n, u, e, _p(scratch), _p(g_in),
+                  _stream())
+        return g_in, None
+
+
+def flux_crop_around_center(bitmaps: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """Bilinear crop of every ``[U,E]`` bitmap around its centre of mass; ``scale[n] = (crop_w / target_w, crop_h /
+    target_h)``.  Differentiable w.r.t. the bitmaps (through the resampling and through the centre)."""
+    return _FluxCropFn.apply(bitmaps, scale)
+
+
+# --------------------------------------------------------------------------------------------
 # NURBS
 # --------------------------------------------------------------------------------------------
 _grid_cache: dict = {}

@@ -279,6 +279,27 @@ int32_t ab200_bilinear_splatting(const float* be, const float* bu, const float* 
                                  int64_t rays_per_sample, int32_t res_e, int32_t res_u, float* out, void* stream);
 
 /*
+ * Step after the ray tracer (flux post-processing, artist/flux/bitmap.py).
+ *   ab200_flux_moments   get_center_of_mass :12-55: moments[b] = (sum, e-, u- centre of mass) of bitmaps [n,U,E]; pixel
+ *                        units (normalised = 0) or the normalised [-1,1] coordinates the crop uses (normalised = 1)
+ *   ab200_flux_crop_fwd  crop_flux_distributions_around_center :121-246: bilinear resampling (affine_grid + grid_sample,
+ *                        align_corners, zero padding) of every bitmap around its centre of mass with
+ *                        scale[b] = (crop_width / target width, crop_height / target height); writes moments [n,3]
+ *                        (kept for the backward) and out [n,U,E]
+ *   ab200_flux_crop_bwd  its backward (through the resampling AND through the centre of mass), a deterministic gather;
+ *                        scratch = 2n floats
+ */
+int32_t ab200_flux_moments(const float* bitmaps, int32_t n_bitmaps, int32_t res_u, int32_t res_e, int32_t normalised,
+                           float* moments, void* stream);
+/* backward of the two centre coordinates: grad_centre [n,2] -> grad_bitmaps [n,U,E] */
+int32_t ab200_flux_moments_bwd(const float* moments, const float* grad_centre, int32_t n_bitmaps, int32_t res_u, int32_t res_e,
+                               int32_t normalised, float* grad_bitmaps, void* stream);
+int32_t ab200_flux_crop_fwd(const float* bitmaps, const float* scale, int32_t n_bitmaps, int32_t res_u, int32_t res_e,
+                            float* moments, float* out, void* stream);
+int32_t ab200_flux_crop_bwd(const float* bitmaps, const float* scale, const float* moments, const float* grad_out,
+                            int32_t n_bitmaps, int32_t res_u, int32_t res_e, float* scratch, float* grad_in, void* stream);
+
+/*
  * ab200_trace_host - end-to-end convenience entry with HOST buffers: uploads the per-call inputs
  * (incident directions, target indices, aligned points/normals if given on the host), traces,
  * and downloads the per-target bitmaps.  Device scratch is supplied by the caller.

@@ -794,3 +794,40 @@ def incident_ray_directions_to_orientations(k: Kin, incident: torch.Tensor, aim_
 def align_surfaces(points: torch.Tensor, normals: torch.Tensor, orientations: torch.Tensor):
     """``heliostat_group_rigid_body.py:217-222``: ``[N,P,4] @ O^T``."""
     return points @ orientations.transpose(1, 2), normals @ orientations.transpose(1, 2)
+
+
+# --------------------------------------------------------------------------------------
+# step after the path: flux-bitmap centre of mass and crop  (artist/flux/bitmap.py:12-55, 121-246)
+# --------------------------------------------------------------------------------------
+
+
+def flux_center_of_mass(bitmaps: torch.Tensor) -> torch.Tensor:
+    """``[B,U,E]`` -> ``[B,2]`` (e, u) centre of mass in pixel units (``bitmap.py:37-55``)."""
+    _, height, width = bitmaps.shape
+    norm = bitmaps / (bitmaps.sum(dim=(1, 2), keepdim=True) + 1e-8)
+    e = torch.linspace(0, width - 1, width)
+    u = torch.linspace(0, height - 1, height)
+    ug, eg = torch.meshgrid(u, e, indexing="ij")
+    return torch.stack([(eg * norm).sum(dim=(1, 2)), (ug * norm).sum(dim=(1, 2))], dim=1)
+
+
+def crop_flux_around_center(bitmaps: torch.Tensor, target_dimensions: torch.Tensor, crop_width: float = 6,
+                            crop_height: float = 6) -> torch.Tensor:
+    """Centre-of-mass crop (``bitmap.py:157-246``): ``target_dimensions [B,2]`` = (width, height) of each bitmap's
+    target area in metres; affine_grid + grid_sample (bilinear, align_corners=True, zero padding)."""
+    n, height, width = bitmaps.shape
+    norm = bitmaps / (bitmaps.sum(dim=(2, 1), keepdim=True) + 1e-8)
+    y = torch.linspace(-1, 1, height)
+    x = torch.linspace(-1, 1, width)
+    yg, xg = torch.meshgrid(y, x, indexing="ij")
+    cx = (xg * norm).sum(dim=(2, 1))
+    cy = (yg * norm).sum(dim=(2, 1))
+    w = target_dimensions[:, 0].clamp(min=1e-8)
+    h = target_dimensions[:, 1].clamp(min=1e-8)
+    theta = torch.zeros(n, 2, 3)
+    theta[:, 0, 0] = crop_width / w
+    theta[:, 1, 1] = crop_height / h
+    theta[:, 0, 2] = cx
+    theta[:, 1, 2] = cy
+    grid = torch.nn.functional.affine_grid(theta, size=[n, 1, height, width], align_corners=True)
+    return torch.nn.functional.grid_sample(bitmaps[:, None], grid, align_corners=True, padding_mode="zeros")[:, 0]

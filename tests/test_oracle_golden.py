@@ -95,3 +95,14 @@ def test_blocking_trace_bit_exact(golden, batch_size):
     assert torch.equal(flux, want["flux"]) and torch.equal(bl, want["blocking"])
     assert torch.equal(ic, want["intercept"]) and torch.equal(ot, want["on_target"])
     assert want["blocking"].min() < 0.2, "fixture must contain real shadowing"
+
+
+def test_flux_center_of_mass_and_crop_bit_exact():
+    """The oracle's restatement of artist/flux/bitmap.py against the real reference (tests/golden/make_flux_golden.py)."""
+    import os
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flux_golden.pt"), weights_only=False)
+    for key, c in g.items():
+        assert torch.equal(O.flux_center_of_mass(c["flux"]), c["center_of_mass"]), key
+        got = O.crop_flux_around_center(c["flux"], c["target_dimensions"], c["crop"][0], c["crop"][1])
+        assert torch.equal(got, c["cropped"]), key
