@@ -241,6 +241,8 @@ def cpu_oracle_step_factory(n: int, threads: int):
     p = 4 * POINTS_PER_FACET[0] * POINTS_PER_FACET[1]
     du, de = O.sun_distortions(RAYS, p, n, 7)
 
+    first = {}
+
     def step():
         opt.zero_grad(set_to_none=True)
         pts, nrm = O.nurbs_points_and_normals(cp, 3, 3, ev, ft["canting"], ft["facet_translations"])
@@ -251,10 +253,32 @@ def cpu_oracle_step_factory(n: int, threads: int):
         total = O.bitmaps_per_target(flux, tidx, tg.n_total)
         loss = (total * total).mean()
         loss.backward()
+        if not first:   # outputs of the very first step (initial control points): the parity reference of the own arm
+            first.update(total=total.detach().clone(), grad=cp.grad.detach().clone(), du=du, de=de)
         opt.step()
         return loss
 
+    step.first = first
     return step, n * p * RAYS
+
+
+def parity_against_cpu_step(dev: torch.device, first: dict) -> dict:
+    """The own arm on the CPU baseline's sample (same field, same distortion samples, first step): per-target flux and
+    control-point gradient against the oracle's - the 'flux max rel err' half of BASELINE.json's metric."""
+    from artist_b200 import ops
+
+    n = first["du"].shape[0]
+    wl = Workload(dev, n, 1, 0)
+    ds = wl.tracer.distortions_dataset
+    ds.distortions_u, ds.distortions_e = first["du"].to(dev), first["de"].to(dev)
+    wl.tracer._packed = ops.pack_distortions(ds.distortions_u, ds.distortions_e)
+    wl.step()
+    total, grad = wl.last_total.detach().cpu(), wl.cp.grad.detach().cpu()
+    return {"flux_max_rel_err": float((total - first["total"]).abs().max() / first["total"].max()),
+            "grad_max_rel_err": float((grad - first["grad"]).abs().max() / first["grad"].abs().max()),
+            "sample": f"{n} heliostats of the bench field, first step, distortion samples of the CPU baseline step; "
+                      "per-target flux relative to its peak, control-point gradient relative to its largest entry; "
+                      "CPU side = oracle port (pinned bit-exact to the reference), GPU side = device trig + fixed-point bitmap"}
 
 
 def run_reference(args) -> None:
@@ -391,6 +415,7 @@ def main() -> None:
             for _ in range(reps):
                 step()
             dt = (time.perf_counter() - t0) / reps
+            out["parity"] = parity_against_cpu_step(dev, step.first)
             out["cpu_baseline"] = {"value": rays / dt, "unit": "rays/s", "cores": threads, "kind": "port",
                                    "sample": f"{CPU_SAMPLE_HELIOSTATS} heliostats ({rays} rays) of the same field per step, "
                                              f"{reps} timed steps after 1 warm-up, torch CPU oracle port with {threads} threads"}
