@@ -54,6 +54,16 @@ struct Window {
 };
 
 constexpr int kWindowSampleStride = 8;
+// diagnostics (only when ab200_trace_args::stats is given): cycles thread 0 spends in each phase of a CTA, summed over
+// the CTAs of a launch: stats[4 + k] forward, stats[12 + k] backward
+#define AB200_PHASE(base, k)                                                                                   \
+    do {                                                                                                        \
+        if (prm.a.stats && threadIdx.x == 0) {                                                                  \
+            const long long t_now = clock64();                                                                  \
+            atomicAdd(reinterpret_cast<unsigned long long*>(prm.a.stats) + (base) + (k), (unsigned long long)(t_now - t_phase)); \
+            t_phase = t_now;                                                                                    \
+        }                                                                                                       \
+    } while (0)
 #ifndef AB200_FWD_THREADS
 #define AB200_FWD_THREADS 1024
 #endif
@@ -689,6 +699,7 @@ trace_fwd_kernel(const TraceParams prm) {
     // start-up loads, all issued before the first barrier so that their latencies overlap: target constants (thread
     // 0), orientation (threads 32..47), incident direction and the window-sample rows (every thread); meanwhile the
     // whole shared-memory window is cleared
+    long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
     const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
     const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
     WindowSamples ws;
@@ -709,6 +720,7 @@ trace_fwd_kernel(const TraceParams prm) {
         for (int i = (n4 << 2) + tid; i < prm.win_cap; i += THREADS) win_u[i] = 0u;
     }
     __syncthreads();
+    AB200_PHASE(4, 0);   // start-up loads + window clear
     PointSrc src;
     src.pts = pts_h;
     src.nrm = nrm_h;
@@ -717,6 +729,7 @@ trace_fwd_kernel(const TraceParams prm) {
 
     Window W;
     place_window<THREADS>(W, prm, T, src, ws, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    AB200_PHASE(4, 1);   // window placement
     float* out_f = prm.a.flux + (size_t)h * U * E;
     unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
     if (prm.self_zero) {
@@ -747,6 +760,7 @@ trace_fwd_kernel(const TraceParams prm) {
         }
     }
     __syncthreads();
+    AB200_PHASE(4, 2);   // clearing the bitmap row outside the window
 
     FwdCtx fc;
     fc.win_u = win_u; fc.win_f = win_f; fc.out_f = out_f;
@@ -786,6 +800,7 @@ trace_fwd_kernel(const TraceParams prm) {
         fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
     }
 
+    AB200_PHASE(4, 3);   // ray loop (thread 0)
     // ---- epilogue: counters, window flush -----------------------------------------------------
     cnt_lam = warp_sum(cnt_lam);
     cnt_int = warp_sum(cnt_int);
@@ -803,6 +818,7 @@ trace_fwd_kernel(const TraceParams prm) {
     if (prm.a.stats && fell_back) atomicAdd(reinterpret_cast<unsigned long long*>(prm.a.stats) + 0, 1ull);
     if (!FP32ACC) __threadfence();  // integer REDs of this thread are performed before the barrier
     __syncthreads();
+    AB200_PHASE(4, 4);   // waiting for the CTA's last warp
 
     const bool single = (prm.split == 1);
     if (tid == 0) {
@@ -857,6 +873,7 @@ trace_fwd_kernel(const TraceParams prm) {
                 }
             }
         }
+        AB200_PHASE(4, 5);   // window flush (thread 0)
     } else {
         for (int r = warp; r < W.wh; r += nwarps) {
             unsigned* orow = out_u + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
@@ -1399,6 +1416,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     const int p_begin = chunk * prm.pts_per_chunk;
     const int p_end = min(P, p_begin + prm.pts_per_chunk);
 
+    long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
     // start-up loads issued together before the first barrier (see trace_fwd_kernel)
     PointSrc src;
     src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
@@ -1411,6 +1429,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
     __syncthreads();
+    AB200_PHASE(12, 0);
     const TargetCtx T = T_sh;
     float gori[12];
 #pragma unroll
@@ -1419,6 +1438,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
 
     Window W;
     place_window<THREADS>(W, prm, T, src, ws, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    AB200_PHASE(12, 1);
     const float* gf = grad_flux + (size_t)h * grad_stride;
     {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
         const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
@@ -1428,6 +1448,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
         }
     }
     __syncthreads();
+    AB200_PHASE(12, 2);  // staging the gradient window
     BwdCtx bc;
     bc.win_g = win_g; bc.gf = gf; bc.e0 = W.e0; bc.u0 = W.u0; bc.ww = W.ww;
     bc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; bc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
@@ -1456,6 +1477,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     } else {
         bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
     }
+    AB200_PHASE(12, 3);  // ray loop (thread 0)
     if (gori_acc) {
         // dL/dO rows 0..2 of this sample: warp shuffle tree, then the warps' partial sums in index order (fixed order);
         // the gradient window in shared memory is dead by now and serves as scratch
@@ -1473,6 +1495,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
             float* dst = grad_orientations + (size_t)h * 16 + tid;
             if (prm.split == 1) *dst = sum; else atomicAdd(dst, sum);   // caller zeroes the buffer (row 3 stays 0)
         }
+        AB200_PHASE(12, 4);  // waiting for the last warp + dL/dO reduction
     }
 }
 

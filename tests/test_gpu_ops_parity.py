@@ -63,6 +63,44 @@ def test_nurbs_backward_matches_autograd():
     assert (cpc.grad.cpu() - cp.grad).abs().max() <= 2e-5 * scale
 
 
+@pytest.mark.parametrize("cps,ppf,deg,canting", [
+    ((10, 10), (50, 50), (3, 3), True),     # the benchmark shape
+    ((20, 20), (13, 11), (3, 3), True),     # more u-spans than grid rows: the window shifts several rows per step
+    ((5, 6), (40, 64), (2, 3), False),      # mixed degrees, no canting, 64 columns per facet
+    ((6, 5), (9, 128), (3, 2), True),       # 128 columns: two facets per CTA
+])
+def test_nurbs_backward_column_walk_kernel(cps, ppf, deg, canting, monkeypatch):
+    """The column-walk backward (default for shared sorted grids) against the oracle's autograd and against the
+    row-block kernel it replaces (AB200_NURBS_BWD_ROWBLOCK=1 selects that one at call time)."""
+    from artist_b200 import ops
+
+    n = 3
+    ft, ev = _nurbs_inputs(n=n, cps=cps, ppf=ppf)
+    k = ppf[0] * ppf[1]
+    torch.manual_seed(1)
+    wp, wn = torch.randn(n, 4, k, 4), torch.randn(n, 4, k, 4)
+    cant = ft["canting"] if canting else None
+    tr = ft["facet_translations"] if canting else None
+    cp = ft["nurbs_control_points"].clone().requires_grad_(True)
+    pts, nrm = O.nurbs_points_and_normals(cp, deg[0], deg[1], ev, cant, tr)
+    ((pts * wp).sum() + (nrm * wn).sum()).backward()
+    ku, kv = O.uniform_knots(cps[0], deg[0]).to(DEV), O.uniform_knots(cps[1], deg[1]).to(DEV)
+    grads = {}
+    for mode in ("cols", "rowblock"):
+        if mode == "rowblock":
+            monkeypatch.setenv("AB200_NURBS_BWD_ROWBLOCK", "1")
+        else:
+            monkeypatch.delenv("AB200_NURBS_BWD_ROWBLOCK", raising=False)
+        cpc = ft["nurbs_control_points"].to(DEV).requires_grad_(True)
+        gp, gn = ops.nurbs_points_and_normals(cpc, ev.to(DEV), ku, kv, deg[0], deg[1], None if cant is None else cant.to(DEV),
+                                              None if tr is None else tr.to(DEV))
+        ((gp * wp.to(DEV)).sum() + (gn * wn.to(DEV)).sum()).backward()
+        grads[mode] = cpc.grad.cpu()
+    scale = cp.grad.abs().max()
+    assert (grads["cols"] - cp.grad).abs().max() <= 2e-5 * scale
+    assert (grads["cols"] - grads["rowblock"]).abs().max() <= 2e-5 * scale
+
+
 def test_nurbs_backward_unstructured_points_use_generic_gather():
     from artist_b200 import ops
 
