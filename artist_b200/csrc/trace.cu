@@ -9,6 +9,7 @@
 // profiles/r01_atomics_microbench.txt).  Integer adds are order independent, so the bitmap is
 // bit-reproducible run to run.  Rays that fall outside the window use integer REDG atomics on
 // the (pre-zeroed) output row itself, which is converted to fp32 in place afterwards.
+#include <cstdint>
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
@@ -45,6 +46,8 @@ struct TraceParams {
     float sigma;        // scatter sigma used for the window margin
     int simple_counts;  // 1: magnitude, (1 - extinction), reflectivity >= 1e-6: lambert > 0 and intensity > 0 hold exactly for valid rays
     int self_zero;      // 1: every CTA clears the part of its bitmap row outside the window itself (no memset pass)
+    int quad;           // 1: E % 4 == 0 and the bitmap rows are 16-byte aligned: the window is placed on 4-column quads, so
+                        //    that clearing, staging and flushing move float4 / uint4
     PackedIdentities ident;  // 1, -0, -1 as run-time values (see common.cuh, packed arithmetic)
 };
 
@@ -53,7 +56,14 @@ struct Window {
     int e0, u0, ww, wh;
 };
 
-constexpr int kWindowSampleStride = 8;
+#ifndef AB200_WIN_SAMPLE_STRIDE
+#define AB200_WIN_SAMPLE_STRIDE 32
+#endif
+// every 32nd surface point places the window: each sampled row is its own 32-byte DRAM sector, and a CTA that floods the
+// load queue with thousands of scattered sector requests spends ~10 % of its life waiting for them (measured with
+// AB200_PHASE: stride 8 -> 19 K cycles before the first barrier).  Neighbouring points reflect to within a few pixels
+// of each other, far inside the 4-sigma margin the window gets anyway.
+constexpr int kWindowSampleStride = AB200_WIN_SAMPLE_STRIDE;
 // diagnostics (only when ab200_trace_args::stats is given): cycles thread 0 spends in each phase of a CTA, summed over
 // the CTAs of a launch: stats[4 + k] forward, stats[12 + k] backward
 #define AB200_PHASE(base, k)                                                                                   \
@@ -177,6 +187,12 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
                     while ((long long)nww * nwh > prm.win_cap) { if (nww > nwh) --nww; else --nwh; }
                     e_lo += (ww - nww) / 2; u_lo += (wh - nwh) / 2;
                     ww = nww; wh = nwh;
+                }
+                if (prm.quad && ww >= 2 && wh >= 2) {   // whole quads: widen to multiples of 4 columns, give rows back if needed
+                    const int a_lo = e_lo & ~3, a_hi = min(E, (e_lo + ww + 3) & ~3);
+                    const int aw = a_hi - a_lo;
+                    if ((long long)aw * wh > prm.win_cap) { const int nwh = prm.win_cap / aw; u_lo += (wh - nwh) / 2; wh = nwh; }
+                    e_lo = a_lo; ww = aw;
                 }
                 if (ww < 2 || wh < 2) { w.e0 = 1 << 28; w.u0 = 1 << 28; w.ww = 0; w.wh = 0; }
                 else { w.e0 = e_lo; w.u0 = u_lo; w.ww = ww; w.wh = wh; }
@@ -737,7 +753,18 @@ trace_fwd_kernel(const TraceParams prm) {
         // rows of the window: [U - u0 - wh, U - 1 - u0], columns [e0, e0 + ww)
         const int r_lo = U - W.u0 - W.wh, r_hi = U - 1 - W.u0, c_lo = W.e0, c_hi = W.e0 + W.ww;
         const int warp_z = tid >> 5, lane_z = tid & 31;
-        if ((E & 3) == 0) {
+        if (prm.quad) {
+            // every quad is entirely inside or outside the window: one predicate and one 16-byte store per quad
+            const int e4 = E >> 2, q_lo = c_lo >> 2, q_hi = c_hi >> 2, n4 = U * e4;
+            const int d_row = THREADS / e4, d_q = THREADS - d_row * e4;
+            float4* o4 = reinterpret_cast<float4*>(out_f);
+            int row = tid / e4, q = tid - row * e4;
+            for (int idx = tid; idx < n4; idx += THREADS) {
+                if (!(row >= r_lo && row <= r_hi && q >= q_lo && q < q_hi)) o4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+                row += d_row; q += d_q;
+                if (q >= e4) { q -= e4; ++row; }
+            }
+        } else if ((E & 3) == 0) {
             const int e4 = E >> 2;
             for (int row = warp_z; row < U; row += THREADS / 32) {
                 float4* o4 = reinterpret_cast<float4*>(out_f + (size_t)row * E);
@@ -845,7 +872,52 @@ trace_fwd_kernel(const TraceParams prm) {
         }
         return;
     }
-    if (single) {
+    if (single && prm.quad && W.ww > 0) {
+        const float inv = prm.fx_inv;
+        const bool any_fb = fallback_sh != 0;
+        {   // window -> output rows, one quad (uint4 -> float4) per thread and iteration
+            const int qw = W.ww >> 2, n4 = W.wh * qw;
+            const int d_r = THREADS / qw, d_q = THREADS - d_r * qw;
+            const uint4* w4 = reinterpret_cast<const uint4*>(win_u);
+            int r = tid / qw, q = tid - r * qw;
+            for (int idx = tid; idx < n4; idx += THREADS) {
+                const uint4 v = w4[idx];
+                float4* orow = reinterpret_cast<float4*>(out_f + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0);
+                __stcs(orow + q, make_float4(__uint2float_rn(v.x) * inv, __uint2float_rn(v.y) * inv, __uint2float_rn(v.z) * inv,
+                                             __uint2float_rn(v.w) * inv));
+                r += d_r; q += d_q;
+                if (q >= qw) { q -= qw; ++r; }
+            }
+        }
+        AB200_PHASE(4, 5);   // window flush (thread 0)
+        if (any_fb) {
+            // integer taps that landed outside the window (on the cleared part of the row): convert in place
+            const int e4 = E >> 2, q_lo = W.e0 >> 2, q_hi = (W.e0 + W.ww) >> 2, n4 = U * e4;
+            const int r_lo = U - W.u0 - W.wh, r_hi = U - 1 - W.u0;
+            const int d_row = THREADS / e4, d_q = THREADS - d_row * e4;
+            uint4* o4 = reinterpret_cast<uint4*>(out_f);
+            int row = tid / e4, q = tid - row * e4;
+            constexpr int kBatch = 4;   // independent L2 reads per thread before the first conversion
+            for (int idx0 = tid; idx0 < n4; idx0 += kBatch * THREADS) {
+                uint4 v[kBatch];
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k) {
+                    const int idx = idx0 + k * THREADS;
+                    v[k] = make_uint4(0u, 0u, 0u, 0u);
+                    if (idx < n4 && !(row >= r_lo && row <= r_hi && q >= q_lo && q < q_hi)) v[k] = __ldcg(o4 + idx);
+                    row += d_row; q += d_q;
+                    if (q >= e4) { q -= e4; ++row; }
+                }
+#pragma unroll
+                for (int k = 0; k < kBatch; ++k)
+                    if (v[k].x | v[k].y | v[k].z | v[k].w)
+                        reinterpret_cast<float4*>(o4)[idx0 + k * THREADS] =
+                            make_float4(__uint2float_rn(v[k].x) * inv, __uint2float_rn(v[k].y) * inv,
+                                        __uint2float_rn(v[k].z) * inv, __uint2float_rn(v[k].w) * inv);
+            }
+        }
+        AB200_PHASE(4, 6);   // conversion of the out-of-window taps (thread 0)
+    } else if (single) {
         const float inv = prm.fx_inv;
         const bool any_fb = fallback_sh != 0;
         for (int r = warp; r < W.wh; r += nwarps) {
@@ -1442,6 +1514,17 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     const float* gf = grad_flux + (size_t)h * grad_stride;
     {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
         const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
+        if (prm.quad && W.ww > 0) {
+            const int qw = W.ww >> 2, n4 = W.wh * qw;
+            const int d_r = THREADS / qw, d_q = THREADS - d_r * qw;
+            float4* w4 = reinterpret_cast<float4*>(win_g);
+            int r = tid / qw, q = tid - r * qw;
+            for (int idx = tid; idx < n4; idx += THREADS) {
+                w4[idx] = __ldg(reinterpret_cast<const float4*>(gf + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0) + q);
+                r += d_r; q += d_q;
+                if (q >= qw) { q -= qw; ++r; }
+            }
+        } else
         for (int r = warp; r < W.wh; r += nwarps) {
             const float* grow = gf + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
             for (int c = lane; c < W.ww; c += 32) win_g[r * W.ww + c] = __ldg(grow + c);
@@ -1569,6 +1652,7 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
     prm.sigma = a->scatter_sigma > 0.f ? a->scatter_sigma : 2.5e-3f;
     prm.ident.one = 1.0f; prm.ident.negzero = -0.0f; prm.ident.negone = -1.0f;
     prm.self_zero = 0;
+    prm.quad = 0;
     prm.simple_counts = (a->ray_magnitude >= 1e-6f && a->one_minus_extinction >= 1e-6f && a->reflectivity >= 1e-6f &&
                          a->ray_magnitude <= 1e6f && a->one_minus_extinction <= 1e6f && a->reflectivity <= 1e6f) ? 1 : 0;
 }
@@ -1656,6 +1740,7 @@ extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
     TraceParams prm;
     fill_params(prm, a, pl);
     prm.self_zero = self_zero ? 1 : 0;
+    prm.quad = (pl.split == 1 && !fp32acc && a->res_e % 4 == 0 && reinterpret_cast<uintptr_t>(a->flux) % 16 == 0) ? 1 : 0;
     cudaError_t e = (pl.threads == kFwdThreadsLarge) ? launch_fwd_trig<kFwdThreadsLarge>(prm, pl, st, dbg, fp32acc)
                                                      : launch_fwd_trig<512>(prm, pl, st, dbg, fp32acc);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_fwd launch failed: %s", cudaGetErrorString(e));
@@ -1690,6 +1775,7 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
     TraceParams prm;
     fill_params(prm, a, pl);
     const long long gstride = b->grad_flux_stride >= 0 ? b->grad_flux_stride : (long long)a->res_u * a->res_e;
+    prm.quad = (pl.split == 1 && a->res_e % 4 == 0 && gstride % 4 == 0 && reinterpret_cast<uintptr_t>(b->grad_flux) % 16 == 0) ? 1 : 0;
     cudaError_t e = (pl.threads == kBwdThreadsLarge)
                         ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations)
                         : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations);

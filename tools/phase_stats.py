@@ -19,7 +19,7 @@ st = ops.trace_stats.tolist()
 ops.trace_stats = None
 print(f"samples {n}: threads on the global fallback {st[0]}; mean window {st[1] / max(st[2], 1):.0f} cells")
 for name, base, labels in (("forward", 4, ["start-up loads + window clear", "window placement", "clear bitmap row outside window",
-                                            "ray loop (thread 0)", "wait for last warp", "window flush"]),
+                                            "ray loop (thread 0)", "wait for last warp", "window flush", "out-of-window tap conversion"]),
                            ("backward", 12, ["start-up loads", "window placement", "stage gradient window", "ray loop (thread 0)",
                                              "wait + dL/dO reduction"])):
     tot = sum(st[base:base + len(labels)])
