@@ -207,6 +207,24 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
+// The quads (4 columns x 1 row, 16 bytes) of a [U,E] bitmap row that lie OUTSIDE a quad-aligned window, enumerated
+// without gaps: first the full rows below / above the window, then the strips left and right of it.
+struct OutsideQuads {
+    int e4, q_lo, qw, side, r_lo, wh, n_full, n_out;
+    __device__ OutsideQuads(const Window& W, int E, int U) {
+        e4 = E >> 2; q_lo = W.e0 >> 2; qw = W.ww >> 2; side = e4 - qw; wh = W.wh;
+        if (W.ww <= 0) { q_lo = 0; qw = 0; side = e4; wh = 0; }
+        r_lo = U - W.u0 - W.wh;   // first output row of the window (output rows are flipped)
+        n_full = (U - wh) * e4; n_out = n_full + wh * side;
+    }
+    __device__ __forceinline__ int at(int i) const {   // quad index (row * e4 + q) of the i-th outside quad
+        int row, q;
+        if (i < n_full) { row = i / e4; q = i - row * e4; if (row >= r_lo) row += wh; }
+        else { const int j = i - n_full, rr = j / side, qq = j - rr * side; row = r_lo + rr; q = qq < q_lo ? qq : qq + qw; }
+        return row * e4 + q;
+    }
+};
+
 struct FwdCtx {
     unsigned* win_u;     // shared-memory window (fixed point) ...
     float* win_f;        // ... or fp32 (AB200_FLAG_FP32_ACCUM)
@@ -492,8 +510,17 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
     const unsigned kMagicBits = 0x4B000000u;   // bits(2^23)
     const bool axis_n = (T.n0 == 0.0f) && (T.n2 == 0.0f);
-    const unsigned bias_e = kMagicBits + (unsigned)fc.e0, bias_u = kMagicBits + (unsigned)fc.u0;
-    const unsigned win_base = (unsigned)__cvta_generic_to_shared(fc.win_u), row_bytes = (unsigned)fc.ww * 4u;
+    // Pixel indices relative to the window come straight out of the floor() trick: be + (1.5 * 2^23 - e0), rounded down,
+    // has the bit pattern 0x4B400000 + (floor(be) - e0) (two's complement wrap-around for negative differences), so
+    // cex = bits - 0x4B400000 costs ONE integer instruction with an immediate operand.  The window's shared-memory
+    // address is kept opaque so that it stays in a register instead of being re-derived for every tap.
+    const int e0w = fc.ww > 0 ? fc.e0 : 0, u0w = fc.ww > 0 ? fc.u0 : 0;   // (an empty window has a huge origin)
+    const float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
+    const unsigned kIdxBits = 0x4B400000u;
+    const unsigned wwm1 = (unsigned)max(fc.ww, 1) - 1u, whm1 = (unsigned)max(fc.wh, 1) - 1u;   // empty window: nothing is "inside"
+    unsigned win_base = (unsigned)__cvta_generic_to_shared(fc.win_u);
+    asm volatile("" : "+r"(win_base));
+    const unsigned row_bytes = (unsigned)fc.ww * 4u;
     // factor counters: valid rays = R * (regular points) - cnt_bad; invalid rays are rare, so the bookkeeping (and the
     // irregularity flag, which implies invalid) lives in a rarely taken branch
     int cnt_bad = 0, n_reg_points = 0, cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
@@ -620,11 +647,11 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             // from one round-down add of 2^23 (FMA pipe) instead of FRND + F2I (XU pipe): for 0 <= x < 2^23 the sum's
             // low mantissa bits ARE floor(x).
             const float kMagic = 8388608.0f;
-            const float2 me = make_float2(__fadd_rd(be.x, kMagic), __fadd_rd(be.y, kMagic));
-            const float2 mu = make_float2(__fadd_rd(bu.x, kMagic), __fadd_rd(bu.y, kMagic));
+            const float2 me = make_float2(__fadd_rd(be.x, magic_e), __fadd_rd(be.y, magic_e));
+            const float2 mu = make_float2(__fadd_rd(bu.x, magic_u), __fadd_rd(bu.y, magic_u));
             // high weights = fractional parts (exact); low weights = 1 - high, the same real number as the reference's
             // (ie + 1) - be with its single rounding placed differently (<= 1 ulp of the weight, 1e-7 of a tap)
-            const float2 whe = K.sub(be, K.sub(me, bc2(kMagic))), whu = K.sub(bu, K.sub(mu, bc2(kMagic)));
+            const float2 whe = K.sub(be, K.sub(me, bc2(magic_e))), whu = K.sub(bu, K.sub(mu, bc2(magic_u)));
             const float2 wle = K.sub(K.one, whe), wlu = K.sub(K.one, whu);
             float2 v1, v2, v3, v4;   // tap values (fp32 accumulate) or 2^23 + round(scaled tap value) (fixed point)
             if (FP32ACC) {
@@ -640,12 +667,11 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
 #pragma unroll
             for (int lane = 0; lane < 2; ++lane) {
                 if (!(lane ? valid1 : valid0)) continue;
-                // a valid ray has me, mu in [2^23, 2^23 + 2^22): bits - bits(2^23) is the pixel index
-                const int cex = (int)(__float_as_uint(lane ? me.y : me.x) - bias_e);
-                const int cux = (int)(__float_as_uint(lane ? mu.y : mu.x) - bias_u);
-                const int ie = cex + fc.e0, iu = cux + fc.u0;   // only the slow paths need the absolute pixel index
+                const int cex = (int)(__float_as_uint(lane ? me.y : me.x) - kIdxBits);   // ie - e0
+                const int cux = (int)(__float_as_uint(lane ? mu.y : mu.x) - kIdxBits);   // iu - u0
+                const int ie = cex + e0w, iu = cux + u0w;   // only the slow paths need the absolute pixel index
                 // inside the window interior: implies ie + 1 < E and iu + 1 < U (the window lies on the bitmap)
-                const bool fast = ((unsigned)cex < (unsigned)fc.wwm1) && ((unsigned)cux < (unsigned)fc.whm1);
+                const bool fast = ((unsigned)cex < wwm1) && ((unsigned)cux < whm1);
                 const float a1 = lane ? v1.y : v1.x, a2 = lane ? v2.y : v2.x, a3 = lane ? v3.y : v3.x, a4 = lane ? v4.y : v4.x;
                 if (FP32ACC) {
                     if (fast) {
@@ -748,23 +774,18 @@ trace_fwd_kernel(const TraceParams prm) {
     AB200_PHASE(4, 1);   // window placement
     float* out_f = prm.a.flux + (size_t)h * U * E;
     unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
-    if (prm.self_zero) {
+    if (prm.self_zero && prm.quad) {
+        // clear the quads the window flush will not overwrite (the global-path taps need zeros to add to): a handful
+        // of 16-byte stores per thread (store bandwidth of an SM is ~32 B/clk: clearing the whole row costs 8 K cycles)
+        const OutsideQuads oq(W, E, U);
+        float4* o4 = reinterpret_cast<float4*>(out_f);
+        for (int i = tid; i < oq.n_out; i += THREADS) o4[oq.at(i)] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (prm.self_zero) {
         // clear the pixels the window flush will not overwrite (the global-path taps need zeros to add to); output
         // rows of the window: [U - u0 - wh, U - 1 - u0], columns [e0, e0 + ww)
         const int r_lo = U - W.u0 - W.wh, r_hi = U - 1 - W.u0, c_lo = W.e0, c_hi = W.e0 + W.ww;
         const int warp_z = tid >> 5, lane_z = tid & 31;
-        if (prm.quad) {
-            // every quad is entirely inside or outside the window: one predicate and one 16-byte store per quad
-            const int e4 = E >> 2, q_lo = c_lo >> 2, q_hi = c_hi >> 2, n4 = U * e4;
-            const int d_row = THREADS / e4, d_q = THREADS - d_row * e4;
-            float4* o4 = reinterpret_cast<float4*>(out_f);
-            int row = tid / e4, q = tid - row * e4;
-            for (int idx = tid; idx < n4; idx += THREADS) {
-                if (!(row >= r_lo && row <= r_hi && q >= q_lo && q < q_hi)) o4[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-                row += d_row; q += d_q;
-                if (q >= e4) { q -= e4; ++row; }
-            }
-        } else if ((E & 3) == 0) {
+        if ((E & 3) == 0) {
             const int e4 = E >> 2;
             for (int row = warp_z; row < U; row += THREADS / 32) {
                 float4* o4 = reinterpret_cast<float4*>(out_f + (size_t)row * E);
@@ -891,27 +912,26 @@ trace_fwd_kernel(const TraceParams prm) {
         }
         AB200_PHASE(4, 5);   // window flush (thread 0)
         if (any_fb) {
-            // integer taps that landed outside the window (on the cleared part of the row): convert in place
-            const int e4 = E >> 2, q_lo = W.e0 >> 2, q_hi = (W.e0 + W.ww) >> 2, n4 = U * e4;
-            const int r_lo = U - W.u0 - W.wh, r_hi = U - 1 - W.u0;
-            const int d_row = THREADS / e4, d_q = THREADS - d_row * e4;
+            // integer taps that landed outside the window (on the cleared part of the row): convert in place.  Only the
+            // out-of-window quads are enumerated: the full rows below / above the window, then the strips left and right
+            // of it - a handful per thread, all of whose L2 reads are in flight together
+            const OutsideQuads oq(W, E, U);
             uint4* o4 = reinterpret_cast<uint4*>(out_f);
-            int row = tid / e4, q = tid - row * e4;
-            constexpr int kBatch = 4;   // independent L2 reads per thread before the first conversion
-            for (int idx0 = tid; idx0 < n4; idx0 += kBatch * THREADS) {
+            constexpr int kBatch = 4;
+            for (int idx0 = tid; idx0 < oq.n_out; idx0 += kBatch * THREADS) {
                 uint4 v[kBatch];
+                int at[kBatch];
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k) {
-                    const int idx = idx0 + k * THREADS;
+                    const int i = idx0 + k * THREADS;
                     v[k] = make_uint4(0u, 0u, 0u, 0u);
-                    if (idx < n4 && !(row >= r_lo && row <= r_hi && q >= q_lo && q < q_hi)) v[k] = __ldcg(o4 + idx);
-                    row += d_row; q += d_q;
-                    if (q >= e4) { q -= e4; ++row; }
+                    at[k] = 0;
+                    if (i < oq.n_out) { at[k] = oq.at(i); v[k] = __ldcg(o4 + at[k]); }
                 }
 #pragma unroll
                 for (int k = 0; k < kBatch; ++k)
                     if (v[k].x | v[k].y | v[k].z | v[k].w)
-                        reinterpret_cast<float4*>(o4)[idx0 + k * THREADS] =
+                        reinterpret_cast<float4*>(o4)[at[k]] =
                             make_float4(__uint2float_rn(v[k].x) * inv, __uint2float_rn(v[k].y) * inv,
                                         __uint2float_rn(v[k].z) * inv, __uint2float_rn(v[k].w) * inv);
             }
