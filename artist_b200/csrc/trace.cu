@@ -1302,11 +1302,12 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     const float k_lam = mag * k_or;                         // intensity = k_lam * (-a)
     const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
     const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
-    const unsigned kMagicBits = 0x4B000000u;
     const bool axis_n = (T.n0 == 0.0f) && (T.n2 == 0.0f);
-    const float kMagic = 8388608.0f;
     const float2 zero2 = make_float2(0.f, 0.f);
-    const unsigned bias_e = kMagicBits + (unsigned)bc.e0, bias_u = kMagicBits + (unsigned)bc.u0;
+    // window-relative pixel indices straight from the floor() trick (see fwd_rays_planar_fast2)
+    const int e0w = bc.ww > 0 ? bc.e0 : 0, u0w = bc.ww > 0 ? bc.u0 : 0;
+    const float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
+    const unsigned kIdxBits = 0x4B400000u;
     bool any_irr = false;
     const int n_pairs = (R + 1) >> 1;
     const long long step_inner = 2 * (long long)P, step_last = (long long)THREADS - (long long)(n_pairs - 1) * 2 * (long long)P;
@@ -1381,37 +1382,50 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                 const bool valid0 = ang0 && fr0 && (__float_as_uint(be0.x) <= em1_bits) && (__float_as_uint(bu0.x) <= um1_bits);
                 const bool valid1 = two && ang1 && fr1 && (__float_as_uint(be0.y) <= em1_bits) && (__float_as_uint(bu0.y) <= um1_bits);
                 const float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
-                const float2 me = make_float2(__fadd_rd(be.x, kMagic), __fadd_rd(be.y, kMagic));
-                const float2 mu = make_float2(__fadd_rd(bu.x, kMagic), __fadd_rd(bu.y, kMagic));
-                const int ie0 = (int)(__float_as_uint(me.x) - kMagicBits), iu0 = (int)(__float_as_uint(mu.x) - kMagicBits);
-                const int ie1 = (int)(__float_as_uint(me.y) - kMagicBits), iu1 = (int)(__float_as_uint(mu.y) - kMagicBits);
+                const float2 me = make_float2(__fadd_rd(be.x, magic_e), __fadd_rd(be.y, magic_e));
+                const float2 mu = make_float2(__fadd_rd(bu.x, magic_u), __fadd_rd(bu.y, magic_u));
+                const int cex0 = (int)(__float_as_uint(me.x) - kIdxBits), cux0 = (int)(__float_as_uint(mu.x) - kIdxBits);   // ie - e0, iu - u0
+                const int cex1 = (int)(__float_as_uint(me.y) - kIdxBits), cux1 = (int)(__float_as_uint(mu.y) - kIdxBits);
                 if (!(valid0 && valid1))   // rare; irregular implies invalid
                     any_irr |= !ang0 || ((a.x < 0.0f) && !fr0) || (two && (!ang1 || ((a.y < 0.0f) && !fr1)));
-                // on the bitmap: ie + 1 < E and iu + 1 < U (the lower bounds hold for valid rays)
-                const bool live0 = valid0 && ((unsigned)ie0 < (unsigned)(E - 1)) && ((unsigned)iu0 < (unsigned)(U - 1));
-                const bool live1 = valid1 && ((unsigned)ie1 < (unsigned)(E - 1)) && ((unsigned)iu1 < (unsigned)(U - 1));
-                if (!(live0 || live1)) continue;
+                // ---- gather the four gradient taps per live lane ----
+                // window interior (implies on the bitmap: ie + 1 < E and iu + 1 < U)
+                const bool in0 = valid0 && ((unsigned)cex0 < (unsigned)bc.wwm1) && ((unsigned)cux0 < (unsigned)bc.whm1);
+                const bool in1 = valid1 && ((unsigned)cex1 < (unsigned)bc.wwm1) && ((unsigned)cux1 < (unsigned)bc.whm1);
+                float2 g1, g2, g3, g4;
+                bool live0 = true, live1 = true;
+                if (in0 && in1) {   // the common case: eight shared-memory loads
+                    const float* b0 = bc.win_g + cux0 * bc.ww + cex0;
+                    const float* b1 = bc.win_g + cux1 * bc.ww + cex1;
+                    g1.x = b0[bc.ww]; g2.x = b0[bc.ww + 1]; g3.x = b0[1]; g4.x = b0[0];
+                    g1.y = b1[bc.ww]; g2.y = b1[bc.ww + 1]; g3.y = b1[1]; g4.y = b1[0];
+                } else {
+                    g1 = g2 = g3 = g4 = zero2;
+                    // on the bitmap: ie + 1 < E and iu + 1 < U (the lower bounds hold for valid rays)
+                    const int ie0 = cex0 + e0w, iu0 = cux0 + u0w, ie1 = cex1 + e0w, iu1 = cux1 + u0w;
+                    live0 = valid0 && ((unsigned)ie0 < (unsigned)(E - 1)) && ((unsigned)iu0 < (unsigned)(U - 1));
+                    live1 = valid1 && ((unsigned)ie1 < (unsigned)(E - 1)) && ((unsigned)iu1 < (unsigned)(U - 1));
+                    if (!(live0 || live1)) continue;
+#pragma unroll
+                    for (int lane = 0; lane < 2; ++lane) {
+                        if (!(lane ? live1 : live0)) continue;
+                        const int ie = lane ? ie1 : ie0, iu = lane ? iu1 : iu0;
+                        const int cex = lane ? cex1 : cex0, cux = lane ? cux1 : cux0;
+                        float t1, t2, t3, t4;
+                        if (lane ? in1 : in0) {
+                            const float* b = bc.win_g + cux * bc.ww + cex;
+                            t1 = b[bc.ww]; t2 = b[bc.ww + 1]; t3 = b[1]; t4 = b[0];
+                        } else {
+                            const float* row_hi = bc.gf + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                            const float* row_lo = row_hi + E;
+                            t1 = __ldg(row_hi); t2 = __ldg(row_hi + 1); t3 = __ldg(row_lo + 1); t4 = __ldg(row_lo);
+                        }
+                        if (lane) { g1.y = t1; g2.y = t2; g3.y = t3; g4.y = t4; } else { g1.x = t1; g2.x = t2; g3.x = t3; g4.x = t4; }
+                    }
+                }
                 // fractional parts (exact); the low weights are 1 - high here - the last-bit difference to the forward's
                 // (ie + 1) - be only touches the gradient VALUE, never the pixel choice
-                float2 whe = K.sub(be, K.sub(me, bc2(kMagic))), whu = K.sub(bu, K.sub(mu, bc2(kMagic)));
-                // ---- gather the four gradient taps per live lane ----
-                float2 g1 = zero2, g2 = zero2, g3 = zero2, g4 = zero2;
-#pragma unroll
-                for (int lane = 0; lane < 2; ++lane) {
-                    if (!(lane ? live1 : live0)) continue;
-                    const int ie = lane ? ie1 : ie0, iu = lane ? iu1 : iu0;
-                    const int cex = (int)(__float_as_uint(lane ? me.y : me.x) - bias_e), cux = (int)(__float_as_uint(lane ? mu.y : mu.x) - bias_u);
-                    float t1, t2, t3, t4;
-                    if (((unsigned)cex < (unsigned)bc.wwm1) && ((unsigned)cux < (unsigned)bc.whm1)) {
-                        const float* b = bc.win_g + cux * bc.ww + cex;
-                        t1 = b[bc.ww]; t2 = b[bc.ww + 1]; t3 = b[1]; t4 = b[0];
-                    } else {
-                        const float* row_hi = bc.gf + (size_t)(U - 1 - (iu + 1)) * E + ie;
-                        const float* row_lo = row_hi + E;
-                        t1 = __ldg(row_hi); t2 = __ldg(row_hi + 1); t3 = __ldg(row_lo + 1); t4 = __ldg(row_lo);
-                    }
-                    if (lane) { g1.y = t1; g2.y = t2; g3.y = t3; g4.y = t4; } else { g1.x = t1; g2.x = t2; g3.x = t3; g4.x = t4; }
-                }
+                float2 whe = K.sub(be, K.sub(me, bc2(magic_e))), whu = K.sub(bu, K.sub(mu, bc2(magic_u)));
                 float2 dead_scale = make_float2(1.f, 1.f);
                 if (!(live0 && live1)) {   // rare: silence the dead lane (its values may be anything, even NaN)
                     if (!live0) {

@@ -304,6 +304,8 @@ class _PerTargetFn(torch.autograd.Function):
         target_idx_object = target_idx
         target_idx = _i32(target_idx, "target_area_indices")
         n, u, e = bitmaps.shape
+        if n_targets > 1 and bitmaps.requires_grad:
+            prefetch_uniform_target(target_idx_object)
         out = torch.empty(n_targets, u, e, device=bitmaps.device)
         _lib.call("ab200_bitmaps_per_target", _p(bitmaps), _p(target_idx), n, n_targets, u, e, _p(out), _stream())
         ctx.save_for_backward(target_idx)
@@ -333,8 +335,13 @@ def _uniform_target(target_idx: torch.Tensor) -> int | None:
     hit = _uniform_cache.get(id(target_idx))
     if hit is not None and hit[0]() is target_idx and hit[1] == target_idx._version:
         return hit[2]
+    pend = _uniform_pending.pop(id(target_idx), None)
     if target_idx.numel() == 0:
         result = None
+    elif pend is not None and pend[0]() is target_idx and pend[1] == target_idx._version:
+        pend[3].synchronize()   # the side-stream check started by prefetch_uniform_target: long finished by now
+        lo_hi = pend[2].tolist()
+        result = int(lo_hi[0]) if lo_hi[0] == lo_hi[1] else None
     else:
         lo, hi = torch.aminmax(target_idx)
         lo_hi = torch.stack([lo, hi]).tolist()
@@ -343,6 +350,41 @@ def _uniform_target(target_idx: torch.Tensor) -> int | None:
         _uniform_cache.clear()
     _uniform_cache[id(target_idx)] = (weakref.ref(target_idx), target_idx._version, result)
     return result
+
+
+_uniform_pending: dict = {}
+_side_stream: "torch.cuda.Stream | None" = None
+
+
+def prefetch_uniform_target(target_idx: torch.Tensor) -> None:
+    """Start the "do all samples aim at ONE target?" check of ``_uniform_target`` on a side stream, result into pinned host
+    memory.  ``trace_rays`` calls this before it launches the forward trace, so by the time the backward pass asks, the
+    answer is on the host and no device->host read has to wait in the middle of the step (which would drain the launch
+    pipeline).  No-op when the answer for this tensor object and version is already known or on its way."""
+    import weakref
+
+    global _side_stream
+    if not target_idx.is_cuda or target_idx.numel() == 0:
+        return
+    k = id(target_idx)
+    for table in (_uniform_cache, _uniform_pending):
+        hit = table.get(k)
+        if hit is not None and hit[0]() is target_idx and hit[1] == target_idx._version:
+            return
+    dev = target_idx.device
+    if _side_stream is None or _side_stream.device != dev:
+        _side_stream = torch.cuda.Stream(device=dev)
+    _side_stream.wait_stream(torch.cuda.current_stream(dev))
+    host = torch.empty(2, dtype=target_idx.dtype, pin_memory=True)
+    with torch.cuda.stream(_side_stream):
+        lo, hi = torch.aminmax(target_idx)
+        host.copy_(torch.stack([lo, hi]), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(_side_stream)
+    target_idx.record_stream(_side_stream)
+    if len(_uniform_pending) > 64:
+        _uniform_pending.clear()
+    _uniform_pending[k] = (weakref.ref(target_idx), target_idx._version, host, done)
 
 
 def bitmaps_per_target(bitmaps, target_idx, n_targets: int):

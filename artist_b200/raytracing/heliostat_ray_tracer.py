@@ -97,6 +97,8 @@ class HeliostatRayTracer:
             ray_magnitude=float(self.ray_magnitude), ray_extinction_factor=ray_extinction_factor,
             mirror_reflectivity=mirror_reflectivity, scatter_sigma=sigma)
         blocking = self._blocking_inputs(target_area_indices) if self.blocking_active else None
+        if torch.is_grad_enabled() and self._targets.n_planar + self._targets.n_cyl > 1:
+            ops.prefetch_uniform_target(target_area_indices)   # for get_bitmaps_per_target's backward, off the critical path
         fused = group._fused_alignment()
         if fused is not None:   # alignment not materialised: the kernels rotate the un-aligned rows themselves
             points, normals, orientations = fused
@@ -178,8 +180,13 @@ class HeliostatRayTracer:
     def get_bitmaps_per_target(self, bitmaps_per_heliostat: torch.Tensor, target_area_indices: torch.Tensor,
                                device: torch.device | None = None) -> torch.Tensor:
         """``[N,U,E]`` -> ``[T,U,E]`` (``:563-608``)."""
-        n_targets = int(self.scenario.solar_tower.number_of_target_areas_per_type.sum())
-        return ops.bitmaps_per_target(bitmaps_per_heliostat, target_area_indices, n_targets)
+        # the count lives in a device tensor (as upstream): read it once per tensor version, not once per call (a
+        # device->host read in the middle of every step stalls the launch pipeline)
+        per_type = self.scenario.solar_tower.number_of_target_areas_per_type
+        key = (id(per_type), per_type._version)
+        if getattr(self, "_n_targets_key", None) != key:
+            self._n_targets, self._n_targets_key, self._n_targets_ref = int(per_type.sum()), key, per_type
+        return ops.bitmaps_per_target(bitmaps_per_heliostat, target_area_indices, self._n_targets)
 
     def bilinear_splatting(self, bitmap_intersections_e: torch.Tensor, bitmap_intersections_u: torch.Tensor,
                            absolute_intensities: torch.Tensor, device: torch.device | None = None) -> torch.Tensor:
