@@ -35,6 +35,37 @@ def test_nurbs_forward_bit_equal_points(canting, cps, ppf):
     assert (gn.cpu() - nrm).abs().max() <= 2.4e-7
 
 
+@pytest.mark.parametrize("cps,ppf,deg,canting", [
+    ((10, 10), (50, 50), (3, 3), True),
+    ((20, 20), (13, 11), (3, 3), True),
+    ((5, 6), (40, 64), (2, 3), False),
+    ((6, 5), (9, 128), (3, 2), True),
+])
+def test_nurbs_forward_column_walk_equals_row_table_kernel(cps, ppf, deg, canting, monkeypatch):
+    """The column-walk forward (default for shared sorted grids) issues the reference's strict mul/add sequence as
+    packed operations: points AND normals must equal the row-table kernel's bit for bit (AB200_NURBS_FWD_ROWTABLE=1
+    selects that one at call time), and the points must equal the oracle's."""
+    from artist_b200 import ops
+
+    ft, ev = _nurbs_inputs(n=3, cps=cps, ppf=ppf)
+    cant = ft["canting"] if canting else None
+    tr = ft["facet_translations"] if canting else None
+    ku, kv = O.uniform_knots(cps[0], deg[0]).to(DEV), O.uniform_knots(cps[1], deg[1]).to(DEV)
+    res = {}
+    for mode in ("cols", "rowtable"):
+        if mode == "rowtable":
+            monkeypatch.setenv("AB200_NURBS_FWD_ROWTABLE", "1")
+        else:
+            monkeypatch.delenv("AB200_NURBS_FWD_ROWTABLE", raising=False)
+        gp, gn = ops.nurbs_points_and_normals(ft["nurbs_control_points"].to(DEV), ev.to(DEV), ku, kv, deg[0], deg[1],
+                                              None if cant is None else cant.to(DEV), None if tr is None else tr.to(DEV))
+        res[mode] = (gp.cpu(), gn.cpu())
+    assert torch.equal(res["cols"][0], res["rowtable"][0]) and torch.equal(res["cols"][1], res["rowtable"][1])
+    pts, nrm = O.nurbs_points_and_normals(ft["nurbs_control_points"], deg[0], deg[1], ev, cant, tr)
+    assert torch.equal(res["cols"][0], pts), f"max diff {(res['cols'][0] - pts).abs().max():.3e}"
+    assert (res["cols"][1] - nrm).abs().max() <= 2.4e-7
+
+
 def test_nurbs_degree_2_and_shared_grid():
     from artist_b200 import ops
 
