@@ -110,6 +110,10 @@ EXPORTS = {
     "ab200_flux_crop_fwd": ([c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p, C.c_void_p], C.c_int32),
     "ab200_flux_crop_bwd": ([c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p,
                              C.c_void_p], C.c_int32),
+    "ab200_flux_loss_fwd": ([c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_float_p, c_float_p, C.c_void_p],
+                            C.c_int32),
+    "ab200_flux_loss_bwd": ([c_float_p, c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, c_float_p,
+                            C.c_void_p], C.c_int32),
     "ab200_reflect": ([c_float_p, c_float_p, C.c_int32, C.c_int32, c_float_p, C.c_void_p], C.c_int32),
     "ab200_scatter_rays": ([c_float_p, c_float_p, c_float_p, C.c_int32, C.c_int32, C.c_int32, c_float_p, C.c_void_p], C.c_int32),
     "ab200_line_intersections": ([c_float_p, c_float_p, c_float_p, C.POINTER(Targets), c_int_p, C.c_int32, C.c_int32,

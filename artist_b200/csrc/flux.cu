@@ -159,6 +159,79 @@ __global__ void __launch_bounds__(256) flux_crop_bwd_kernel(const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Losses on flux bitmaps (artist/optim/loss.py): PixelLoss :251-319 and KLDivergenceLoss :322-410, reduced over the
+// whole bitmap (reduction_dimensions = (1, 2), what every caller passes).  One CTA per sample; the bitmap pair is
+// read once from HBM (the second pass of the KL loss hits L1/L2), the reference re-reads both [N,U,E] tensors once per
+// eager op (normalise, add, log, KLDiv, sum: ~10 passes).
+//   kind 0: loss = sum (p - g)^2 / sum g
+//   kind 1: P = g / max(sum |g|, 1e-12), Q = p / max(sum |p|, 1e-12), lP = log(P + 1e-12), lQ = log(Q + 1e-12),
+//           loss = sum exp(lP) * (lP - lQ)                       (KLDivLoss(reduction="none", log_target=True))
+// aux[b] = (sum g | max(sum|p|,eps), max(sum|g|,eps), sum_x A_x Q_x with A_x = -exp(lP_x) / (Q_x + eps), sum|p| > eps)
+// ---------------------------------------------------------------------------------------------
+constexpr float kLossEps = 1e-12f;
+
+__global__ void __launch_bounds__(256) flux_loss_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt, int n_px,
+                                                            int kind, float* __restrict__ loss, float* __restrict__ aux) {
+    __shared__ float red[96];
+    const int b = blockIdx.x;
+    const float* p = pred + (size_t)b * n_px;
+    const float* g = gt + (size_t)b * n_px;
+    if (kind == 0) {
+        float se = 0.f, sg = 0.f, unused = 0.f;
+        for (int k = threadIdx.x; k < n_px; k += blockDim.x) {
+            const float pv = __ldg(p + k), gv = __ldg(g + k), d = pv - gv;
+            se = fmaf(d, d, se); sg += gv;
+        }
+        block_sum3(se, sg, unused, red);
+        if (threadIdx.x == 0) { loss[b] = se / sg; aux[4 * b] = sg; aux[4 * b + 1] = 0.f; aux[4 * b + 2] = 0.f; aux[4 * b + 3] = 0.f; }
+        return;
+    }
+    float sp = 0.f, sg = 0.f, unused = 0.f;
+    for (int k = threadIdx.x; k < n_px; k += blockDim.x) { sp += fabsf(__ldg(p + k)); sg += fabsf(__ldg(g + k)); }
+    block_sum3(sp, sg, unused, red);
+    const float dp = fmaxf(sp, kLossEps), dg = fmaxf(sg, kLossEps);
+    float kl = 0.f, saq = 0.f;
+    for (int k = threadIdx.x; k < n_px; k += blockDim.x) {
+        const float P = __ldg(g + k) / dg, Q = __ldg(p + k) / dp;
+        const float lP = logf(P + kLossEps), lQ = logf(Q + kLossEps);
+        const float eP = expf(lP);
+        kl = fmaf(eP, lP - lQ, kl);
+        saq = fmaf(-eP / (Q + kLossEps), Q, saq);
+    }
+    unused = 0.f;
+    block_sum3(kl, saq, unused, red);
+    if (threadIdx.x == 0) {
+        loss[b] = kl;
+        aux[4 * b] = dp; aux[4 * b + 1] = dg; aux[4 * b + 2] = saq; aux[4 * b + 3] = sp > kLossEps ? 1.0f : 0.0f;
+    }
+}
+
+// d loss[b] / d prediction[b, :, :] * grad_loss[b]
+__global__ void __launch_bounds__(256) flux_loss_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ gt,
+                                                            const float* __restrict__ aux, const float* __restrict__ grad_loss,
+                                                            int n_px, int kind, float* __restrict__ grad_pred) {
+    const int b = blockIdx.y;
+    const float* p = pred + (size_t)b * n_px;
+    const float* g = gt + (size_t)b * n_px;
+    float* o = grad_pred + (size_t)b * n_px;
+    const float gl = grad_loss[b];
+    if (kind == 0) {
+        const float k2 = 2.0f * gl / aux[4 * b];
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_px; k += gridDim.x * blockDim.x) o[k] = k2 * (__ldg(p + k) - __ldg(g + k));
+        return;
+    }
+    const float dp = aux[4 * b], dg = aux[4 * b + 1], saq = aux[4 * b + 2], through_norm = aux[4 * b + 3];
+    const float inv_dp = gl / dp;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_px; k += gridDim.x * blockDim.x) {
+        const float pv = __ldg(p + k);
+        const float P = __ldg(g + k) / dg, Q = pv / dp;
+        const float A = -expf(logf(P + kLossEps)) / (Q + kLossEps);
+        const float sgn = pv > 0.f ? 1.0f : (pv < 0.f ? -1.0f : 0.0f);
+        o[k] = inv_dp * (A - through_norm * sgn * saq);
+    }
+}
+
 }  // namespace ab200
 
 using namespace ab200;
@@ -212,6 +285,33 @@ extern "C" int32_t ab200_flux_crop_bwd(const float* bitmaps, const float* scale,
     dim3 grid((unsigned)((res_u * res_e + 1023) / 1024), (unsigned)n_bitmaps);
     flux_crop_bwd_kernel<<<grid, 256, 0, st>>>(scale, moments, scratch, grad_out, res_u, res_e, grad_in);
     note_launch(2);
+    AB200_CUDA_TRY(cudaGetLastError());
+    return AB200_OK;
+}
+
+extern "C" int32_t ab200_flux_loss_fwd(const float* prediction, const float* ground_truth, int32_t n_bitmaps, int32_t res_u,
+                                       int32_t res_e, int32_t kind, float* loss, float* aux, void* stream) {
+    AB200_REQUIRE(prediction && ground_truth && loss && aux, AB200_EINVAL, "NULL pointer");
+    AB200_REQUIRE(n_bitmaps >= 0 && res_u >= 1 && res_e >= 1, AB200_EINVAL, "bad sizes");
+    AB200_REQUIRE(kind == AB200_LOSS_PIXEL || kind == AB200_LOSS_KL_DIVERGENCE, AB200_EINVAL, "unknown loss kind %d", kind);
+    if (n_bitmaps == 0) return AB200_OK;
+    flux_loss_fwd_kernel<<<n_bitmaps, 256, 0, static_cast<cudaStream_t>(stream)>>>(prediction, ground_truth, res_u * res_e, kind, loss, aux);
+    note_launch();
+    AB200_CUDA_TRY(cudaGetLastError());
+    return AB200_OK;
+}
+
+extern "C" int32_t ab200_flux_loss_bwd(const float* prediction, const float* ground_truth, const float* aux, const float* grad_loss,
+                                       int32_t n_bitmaps, int32_t res_u, int32_t res_e, int32_t kind, float* grad_prediction,
+                                       void* stream) {
+    AB200_REQUIRE(prediction && ground_truth && aux && grad_loss && grad_prediction, AB200_EINVAL, "NULL pointer");
+    AB200_REQUIRE(n_bitmaps >= 0 && n_bitmaps <= 65535 && res_u >= 1 && res_e >= 1, AB200_EINVAL, "bad sizes");
+    AB200_REQUIRE(kind == AB200_LOSS_PIXEL || kind == AB200_LOSS_KL_DIVERGENCE, AB200_EINVAL, "unknown loss kind %d", kind);
+    if (n_bitmaps == 0) return AB200_OK;
+    dim3 grid((unsigned)((res_u * res_e + 1023) / 1024), (unsigned)n_bitmaps);
+    flux_loss_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(prediction, ground_truth, aux, grad_loss, res_u * res_e, kind,
+                                                                            grad_prediction);
+    note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }

@@ -449,6 +449,43 @@ def flux_crop_around_center(bitmaps: torch.Tensor, scale: torch.Tensor) -> torch
     return _FluxCropFn.apply(bitmaps, scale)
 
 
+LOSS_PIXEL, LOSS_KL_DIVERGENCE = 0, 1
+
+
+class _FluxLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prediction, ground_truth, kind):
+        prediction = _f32(prediction, "prediction")
+        ground_truth = _f32(ground_truth.detach(), "ground_truth")
+        if prediction.dim() != 3 or prediction.shape != ground_truth.shape:
+            raise _lib.Ab200Error(f"prediction and ground_truth must both be [N,U,E], got {tuple(prediction.shape)} and "
+                                  f"{tuple(ground_truth.shape)}")
+        n, u, e = prediction.shape
+        loss = torch.empty(n, device=prediction.device)
+        aux = torch.empty(n, 4, device=prediction.device)
+        _lib.call("ab200_flux_loss_fwd", _p(prediction), _p(ground_truth), n, u, e, kind, _p(loss), _p(aux), _stream())
+        ctx.save_for_backward(prediction, ground_truth, aux)
+        ctx.kind = kind
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        prediction, ground_truth, aux = ctx.saved_tensors
+        n, u, e = prediction.shape
+        g_loss = _f32(g_loss, "grad_loss")
+        g = torch.empty_like(prediction)
+        _lib.call("ab200_flux_loss_bwd", _p(prediction), _p(ground_truth), _p(aux), _p(g_loss), n, u, e, ctx.kind, _p(g),
+                  _stream())
+        return g, None, None
+
+
+def flux_loss(prediction: torch.Tensor, ground_truth: torch.Tensor, kind: int) -> torch.Tensor:
+    """Per-sample loss ``[N]`` of ``[N,U,E]`` flux bitmaps against a (constant) ground truth, reduced over the whole
+    bitmap: ``LOSS_PIXEL`` (``artist/optim/loss.py:251-319``) or ``LOSS_KL_DIVERGENCE`` (``:322-410``).  One fused
+    kernel forward, one backward (gradient w.r.t. the prediction)."""
+    return _FluxLossFn.apply(prediction, ground_truth, kind)
+
+
 # --------------------------------------------------------------------------------------------
 # NURBS
 # --------------------------------------------------------------------------------------------

@@ -300,6 +300,21 @@ int32_t ab200_flux_crop_bwd(const float* bitmaps, const float* scale, const floa
                             int32_t n_bitmaps, int32_t res_u, int32_t res_e, float* scratch, float* grad_in, void* stream);
 
 /*
+ * Losses on flux bitmaps (artist/optim/loss.py), reduced over the whole bitmap (reduction_dimensions = (1, 2)):
+ *   AB200_LOSS_PIXEL          PixelLoss :251-319:        loss[b] = sum (p - g)^2 / sum g
+ *   AB200_LOSS_KL_DIVERGENCE  KLDivergenceLoss :322-410: both bitmaps L1-normalised (eps 1e-12), + 1e-12, log,
+ *                                                        KLDivLoss(log_target=True), summed
+ * prediction, ground_truth [n,U,E]; loss [n]; aux [n,4] (kept for the backward).  ab200_flux_loss_bwd writes
+ * grad_prediction [n,U,E] = d loss[b] / d prediction * grad_loss[b] (the ground truth is a constant).
+ */
+#define AB200_LOSS_PIXEL 0
+#define AB200_LOSS_KL_DIVERGENCE 1
+int32_t ab200_flux_loss_fwd(const float* prediction, const float* ground_truth, int32_t n_bitmaps, int32_t res_u, int32_t res_e,
+                            int32_t kind, float* loss, float* aux, void* stream);
+int32_t ab200_flux_loss_bwd(const float* prediction, const float* ground_truth, const float* aux, const float* grad_loss,
+                            int32_t n_bitmaps, int32_t res_u, int32_t res_e, int32_t kind, float* grad_prediction, void* stream);
+
+/*
  * ab200_trace_host - end-to-end convenience entry with HOST buffers: uploads the per-call inputs
  * (incident directions, target indices, aligned points/normals if given on the host), traces,
  * and downloads the per-target bitmaps.  Device scratch is supplied by the caller.

@@ -831,3 +831,21 @@ def crop_flux_around_center(bitmaps: torch.Tensor, target_dimensions: torch.Tens
     theta[:, 1, 2] = cy
     grid = torch.nn.functional.affine_grid(theta, size=[n, 1, height, width], align_corners=True)
     return torch.nn.functional.grid_sample(bitmaps[:, None], grid, align_corners=True, padding_mode="zeros")[:, 0]
+
+
+# --------------------------------------------------------------------------------------------
+# bitmap losses  (artist/optim/loss.py:251-319 PixelLoss, :322-410 KLDivergenceLoss)
+# --------------------------------------------------------------------------------------------
+def pixel_loss(prediction: torch.Tensor, ground_truth: torch.Tensor, reduction_dimensions=(1, 2)) -> torch.Tensor:
+    """``loss.py:317-319``: summed squared error per sample / total ground-truth intensity of the sample."""
+    return torch.nn.functional.mse_loss(prediction, ground_truth, reduction="none").sum(dim=reduction_dimensions) / \
+        ground_truth.sum(dim=(1, 2))
+
+
+def kl_divergence_loss(prediction: torch.Tensor, ground_truth: torch.Tensor, reduction_dimensions=(1, 2)) -> torch.Tensor:
+    """``loss.py:389-410``: both bitmaps L1-normalised (eps), shifted by eps, ``KLDivLoss(log_target=True)`` of the logs."""
+    eps = 1e-12
+    p = torch.nn.functional.normalize(ground_truth, p=1, dim=(1, 2), eps=eps)
+    q = torch.nn.functional.normalize(prediction, p=1, dim=(1, 2), eps=eps)
+    loss = torch.nn.functional.kl_div(torch.log(q + eps), torch.log(p + eps), reduction="none", log_target=True)
+    return loss.sum(dim=reduction_dimensions)

@@ -106,3 +106,18 @@ def test_flux_center_of_mass_and_crop_bit_exact():
         assert torch.equal(O.flux_center_of_mass(c["flux"]), c["center_of_mass"]), key
         got = O.crop_flux_around_center(c["flux"], c["target_dimensions"], c["crop"][0], c["crop"][1])
         assert torch.equal(got, c["cropped"]), key
+
+
+def test_bitmap_losses_bit_exact():
+    """The oracle's restatement of PixelLoss / KLDivergenceLoss against the real reference (tests/golden/make_loss_golden.py),
+    forward values and the autograd gradient w.r.t. the prediction."""
+    import os
+
+    g = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loss_golden.pt"), weights_only=False)
+    for key, c in g.items():
+        for name, fn in (("pixel", O.pixel_loss), ("kl", O.kl_divergence_loss)):
+            pred = c["prediction"].clone().requires_grad_(True)
+            loss = fn(pred, c["ground_truth"])
+            assert torch.equal(loss.detach(), c[name]), (key, name)
+            (loss * c["weights"]).sum().backward()
+            assert torch.equal(pred.grad, c[name + "_grad"]), (key, name)

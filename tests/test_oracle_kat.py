@@ -84,3 +84,25 @@ def test_splat_drops_last_row_and_column():
     assert out.shape == (1, 6, 8)
     torch.testing.assert_close(out.sum(), torch.tensor(1.0))          # only the third ray lands
     assert out[0, 6 - 1 - 1, 0] == 0.5 and out[0, 6 - 1 - 2, 0] == 0.5  # rows flipped
+
+
+# the reference's known-answer tests of the bitmap losses (tests/optim/test_loss_functions.py:266-342 pixel, :345-445 KL)
+PIXEL_KATS = [
+    ([[[1.0, 2.0], [3.0, 4.0]]], [[[1.0, 2.0], [3.0, 4.0]]], [0.0]),
+    ([[[2.0, 3.0], [9.0, 12.0]]], [[[1.0, 2.0], [8.0, 6.0]]], [2.2941176470588234]),
+]
+_A = [[0.5, 0.75, 0.41], [0.11, 2.55, 3.09]]
+_B = [[5.4, 5.71, 2.46], [2.86, 0.44, 0.11]]
+KL_KATS = [
+    ([[[0.5, 0.5]]], [[[0.5, 0.5]]], [0.0]),
+    ([_B, _A], [_A, _B], [2.311237096786, 1.351369142532]),
+    ([_A, _B], [_B, _A], [1.351369142532, 2.311237096786]),
+]
+
+
+def test_bitmap_loss_kats():
+    for pred, gt, want in PIXEL_KATS:
+        torch.testing.assert_close(O.pixel_loss(torch.tensor(pred), torch.tensor(gt)), torch.tensor(want), atol=1e-6, rtol=1e-6)
+    for pred, gt, want in KL_KATS:
+        torch.testing.assert_close(O.kl_divergence_loss(torch.tensor(pred), torch.tensor(gt)), torch.tensor(want), atol=1e-6,
+                                   rtol=1e-6)
