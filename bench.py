@@ -56,6 +56,26 @@ def measured_traffic(kernel: str, rays_per_launch: int) -> float | None:
         return None
 
 
+def issue_roof(kernel: str, rays_per_launch: int, kernel_ms: float, sm_mhz: float | None) -> dict | None:
+    """The roof that actually binds the trace kernels: warp-instruction issue (4 per clock and SM).  Instruction count per
+    launch from the committed ncu capture (profiles/trace_traffic.json), duration and SM clock measured live."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "trace_traffic.json")) as fh:
+            t = json.load(fh)
+        if int(t["rays_per_launch"]) != int(rays_per_launch):
+            return None
+        inst = float(t["kernels"][kernel]["warp_instructions_per_launch"])
+    except Exception:
+        return None
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    clock_hz = (sm_mhz or 1965.0) * 1e6
+    peak = sms * 4 * clock_hz
+    achieved = inst / (kernel_ms * 1e-3)
+    return {"bound": "issue", "kernel": kernel, "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instructions/s",
+            "frac": achieved / peak, "warp_instructions_per_launch": inst,
+            "note": "smsp__inst_executed.sum of the committed ncu capture / live kernel time; peak = SMs x 4 issue slots x live SM clock"}
+
+
 def measured_peak_hbm() -> tuple[float, str]:
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -406,6 +426,9 @@ def main() -> None:
                          "fwd_bwd_trace_frac": (wl.rays_per_step * (bf + bb) / ((kern_ms["ab200_trace_fwd"] + kern_ms["ab200_trace_bwd"]) * 1e-3) / 1e9) / peak},
             "clocks": clocks,
         }
+        second = issue_roof(dom, wl.rays_per_step, kern_ms[dom], (clocks or {}).get("sm_mhz"))
+        if second is not None:
+            out["roofline"]["second_roof"] = second
         if world == 1 and not args.skip_cpu_baseline:
             threads = os.cpu_count() or 1
             step, rays = cpu_oracle_step_factory(CPU_SAMPLE_HELIOSTATS, threads)

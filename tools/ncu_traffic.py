@@ -24,7 +24,8 @@ for r in rows[2:]:
     for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
         total += float(d[m].replace(",", "")) * scale[units[hdr.index(m)]]
     out["kernels"][key] = {"dram_bytes_per_launch": total, "duration_ms_under_ncu": float(d["gpu__time_duration.sum"].replace(",", "")) *
-                           {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units[hdr.index("gpu__time_duration.sum")]]}
+                           {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units[hdr.index("gpu__time_duration.sum")]],
+                           "warp_instructions_per_launch": float(d["smsp__inst_executed.sum"].replace(",", ""))}
 dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "trace_traffic.json")
 with open(dst, "w") as fh:
     json.dump(out, fh, indent=1)
