@@ -492,7 +492,9 @@ __device__ __forceinline__ bool front_regular(float a) {
 // The distortion pair of the NEXT iteration (also across the thread's point boundary) is always in flight, and the
 // next point's rows are prefetched into L2 one point ahead, so a point start costs one L2 hit instead of two serial
 // DRAM round trips.
-template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
+// REVEN: the number of rays per point is even (every scenario of the reference: 4, 10, 100, 170, 180, 200), so both
+// lanes of every pair are live and the loads of the software pipeline need no per-lane conditions.
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK, bool REVEN>
 __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h,
                                                       int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
                                                       int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
@@ -552,14 +554,14 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
         const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         ++n_reg_points;
         for (int r = 0; r < R; r += 2) {
-            const bool two = (r + 1 < R);   // an odd R leaves the second lane of the last pair idle
+            const bool two = REVEN || (r + 1 < R);   // an odd R leaves the second lane of the last pair idle
             const float2 d0 = da, d1 = db;
             {
                 const bool inner = r + 2 < R;
                 nx += inner ? step_inner : step_last;
                 if (inner || more) {
                     da = __ldcs(nx);
-                    if (inner ? (r + 3 < R) : (R > 1)) db = __ldcs(nx + P);
+                    if (REVEN || (inner ? (r + 3 < R) : (R > 1))) db = __ldcs(nx + P);
                 }
             }
             float2 cu, su, ce, se;
@@ -832,7 +834,10 @@ trace_fwd_kernel(const TraceParams prm) {
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF && (BLK || prm.simple_counts)) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
-        fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
+        if ((R & 1) == 0)
+            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
+        else
+            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #else
         fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #endif
@@ -1285,7 +1290,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
 // ray (which decides the pixels) repeats the forward's strict operation sequence exactly; the gradient math behind it
 // is ordinary packed FMA arithmetic.  A pair with one dead lane (invalid / off-bitmap ray) zeroes that lane's inputs,
 // so it contributes exact zeros; a pair with two dead lanes is skipped.
-template <int THREADS, int TRIG, bool BLK>
+template <int THREADS, int TRIG, bool BLK, bool REVEN>
 __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc,
                                                       const PointSrc& src, int h, int p_begin, int p_end, float i0, float i1,
                                                       float i2, float* __restrict__ grad_points,
@@ -1330,14 +1335,14 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
         if (point_regular(pc)) {
             const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
             for (int r = 0; r < R; r += 2) {
-                const bool two = (r + 1 < R);
+                const bool two = REVEN || (r + 1 < R);
                 const float2 d0 = da, d1 = db;
                 {
                     const bool inner = r + 2 < R;
                     nx += inner ? step_inner : step_last;
                     if (inner || more) {
                         da = __ldcs(nx);
-                        if (inner ? (r + 3 < R) : (R > 1)) db = __ldcs(nx + P);
+                        if (REVEN || (inner ? (r + 3 < R) : (R > 1))) db = __ldcs(nx + P);
                     }
                 }
                 float2 cu, su, ce, se;
@@ -1583,7 +1588,10 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
-        bwd_rays_planar_fast2<THREADS, TRIG, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
+        if ((prm.a.n_rays & 1) == 0)
+            bwd_rays_planar_fast2<THREADS, TRIG, BLK, true>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
+        else
+            bwd_rays_planar_fast2<THREADS, TRIG, BLK, false>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
 #else
         bwd_rays_planar_fast<THREADS, TRIG, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
 #endif
