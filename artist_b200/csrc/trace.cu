@@ -508,9 +508,9 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
     const Packed K(prm.ident);
     const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
-    const float fxs = prm.fx_scale;
+    const float fxs_sub = prm.fx_scale * 0x1p-100f;   // (exact) see the tap rounding below
+    const float kTwoM49 = 0x1p-49f;
     const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
-    const unsigned kMagicBits = 0x4B000000u;   // bits(2^23)
     const bool axis_n = (T.n0 == 0.0f) && (T.n2 == 0.0f);
     // Pixel indices relative to the window come straight out of the floor() trick: be + (1.5 * 2^23 - e0), rounded down,
     // has the bit pattern 0x4B400000 + (floor(be) - e0) (two's complement wrap-around for negative differences), so
@@ -648,23 +648,28 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             // splat weights (valid rays have 0 <= be <= E-1, 0 <= bu <= U-1).  floor() and the integer pixel index come
             // from one round-down add of 2^23 (FMA pipe) instead of FRND + F2I (XU pipe): for 0 <= x < 2^23 the sum's
             // low mantissa bits ARE floor(x).
-            const float kMagic = 8388608.0f;
             const float2 me = make_float2(__fadd_rd(be.x, magic_e), __fadd_rd(be.y, magic_e));
             const float2 mu = make_float2(__fadd_rd(bu.x, magic_u), __fadd_rd(bu.y, magic_u));
             // high weights = fractional parts (exact); low weights = 1 - high, the same real number as the reference's
             // (ie + 1) - be with its single rounding placed differently (<= 1 ulp of the weight, 1e-7 of a tap)
             const float2 whe = K.sub(be, K.sub(me, bc2(magic_e))), whu = K.sub(bu, K.sub(mu, bc2(magic_u)));
-            const float2 wle = K.sub(K.one, whe), wlu = K.sub(K.one, whu);
-            float2 v1, v2, v3, v4;   // tap values (fp32 accumulate) or 2^23 + round(scaled tap value) (fixed point)
+            const float2 wlu = K.sub(K.one, whu);
+            float2 v1, v2, v3, v4;   // tap values (fp32 accumulate) or the rounded scaled tap value as a SUBNORMAL float (fixed point)
             if (FP32ACC) {
+                const float2 wle = K.sub(K.one, whe);
                 v1 = K.mul(K.mul(wle, whu), inten); v2 = K.mul(K.mul(whe, whu), inten);
                 v3 = K.mul(K.mul(whe, wlu), inten); v4 = K.mul(K.mul(wle, wlu), inten);
             } else {
-                float2 sc = K.mul(inten, bc2(fxs));
+                // round(w_e * w_u * scaled intensity) to an integer WITHOUT a float->int step: the factors carry 2^-49 and
+                // 2^-100 (exact: powers of two, no underflow before a tap is far below one count), so the product of the
+                // last multiplication is tap * 2^-149 - a subnormal float, whose bit pattern IS the integer, rounded to
+                // nearest even by the multiplier itself (the same rounding as adding 2^23 to the unscaled product)
+                float2 sc = K.mul(inten, bc2(fxs_sub));
                 sc.x = fabsf(sc.x); sc.y = fabsf(sc.y);
                 const float2 ahi = K.mul(whu, sc), alo = K.mul(wlu, sc);
-                v1 = pfma(wle, ahi, bc2(kMagic)); v2 = pfma(whe, ahi, bc2(kMagic));
-                v3 = pfma(whe, alo, bc2(kMagic)); v4 = pfma(wle, alo, bc2(kMagic));
+                const float2 whes = K.mul(whe, bc2(kTwoM49)), wles = K.sub(bc2(kTwoM49), whes);
+                v1 = pfma(wles, ahi, bc2(0.0f)); v2 = pfma(whes, ahi, bc2(0.0f));
+                v3 = pfma(whes, alo, bc2(0.0f)); v4 = pfma(wles, alo, bc2(0.0f));
             }
 #pragma unroll
             for (int lane = 0; lane < 2; ++lane) {
@@ -685,8 +690,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
                         atomicAdd(row_hi, a1); atomicAdd(row_hi + 1, a2); atomicAdd(row_lo + 1, a3); atomicAdd(row_lo, a4);
                     }
                 } else {
-                    const unsigned q1 = __float_as_uint(a1) - kMagicBits, q2 = __float_as_uint(a2) - kMagicBits;
-                    const unsigned q3 = __float_as_uint(a3) - kMagicBits, q4 = __float_as_uint(a4) - kMagicBits;
+                    const unsigned q1 = __float_as_uint(a1), q2 = __float_as_uint(a2), q3 = __float_as_uint(a3), q4 = __float_as_uint(a4);
                     if (fast) {
                         // 32-bit shared-window addresses + red.shared: no generic->shared conversion per tap
                         const unsigned lo = win_base + (unsigned)(cux * fc.ww + cex) * 4u, hi = lo + row_bytes;
@@ -831,7 +835,8 @@ trace_fwd_kernel(const TraceParams prm) {
 
     int cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
     bool fell_back = false;
-    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF && (BLK || prm.simple_counts)) {
+    // (fx_scale >= 1e-6: the packed loop's subnormal tap rounding scales it by 2^-100 and needs the result to stay normal)
+    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF && (BLK || prm.simple_counts) && (FP32ACC || prm.fx_scale >= 1e-6f)) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
         if ((R & 1) == 0)
