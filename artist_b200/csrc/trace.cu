@@ -517,7 +517,8 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     // cex = bits - 0x4B400000 costs ONE integer instruction with an immediate operand.  The window's shared-memory
     // address is kept opaque so that it stays in a register instead of being re-derived for every tap.
     const int e0w = fc.ww > 0 ? fc.e0 : 0, u0w = fc.ww > 0 ? fc.u0 : 0;   // (an empty window has a huge origin)
-    const float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
+    float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
+    asm volatile("" : "+f"(magic_e), "+f"(magic_u));   // loop invariants: kept in registers, not re-derived per pair
     const unsigned kIdxBits = 0x4B400000u;
     const unsigned wwm1 = (unsigned)max(fc.ww, 1) - 1u, whm1 = (unsigned)max(fc.wh, 1) - 1u;   // empty window: nothing is "inside"
     unsigned win_base = (unsigned)__cvta_generic_to_shared(fc.win_u);
@@ -1316,7 +1317,8 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     const float2 zero2 = make_float2(0.f, 0.f);
     // window-relative pixel indices straight from the floor() trick (see fwd_rays_planar_fast2)
     const int e0w = bc.ww > 0 ? bc.e0 : 0, u0w = bc.ww > 0 ? bc.u0 : 0;
-    const float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
+    float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
+    asm volatile("" : "+f"(magic_e), "+f"(magic_u));   // loop invariants: kept in registers, not re-derived per pair
     const unsigned kIdxBits = 0x4B400000u;
     bool any_irr = false;
     const int n_pairs = (R + 1) >> 1;
