@@ -520,7 +520,8 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
     asm volatile("" : "+f"(magic_e), "+f"(magic_u));   // loop invariants: kept in registers, not re-derived per pair
     const unsigned kIdxBits = 0x4B400000u;
-    const unsigned wwm1 = (unsigned)max(fc.ww, 1) - 1u, whm1 = (unsigned)max(fc.wh, 1) - 1u;   // empty window: nothing is "inside"
+    unsigned wwm1 = (unsigned)max(fc.ww, 1) - 1u, whm1 = (unsigned)max(fc.wh, 1) - 1u;   // empty window: nothing is "inside"
+    asm volatile("" : "+r"(wwm1), "+r"(whm1));
     unsigned win_base = (unsigned)__cvta_generic_to_shared(fc.win_u);
     asm volatile("" : "+r"(win_base));
     const unsigned row_bytes = (unsigned)fc.ww * 4u;
