@@ -46,6 +46,7 @@ struct TraceParams {
     float sigma;        // scatter sigma used for the window margin
     int simple_counts;  // 1: magnitude, (1 - extinction), reflectivity >= 1e-6: lambert > 0 and intensity > 0 hold exactly for valid rays
     int self_zero;      // 1: every CTA clears the part of its bitmap row outside the window itself (no memset pass)
+    int wave;           // CTAs per wave (number of SMs) in the one-CTA-per-sample mode, else 0: L2 prefetch distance in samples
     int quad;           // 1: E % 4 == 0 and the bitmap rows are 16-byte aligned: the window is placed on 4-column quads, so
                         //    that clearing, staging and flushing move float4 / uint4
     PackedIdentities ident;  // 1, -0, -1 as run-time values (see common.cuh, packed arithmetic)
@@ -202,6 +203,20 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
     }
     __syncthreads();
     win_out = *win_sh;
+}
+
+// The sample the CTA one wave later will trace (one-CTA-per-sample mode): its rows for the window placement are pulled into
+// L2 by this CTA's threads during their last surface point (fwd_/bwd_rays_planar_fast2), its per-sample scalars here.
+__device__ inline void set_next_sample(const float4** next_sh, const TraceParams& prm, int li) {
+    next_sh[0] = nullptr; next_sh[1] = nullptr;
+    if (prm.wave > 0 && li + prm.wave < prm.a.n_local) {
+        const int hn = prm.a.local_rows ? prm.a.local_rows[li + prm.wave] : li + prm.wave;
+        next_sh[0] = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hn * prm.a.n_points;
+        next_sh[1] = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hn * prm.a.n_points;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.a.incident + 4 * hn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.a.target_idx + hn));
+        if (prm.a.orientations) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.a.orientations + (size_t)hn * 16));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -541,6 +556,9 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
         const int pn = p + THREADS;
         const bool more = pn < p_end;
         if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
+        else if (tid * kWindowSampleStride < P && src.next && src.next[0]) {
+            prefetch_l2(src.next[0] + tid * kWindowSampleStride); prefetch_l2(src.next[1] + tid * kWindowSampleStride);
+        }
         PointCtx pc;
         {
             float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
@@ -737,6 +755,7 @@ trace_fwd_kernel(const TraceParams prm) {
     __shared__ int fb_box[4];
     __shared__ BlockPrim blk_sh[kMaxBlockCandidates];
     __shared__ float O_sh[16];
+    __shared__ const float4* next_sh[2];
 
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
@@ -763,6 +782,7 @@ trace_fwd_kernel(const TraceParams prm) {
         fb_box[0] = 1 << 30; fb_box[1] = -1; fb_box[2] = 1 << 30; fb_box[3] = -1;
     }
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
+    if (tid == 64) set_next_sample(next_sh, prm, li);
     {
         uint4* w4 = reinterpret_cast<uint4*>(smem_raw);
         const int n4 = prm.win_cap >> 2;
@@ -775,6 +795,7 @@ trace_fwd_kernel(const TraceParams prm) {
     src.pts = pts_h;
     src.nrm = nrm_h;
     src.O = prm.a.orientations ? O_sh : nullptr;
+    src.next = next_sh;
     const TargetCtx T = T_sh;
 
     Window W;
@@ -1333,6 +1354,9 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
         const int pn = p + THREADS;
         const bool more = pn < p_end;
         if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
+        else if (tid * kWindowSampleStride < P && src.next && src.next[0]) {
+            prefetch_l2(src.next[0] + tid * kWindowSampleStride); prefetch_l2(src.next[1] + tid * kWindowSampleStride);
+        }
         PointCtx pc;
         {
             float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
@@ -1526,6 +1550,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     __shared__ float O_sh[16];
     __shared__ BlockPrim blk_sh[BLK ? kMaxBlockCandidates : 1];
     __shared__ int blk_rows_sh[BLK ? kMaxBlockCandidates : 1];
+    __shared__ const float4* next_sh[2];
 
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
@@ -1547,8 +1572,10 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
                 i2 = __ldg(prm.a.incident + 4 * h + 2);
     if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
+    if (tid == 64) set_next_sample(next_sh, prm, li);
     __syncthreads();
     AB200_PHASE(12, 0);
+    src.next = next_sh;
     const TargetCtx T = T_sh;
     float gori[12];
 #pragma unroll
@@ -1703,6 +1730,7 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
     prm.ident.one = 1.0f; prm.ident.negzero = -0.0f; prm.ident.negone = -1.0f;
     prm.self_zero = 0;
     prm.quad = 0;
+    prm.wave = pl.split == 1 ? sm_count() : 0;
     prm.simple_counts = (a->ray_magnitude >= 1e-6f && a->one_minus_extinction >= 1e-6f && a->reflectivity >= 1e-6f &&
                          a->ray_magnitude <= 1e6f && a->one_minus_extinction <= 1e6f && a->reflectivity <= 1e6f) ? 1 : 0;
 }

@@ -133,6 +133,10 @@ struct PointSrc {
     const float4* pts;
     const float4* nrm;
     const float* O;   // shared memory, row-major 4x4, or nullptr
+    // rows of the sample the CTA one wave later will start with (or nullptr): the threads that will read them for the
+    // window placement pull them into L2 during their last point, so that CTA's start-up waits for L2, not for DRAM
+    // (kept in shared memory: {points, normals} of that sample; no registers inside the ray loops)
+    const float4* const* next = nullptr;
 };
 
 __device__ __forceinline__ float4 apply_orientation(const float* O, const float4 d) {
