@@ -84,6 +84,9 @@ constexpr int kWindowSampleStride = AB200_WIN_SAMPLE_STRIDE;
 #ifndef AB200_WIN_KB
 #define AB200_WIN_KB 224   // shared-memory bitmap window per CTA in the one-CTA-per-sample mode
 #endif
+#ifndef AB200_BWD_TMA_STAGE
+#define AB200_BWD_TMA_STAGE 0   // 1: the backward stages its gradient window with TMA bulk copies (cp.async.bulk + mbarrier)
+#endif
 #ifndef AB200_PACKED_RAYS
 #define AB200_PACKED_RAYS 1     // fast loops process two rays per iteration with fp32x2 (FFMA2) arithmetic
 #endif
@@ -1551,6 +1554,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     __shared__ BlockPrim blk_sh[BLK ? kMaxBlockCandidates : 1];
     __shared__ int blk_rows_sh[BLK ? kMaxBlockCandidates : 1];
     __shared__ const float4* next_sh[2];
+    __shared__ __align__(8) unsigned long long stage_bar;   // mbarrier of the gradient-window staging (TMA bulk copies)
 
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
@@ -1573,6 +1577,11 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
     if (tid == 64) set_next_sample(next_sh, prm, li);
+    const unsigned stage_bar_s = (unsigned)__cvta_generic_to_shared(&stage_bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(stage_bar_s), "r"(THREADS) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     AB200_PHASE(12, 0);
     src.next = next_sh;
@@ -1588,7 +1597,29 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     const float* gf = grad_flux + (size_t)h * grad_stride;
     {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
         const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
-        if (prm.quad && W.ww > 0) {
+        if (AB200_BWD_TMA_STAGE && prm.quad && W.ww > 0) {
+            // TMA: one 1-D bulk copy (cp.async.bulk, global -> shared) per window row, completion counted in bytes on an
+            // mbarrier every thread arrives on - no registers, no LSU instructions per element, and the wait doubles as
+            // the CTA barrier in front of the ray loop
+            const unsigned row_bytes = (unsigned)W.ww * 4u;
+            const unsigned win_s = (unsigned)__cvta_generic_to_shared(win_g);
+            unsigned my_bytes = 0;
+            for (int r = tid; r < W.wh; r += THREADS) my_bytes += row_bytes;
+            unsigned long long state;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 %0, [%1], %2;" : "=l"(state) : "r"(stage_bar_s), "r"(my_bytes) : "memory");
+            (void)state;
+            for (int r = tid; r < W.wh; r += THREADS) {
+                const float* grow = gf + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(win_s + (unsigned)r * row_bytes), "l"(grow), "r"(row_bytes), "r"(stage_bar_s) : "memory");
+            }
+            asm volatile("{\n"
+                         ".reg .pred p;\n"
+                         "STAGE_WAIT_%=:\n"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+                         "@!p bra STAGE_WAIT_%=;\n"
+                         "}\n" ::"r"(stage_bar_s) : "memory");
+        } else if (prm.quad && W.ww > 0) {
             const int qw = W.ww >> 2, n4 = W.wh * qw;
             const int d_r = THREADS / qw, d_q = THREADS - d_r * qw;
             float4* w4 = reinterpret_cast<float4*>(win_g);
@@ -1604,7 +1635,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
             for (int c = lane; c < W.ww; c += 32) win_g[r * W.ww + c] = __ldg(grow + c);
         }
     }
-    __syncthreads();
+    if (!(AB200_BWD_TMA_STAGE && prm.quad && W.ww > 0)) __syncthreads();
     AB200_PHASE(12, 2);  // staging the gradient window
     BwdCtx bc;
     bc.win_g = win_g; bc.gf = gf; bc.e0 = W.e0; bc.u0 = W.u0; bc.ww = W.ww;
