@@ -85,7 +85,7 @@ constexpr int kWindowSampleStride = AB200_WIN_SAMPLE_STRIDE;
 #define AB200_WIN_KB 224   // shared-memory bitmap window per CTA in the one-CTA-per-sample mode
 #endif
 #ifndef AB200_BWD_TMA_STAGE
-#define AB200_BWD_TMA_STAGE 0   // 1: the backward stages its gradient window with TMA bulk copies (cp.async.bulk + mbarrier)
+#define AB200_BWD_TMA_STAGE 1   // 1: the backward stages its gradient window with TMA bulk copies (cp.async.bulk + mbarrier)
 #endif
 #ifndef AB200_PACKED_RAYS
 #define AB200_PACKED_RAYS 1     // fast loops process two rays per iteration with fp32x2 (FFMA2) arithmetic
