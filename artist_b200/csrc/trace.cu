@@ -87,6 +87,9 @@ constexpr int kWindowSampleStride = AB200_WIN_SAMPLE_STRIDE;
 #ifndef AB200_BWD_TMA_STAGE
 #define AB200_BWD_TMA_STAGE 1   // 1: the backward stages its gradient window with TMA bulk copies (cp.async.bulk + mbarrier)
 #endif
+#ifndef AB200_BWD_SPLIT_TAIL
+#define AB200_BWD_SPLIT_TAIL 0   // 1: the backward's last, partial round of points is split by ray pair (see bwd_rays_planar_fast2)
+#endif
 #ifndef AB200_PACKED_RAYS
 #define AB200_PACKED_RAYS 1     // fast loops process two rays per iteration with fp32x2 (FFMA2) arithmetic
 #endif
@@ -1349,37 +1352,10 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     const int n_pairs = (R + 1) >> 1;
     const long long step_inner = 2 * (long long)P, step_last = (long long)THREADS - (long long)(n_pairs - 1) * 2 * (long long)P;
 
-    int p = p_begin + tid;
-    float2 da = zero2, db = zero2;
-    const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
-    if (p < p_end) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
-    for (; p < p_end; p += THREADS) {
-        const int pn = p + THREADS;
-        const bool more = pn < p_end;
-        if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
-        else if (tid * kWindowSampleStride < P && src.next && src.next[0]) {
-            prefetch_l2(src.next[0] + tid * kWindowSampleStride); prefetch_l2(src.next[1] + tid * kWindowSampleStride);
-        }
-        PointCtx pc;
-        {
-            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
-            orient_point(src, o4, n4);
-            make_point(pc, T, i0, i1, i2, o4, n4);
-        }
-        float2 go0 = zero2, go1 = zero2, go2 = zero2, gr0 = zero2, gr1 = zero2, gr2 = zero2;   // one partial sum per lane
-        if (point_regular(pc)) {
-            const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
-            for (int r = 0; r < R; r += 2) {
-                const bool two = REVEN || (r + 1 < R);
-                const float2 d0 = da, d1 = db;
-                {
-                    const bool inner = r + 2 < R;
-                    nx += inner ? step_inner : step_last;
-                    if (inner || more) {
-                        da = __ldcs(nx);
-                        if (REVEN || (inner ? (r + 3 < R) : (R > 1))) db = __ldcs(nx + P);
-                    }
-                }
+    // one pair of rays of a surface point: strict recomputation, tap gather, gradient math; accumulates into go*, gr*
+    auto pair_body = [&](const float2 d0, const float2 d1, const bool two, const int r, const int p, const PointCtx& pc,
+                         const unsigned long long bmask, float2& go0, float2& go1, float2& go2, float2& gr0, float2& gr1,
+                         float2& gr2) {
                 float2 cu, su, ce, se;
                 bool ang0 = true, ang1 = true;
                 if (TRIG == AB200_TRIG_TABLE) {
@@ -1445,7 +1421,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                     const int ie0 = cex0 + e0w, iu0 = cux0 + u0w, ie1 = cex1 + e0w, iu1 = cux1 + u0w;
                     live0 = valid0 && ((unsigned)ie0 < (unsigned)(E - 1)) && ((unsigned)iu0 < (unsigned)(U - 1));
                     live1 = valid1 && ((unsigned)ie1 < (unsigned)(E - 1)) && ((unsigned)iu1 < (unsigned)(U - 1));
-                    if (!(live0 || live1)) continue;
+                    if (!(live0 || live1)) return;
 #pragma unroll
                     for (int lane = 0; lane < 2; ++lane) {
                         if (!(lane ? live1 : live0)) continue;
@@ -1514,19 +1490,15 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                 gr0 = lfma(cu, gdx, lfma(su, q, gr0));
                 gr1 = lfma(make_float2(-su.x, -su.y), gdx, lfma(cu, q, gr1));
                 gr2 = lfma(make_float2(-se.x, -se.y), gdy, lfma(ce, gdz, gr2));
-            }
-        } else {
-            any_irr = true;
-            nx += THREADS;
-            if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
-        }
+    };
+    // per-point epilogue: gradients w.r.t. the (un-aligned) point and normal rows from the sums over the point's rays
+    auto point_epilogue = [&](const int p, const float s_go0, const float s_go1, const float s_go2, const float s_gr0,
+                              const float s_gr1, const float s_gr2) {
         // the point's rows again (L1/L2 hit): cheaper than keeping 11 registers alive across the ray loop
         const float4 o_raw = __ldg(pts + p), n_raw = __ldg(nrm + p);
         float4 o4 = o_raw, n4 = n_raw;
         orient_point(src, o4, n4);
         const float dot_in = sadd(sadd(smul(i0, n4.x), smul(i1, n4.y)), smul(i2, n4.z));
-        const float s_go0 = go0.x + go0.y, s_go1 = go1.x + go1.y, s_go2 = go2.x + go2.y;
-        const float s_gr0 = gr0.x + gr0.y, s_gr1 = gr1.x + gr1.y, s_gr2 = gr2.x + gr2.y;
         // r = i - 2 (i.n) n   ->   grad n = -2 [ (i.n) grad r + (grad r . n) i ]
         const float grn = s_gr0 * n4.x + s_gr1 * n4.y + s_gr2 * n4.z;
         const float gn0 = -2.0f * (dot_in * s_gr0 + grn * i0);
@@ -1536,6 +1508,80 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
         orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
         reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = gp4;
         reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = gn4;
+    };
+    // The CTA's last, partial round (npts mod THREADS points - 16 of 10000 with 768 threads) would keep one warp busy for a
+    // whole point while all others wait at the barrier: those points are split by ray PAIR instead - `slots` (a power of
+    // two) lanes per point, one pair each, partial sums combined by a shuffle tree in a fixed order.
+    const int npts = p_end - p_begin, n_full = (npts / THREADS) * THREADS, n_tail = npts - n_full;
+    int slots = 1;
+    while (slots < n_pairs) slots <<= 1;
+    const bool split_tail = AB200_BWD_SPLIT_TAIL && REVEN && TRIG != AB200_TRIG_TABLE && n_full > 0 && n_tail > 0 && slots <= 32 && n_tail * slots <= THREADS;
+    const int p_end_main = split_tail ? p_begin + n_full : p_end;
+
+    int p = p_begin + tid;
+    float2 da = zero2, db = zero2;
+    const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
+    if (p < p_end_main) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+    for (; p < p_end_main; p += THREADS) {
+        const int pn = p + THREADS;
+        const bool more = pn < p_end_main;
+        if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
+        else if (tid * kWindowSampleStride < P && src.next && src.next[0]) {
+            prefetch_l2(src.next[0] + tid * kWindowSampleStride); prefetch_l2(src.next[1] + tid * kWindowSampleStride);
+        }
+        PointCtx pc;
+        {
+            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
+        }
+        float2 go0 = zero2, go1 = zero2, go2 = zero2, gr0 = zero2, gr1 = zero2, gr2 = zero2;   // one partial sum per lane
+        if (point_regular(pc)) {
+            const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
+            for (int r = 0; r < R; r += 2) {
+                const bool two = REVEN || (r + 1 < R);
+                const float2 d0 = da, d1 = db;
+                {
+                    const bool inner = r + 2 < R;
+                    nx += inner ? step_inner : step_last;
+                    if (inner || more) {
+                        da = __ldcs(nx);
+                        if (REVEN || (inner ? (r + 3 < R) : (R > 1))) db = __ldcs(nx + P);
+                    }
+                }
+                pair_body(d0, d1, two, r, p, pc, bmask, go0, go1, go2, gr0, gr1, gr2);
+            }
+        } else {
+            any_irr = true;
+            nx += THREADS;
+            if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+        }
+        point_epilogue(p, go0.x + go0.y, go1.x + go1.y, go2.x + go2.y, gr0.x + gr0.y, gr1.x + gr1.y, gr2.x + gr2.y);
+    }
+    if (split_tail && (tid & ~31) < n_tail * slots) {   // (whole warps, so that the shuffles below are convergent)
+        const int lp = tid / slots, k = tid - lp * slots;
+        const bool in_range = lp < n_tail, act = in_range && k < n_pairs;
+        const int pt = p_begin + n_full + (in_range ? lp : 0);
+        float2 go0 = zero2, go1 = zero2, go2 = zero2, gr0 = zero2, gr1 = zero2, gr2 = zero2;
+        if (act) {
+            PointCtx pc;
+            float4 o4 = __ldg(pts + pt), n4 = __ldg(nrm + pt);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
+            if (point_regular(pc)) {
+                const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
+                const float2 d0 = __ldcs(dist + (size_t)(2 * k) * P + pt), d1 = __ldcs(dist + (size_t)(2 * k + 1) * P + pt);
+                pair_body(d0, d1, true, 2 * k, pt, pc, bmask, go0, go1, go2, gr0, gr1, gr2);
+            } else {
+                any_irr = true;
+            }
+        }
+        float s[6] = {go0.x + go0.y, go1.x + go1.y, go2.x + go2.y, gr0.x + gr0.y, gr1.x + gr1.y, gr2.x + gr2.y};
+        for (int off = slots >> 1; off > 0; off >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], off);
+        }
+        if (in_range && k == 0) point_epilogue(pt, s[0], s[1], s[2], s[3], s[4], s[5]);
     }
     n_irregular_out = any_irr ? 1 : 0;
 }
