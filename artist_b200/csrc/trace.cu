@@ -88,7 +88,7 @@ constexpr int kWindowSampleStride = AB200_WIN_SAMPLE_STRIDE;
 #define AB200_BWD_TMA_STAGE 1   // 1: the backward stages its gradient window with TMA bulk copies (cp.async.bulk + mbarrier)
 #endif
 #ifndef AB200_BWD_SPLIT_TAIL
-#define AB200_BWD_SPLIT_TAIL 0   // 1: the backward's last, partial round of points is split by ray pair (see bwd_rays_planar_fast2)
+#define AB200_BWD_SPLIT_TAIL 1   // 1: the backward's last, partial round of points is split by ray pair (see bwd_rays_planar_fast2)
 #endif
 #ifndef AB200_PACKED_RAYS
 #define AB200_PACKED_RAYS 1     // fast loops process two rays per iteration with fp32x2 (FFMA2) arithmetic
