@@ -262,3 +262,53 @@ def test_per_target_backward_uniform_and_mixed_targets():
         f = flux.clone().requires_grad_(True)
         (ops.bitmaps_per_target(f, tidx, 3) * wgt).sum().backward()
         assert torch.equal(f.grad, wgt[tidx.long()])
+
+
+def test_one_cta_per_sample_mode_at_bench_scale_equals_split_mode():
+    """The bench configuration (10^4 points, 10 rays, 256 x 256 bitmaps, wide focal spots) with >= 2 x SM-count samples runs
+    the one-CTA-per-sample kernels: capped quad-aligned windows with out-of-window taps (integer REDs + conversion of the
+    outside quads), TMA-staged gradient windows, the pair-split tail of the backward.  A 40-sample slice of the same
+    field runs the split mode (several CTAs per sample, memset + finalize kernels).  The fixed-point flux must be
+    IDENTICAL bit for bit, the factors too, and the gradients equal up to fp32 summation order."""
+    import bench
+    from artist_b200 import ops
+
+    dev = torch.device("cuda:0")
+    n, m = 320, 40
+    wl = bench.Workload(dev, n, 1, 0)
+    g = wl.group
+    g.activate_heliostats(wl.mask)
+    with torch.no_grad():
+        pts, nrm = wl.surf.calculate_surface_points_and_normals(wl.ev, g.active_canting, g.active_facet_translations)
+    g.active_surface_points = pts.reshape(n, -1, 4)
+    g.active_surface_normals = nrm.reshape(n, -1, 4)
+    g.align_surfaces_with_incident_ray_directions(wl.aim, wl.inc, wl.mask)
+    points, normals, orientations = g._fused_alignment()
+    tr = wl.tracer
+    opt = ops.TraceOptions(res_e=bench.RES[0], res_u=bench.RES[1], ray_magnitude=float(tr.ray_magnitude),
+                           mirror_reflectivity=0.935, scatter_sigma=getattr(tr.light_source, "scatter_sigma", 0.0))
+    torch.manual_seed(11)
+    wgt = torch.rand(m, bench.RES[1], bench.RES[0], device=dev)
+
+    def run(k):
+        p = points[:k].detach().clone().requires_grad_(True)
+        q = normals[:k].detach().clone().requires_grad_(True)
+        o = orientations[:k].detach().clone().requires_grad_(True)
+        out = ops.trace(p, q, wl.inc[:k].contiguous(), tr._packed[:k].contiguous(), wl.tidx[:k].contiguous(), tr._targets, opt,
+                        orientations=o)
+        (out[0][:m] * wgt).sum().backward()
+        return out, (p.grad[:m], q.grad[:m], o.grad[:m])
+
+    ops.trace_stats = torch.zeros(20, dtype=torch.int64, device=dev)
+    big, gbig = run(n)
+    stats = ops.trace_stats.tolist()
+    ops.trace_stats = None
+    assert stats[2] == n and stats[0] > 0, "the large-mode kernels with out-of-window taps were meant to run"
+    small, gsmall = run(m)
+    for a, b in zip(big, small):
+        assert torch.equal(a[:m], b)
+    assert big[0].sum() > 0 and torch.isfinite(big[0]).all()
+    for ga, gb, name in zip(gbig, gsmall, ("points", "normals", "orientations")):
+        scale = gb.abs().max()
+        assert scale > 0, name
+        assert (ga - gb).abs().max() <= 2e-5 * scale, f"{name}: {(ga - gb).abs().max() / scale:.2e}"
