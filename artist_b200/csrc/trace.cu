@@ -90,6 +90,9 @@ constexpr int kWindowSampleStride = AB200_WIN_SAMPLE_STRIDE;
 #ifndef AB200_BWD_SPLIT_TAIL
 #define AB200_BWD_SPLIT_TAIL 1   // 1: the backward's last, partial round of points is split by ray pair (see bwd_rays_planar_fast2)
 #endif
+#ifndef AB200_FLUSH_ST
+#define AB200_FLUSH_ST 0   // store flavour of the window flush: 0 st.cs (streaming), 1 plain, 2 st.cg, 3 st.wt (tuning)
+#endif
 #ifndef AB200_PACKED_RAYS
 #define AB200_PACKED_RAYS 1     // fast loops process two rays per iteration with fp32x2 (FFMA2) arithmetic
 #endif
@@ -943,8 +946,17 @@ trace_fwd_kernel(const TraceParams prm) {
             for (int idx = tid; idx < n4; idx += THREADS) {
                 const uint4 v = w4[idx];
                 float4* orow = reinterpret_cast<float4*>(out_f + (size_t)(U - 1 - (W.u0 + r)) * E + W.e0);
-                __stcs(orow + q, make_float4(__uint2float_rn(v.x) * inv, __uint2float_rn(v.y) * inv, __uint2float_rn(v.z) * inv,
-                                             __uint2float_rn(v.w) * inv));
+                const float4 o4v = make_float4(__uint2float_rn(v.x) * inv, __uint2float_rn(v.y) * inv, __uint2float_rn(v.z) * inv,
+                                               __uint2float_rn(v.w) * inv);
+#if AB200_FLUSH_ST == 1
+                orow[q] = o4v;
+#elif AB200_FLUSH_ST == 2
+                __stcg(orow + q, o4v);
+#elif AB200_FLUSH_ST == 3
+                __stwt(orow + q, o4v);
+#else
+                __stcs(orow + q, o4v);
+#endif
                 r += d_r; q += d_q;
                 if (q >= qw) { q -= qw; ++r; }
             }
@@ -1820,6 +1832,8 @@ static cudaError_t launch_fwd(const TraceParams& prm, const LaunchPlan& pl, cuda
         auto kern = trace_fwd_kernel<THREADS, TRIG, DBG, ACC, BLK>;                                          \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes); \
         if (e != cudaSuccess) return e;                                                                      \
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+        if (e != cudaSuccess) return e;                                                                      \
         kern<<<grid, THREADS, pl.smem_bytes, st>>>(prm);                                                     \
         note_launch();                                                                                       \
     } while (0)
@@ -1848,10 +1862,14 @@ static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cuda
         auto kern = trace_bwd_kernel<THREADS, TRIG, true>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori);
     } else {
         auto kern = trace_bwd_kernel<THREADS, TRIG, false>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori);
     }
