@@ -157,7 +157,8 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
     return a
 
 
-trace_stats: torch.Tensor | None = None  # set to a zeroed int64[4] CUDA tensor to collect window diagnostics
+trace_stats: torch.Tensor | None = None  # set to a zeroed int64[20] CUDA tensor to collect diagnostics: [0..2] window use
+# (threads on the global fallback, window cells, CTAs), [4..10] forward / [12..16] backward phase cycles (tools/phase_stats.py)
 
 
 last_blocking_overflow: torch.Tensor | None = None  # int32[1]: samples whose candidate list overflowed (should stay 0)

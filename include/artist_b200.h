@@ -114,8 +114,10 @@ typedef struct ab200_trace_args {
     float* dbg_bu;           /* [N,R,P] */
     float* dbg_t;            /* [N,R,P] */
     float* dbg_lambert;      /* [N,R,P] */
-    int64_t* stats;          /* optional diagnostics (NULL to skip), accumulated: [0] threads that used the global fallback
-                                path, [1] sum of window cells, [2] CTAs */
+    int64_t* stats;          /* optional diagnostics (NULL to skip), int64[20], accumulated: [0] threads that used the global
+                                fallback path, [1] sum of window cells, [2] CTAs, [4..10] cycles of the forward CTA phases
+                                (start-up, placement, clearing, ray loop, wait, flush, tap conversion), [12..16] of the
+                                backward's (start-up, placement, staging, ray loop, reduction) - thread 0, summed over CTAs */
     const float* orientations; /* optional [N,4,4] (NULL = `points`/`normals` are already aligned): fuses
                                 HeliostatGroupRigidBody.align_surfaces_with_* (heliostat_group_rigid_body.py:217-222,
                                 265-270) into the trace - `points`/`normals` are then the UN-aligned active surface

@@ -7,7 +7,7 @@ from artist_b200 import ops
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 dev = torch.device("cuda:0")
 wl = bench.Workload(dev, n, 1, 0)
-ops.trace_stats = torch.zeros(4, dtype=torch.int64, device=dev)
+ops.trace_stats = torch.zeros(20, dtype=torch.int64, device=dev)
 with torch.no_grad():
     flux, ic, ot, _ = wl.tracer.trace_rays(wl.inc, wl.mask, wl.tidx)
 torch.cuda.synchronize()
