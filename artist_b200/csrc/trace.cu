@@ -124,7 +124,7 @@ __device__ __forceinline__ void load_window_samples(WindowSamples& ws, const flo
 template <int THREADS>
 __device__ void place_window(Window& win_out, const TraceParams& prm, const TargetCtx& T, const PointSrc& src,
                              const WindowSamples& ws, int p_begin, int p_end, float i0, float i1, float i2,
-                             float* red /* [6*32] */, Window* win_sh) {
+                             float* red /* [6*32] */, Window* win_sh, const int4* recorded = nullptr) {
     const int tid = threadIdx.x;
     const float4* pts = src.pts;
     const float4* nrm = src.nrm;
@@ -206,6 +206,16 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
                 }
                 if (ww < 2 || wh < 2) { w.e0 = 1 << 28; w.u0 = 1 << 28; w.ww = 0; w.wh = 0; }
                 else { w.e0 = e_lo; w.u0 = u_lo; w.ww = ww; w.wh = wh; }
+            }
+            if (recorded) {   // the window the forward of the same call placed (trusted only as far as it is harmless); the
+                              // rest of the placement is kept as it is: any early exit here costs the ray loop its
+                              // register allocation (spills inside the loop, measured +25 %)
+                const int4 r = __ldg(recorded);
+                const int E = prm.a.res_e, U = prm.a.res_u;
+                if (r.z >= 2 && r.w >= 2 && r.x >= 0 && r.y >= 0 && r.x + r.z <= E && r.y + r.w <= U &&
+                    (long long)r.z * r.w <= prm.win_cap && (!prm.quad || ((r.x | r.z) & 3) == 0)) {
+                    w.e0 = r.x; w.u0 = r.y; w.ww = r.z; w.wh = r.w;
+                }
             }
             *win_sh = w;
         }
@@ -809,6 +819,8 @@ trace_fwd_kernel(const TraceParams prm) {
 
     Window W;
     place_window<THREADS>(W, prm, T, src, ws, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    if (prm.a.windows && prm.split == 1 && tid == 0)   // for the backward of the same call
+        reinterpret_cast<int4*>(prm.a.windows)[h] = make_int4(W.e0, W.u0, W.ww, W.wh);
     AB200_PHASE(4, 1);   // window placement
     float* out_f = prm.a.flux + (size_t)h * U * E;
     unsigned* out_u = reinterpret_cast<unsigned*>(out_f);
@@ -1628,8 +1640,11 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
     src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
     src.O = prm.a.orientations ? O_sh : nullptr;
+    // the forward of the same call recorded its window (ab200_trace_args::windows): no sampling, no placement
+    const bool have_window = prm.a.windows != nullptr && prm.split == 1;
+    const int p_end_samples = have_window ? p_begin : p_end;   // (no surface samples are read then)
     WindowSamples ws;
-    load_window_samples<THREADS>(ws, src.pts, src.nrm, p_begin, p_end);
+    load_window_samples<THREADS>(ws, src.pts, src.nrm, p_begin, p_end_samples);
     const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
                 i2 = __ldg(prm.a.incident + 4 * h + 2);
     if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
@@ -1650,12 +1665,14 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     float* gori_acc = (grad_orientations && src.O) ? gori : nullptr;
 
     Window W;
-    place_window<THREADS>(W, prm, T, src, ws, p_begin, p_end, i0, i1, i2, red, &win_sh);
+    place_window<THREADS>(W, prm, T, src, ws, p_begin, p_end_samples, i0, i1, i2, red, &win_sh,
+                          have_window ? reinterpret_cast<const int4*>(prm.a.windows) + h : nullptr);
+    const bool quad_w = prm.quad;
     AB200_PHASE(12, 1);
     const float* gf = grad_flux + (size_t)h * grad_stride;
     {   // stage the gradient window: win_g[(iu-u0)*ww + (ie-e0)] = grad_flux[h, U-1-iu, ie]
         const int warp = tid >> 5, lane = tid & 31, nwarps = THREADS / 32;
-        if (AB200_BWD_TMA_STAGE && prm.quad && W.ww > 0) {
+        if (AB200_BWD_TMA_STAGE && quad_w && W.ww > 0) {
             // TMA: one 1-D bulk copy (cp.async.bulk, global -> shared) per window row, completion counted in bytes on an
             // mbarrier every thread arrives on - no registers, no LSU instructions per element, and the wait doubles as
             // the CTA barrier in front of the ray loop
@@ -1677,7 +1694,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
                          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
                          "@!p bra STAGE_WAIT_%=;\n"
                          "}\n" ::"r"(stage_bar_s) : "memory");
-        } else if (prm.quad && W.ww > 0) {
+        } else if (quad_w && W.ww > 0) {
             const int qw = W.ww >> 2, n4 = W.wh * qw;
             const int d_r = THREADS / qw, d_q = THREADS - d_r * qw;
             float4* w4 = reinterpret_cast<float4*>(win_g);
@@ -1693,7 +1710,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
             for (int c = lane; c < W.ww; c += 32) win_g[r * W.ww + c] = __ldg(grow + c);
         }
     }
-    if (!(AB200_BWD_TMA_STAGE && prm.quad && W.ww > 0)) __syncthreads();
+    if (!(AB200_BWD_TMA_STAGE && quad_w && W.ww > 0)) __syncthreads();
     AB200_PHASE(12, 2);  // staging the gradient window
     BwdCtx bc;
     bc.win_g = win_g; bc.gf = gf; bc.e0 = W.e0; bc.u0 = W.u0; bc.ww = W.ww;

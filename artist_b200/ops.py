@@ -124,7 +124,8 @@ def pack_distortions(distortions_u: torch.Tensor, distortions_e: torch.Tensor) -
 
 
 def _trace_args(points, normals, incident, distortions, trig, target_idx, targets: TargetTensors, opt: TraceOptions,
-                local_rows, flux, intercept, on_target, blocking, dbg=None, blk=None, orientations=None) -> _lib.TraceArgs:
+                local_rows, flux, intercept, on_target, blocking, dbg=None, blk=None, orientations=None,
+                windows=None) -> _lib.TraceArgs:
     n, p, _ = points.shape
     r = distortions.shape[1]
     a = _lib.TraceArgs()
@@ -154,6 +155,7 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
         a.dbg_be, a.dbg_bu, a.dbg_t, a.dbg_lambert = (_p(d) for d in dbg)
     a.stats = _p(trace_stats)
     a.orientations = _p(orientations)
+    a.windows = _p(windows)
     return a
 
 
@@ -206,11 +208,14 @@ class _TraceFn(torch.autograd.Function):
         blk = None
         if bi is not None:
             blk = (bi, *_prepare_blocking(bi, opt, n, dev))
+        # the backward re-uses the bitmap windows the forward placed (one per sample)
+        windows = torch.empty(n, 4, dtype=torch.int32, device=dev) if any(ctx.needs_input_grad) else None
         args = _trace_args(points, normals, incident, distortions, trig, target_idx, targets, opt, local_rows,
-                           flux, intercept, on_target, blocking, blk=blk, orientations=orientations)
+                           flux, intercept, on_target, blocking, blk=blk, orientations=orientations, windows=windows)
         _lib.call("ab200_trace_fwd", C.byref(args), _stream())
         ctx.save_for_backward(points, normals, incident, distortions, trig, target_idx, local_rows, orientations,
                               *(blk[1:] if blk is not None else ()))
+        ctx.windows = windows
         ctx.targets, ctx.opt, ctx.bi = targets, opt, bi
         ctx.blocker_shapes = None if bi is None else (b_corners.shape, b_spans.shape, b_normals.shape)
         ctx.mark_non_differentiable(intercept, on_target, blocking)
@@ -233,7 +238,7 @@ class _TraceFn(torch.autograd.Function):
         g_normals = torch.empty_like(normals)
         b = _lib.TraceBwdArgs()
         b.fwd = _trace_args(points, normals, incident, distortions, trig, target_idx, ctx.targets, ctx.opt, local_rows,
-                            None, None, None, None, blk=blk, orientations=orientations)
+                            None, None, None, None, blk=blk, orientations=orientations, windows=ctx.windows)
         b.grad_flux, b.grad_points, b.grad_normals = _p(g_flux), _p(g_points), _p(g_normals)
         b.grad_flux_stride = g_stride
         g_corners = g_spans = g_bnormals = None

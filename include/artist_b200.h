@@ -30,7 +30,7 @@ extern "C" {
 #define AB200_ECUDA (-2)    /* a CUDA runtime call or launch failed */
 #define AB200_ELIMIT (-3)   /* size beyond what the kernels support */
 
-#define AB200_ABI_VERSION 2
+#define AB200_ABI_VERSION 3
 
 /* trig source for the per-ray scatter rotation (artist/geometry/transforms.py:52-55) */
 #define AB200_TRIG_SINCOSF 0 /* libdevice sincosf (default) */
@@ -123,6 +123,10 @@ typedef struct ab200_trace_args {
                                 265-270) into the trace - `points`/`normals` are then the UN-aligned active surface
                                 rows and every CTA applies `row @ O^T` itself (same FMA chain as ab200_align_fwd), so
                                 the aligned [N,P,4] tensors are never written to or re-read from HBM */
+    int32_t* windows;        /* optional scratch [N,4] (NULL to skip): ab200_trace_fwd records the shared-memory bitmap window
+                                (e0, u0, width, height) it placed for every sample of the one-CTA-per-sample mode,
+                                ab200_trace_bwd of the same call re-uses it instead of sampling the surface and placing
+                                the window again.  Correctness never depends on it (it only selects the fast path). */
 } ab200_trace_args;
 
 int32_t ab200_trace_fwd(const ab200_trace_args* args, void* stream);
