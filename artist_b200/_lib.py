@@ -124,6 +124,8 @@ EXPORTS = {
     "ab200_blocking_pack": ([c_float_p, c_float_p, c_float_p, C.c_int32, C.c_float, c_float_p, C.c_void_p], C.c_int32),
     "ab200_blocking_candidates": ([c_float_p, C.c_int32, c_int_p, c_float_p, c_float_p, C.c_int32, C.c_float, C.c_int32,
                                    c_int_p, c_int_p, c_int_p, C.c_void_p], C.c_int32),
+    "ab200_sample_distortions": ([c_float_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                  C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_void_p], C.c_int32),
     "ab200_abi_version": ([], C.c_int32),
     "ab200_kernel_launch_count": ([], C.c_int64),
     "ab200_error_string": ([C.c_int32], C.c_char_p),

@@ -779,7 +779,7 @@ trace_fwd_kernel(const TraceParams prm) {
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
     const int chunk = blockIdx.x - li * prm.split;
-    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
+    const int h = prm.a.local_rows ? min(max(prm.a.local_rows[li], 0), prm.a.n_samples - 1) : li;   // (clamped: memory safety)
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
     const int p_begin = chunk * prm.pts_per_chunk;
     const int p_end = min(P, p_begin + prm.pts_per_chunk);
@@ -1629,7 +1629,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     const int tid = threadIdx.x;
     const int li = blockIdx.x / prm.split;
     const int chunk = blockIdx.x - li * prm.split;
-    const int h = prm.a.local_rows ? prm.a.local_rows[li] : li;
+    const int h = prm.a.local_rows ? min(max(prm.a.local_rows[li], 0), prm.a.n_samples - 1) : li;
     const int P = prm.a.n_points, E = prm.a.res_e, U = prm.a.res_u;
     const int p_begin = chunk * prm.pts_per_chunk;
     const int p_end = min(P, p_begin + prm.pts_per_chunk);

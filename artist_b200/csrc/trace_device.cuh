@@ -44,6 +44,9 @@ __device__ __forceinline__ bool const_div_ok(float b) {
 __device__ inline void load_target(TargetCtx& T, const ab200_targets& tg, int tidx, int res_e, int res_u) {
     T.em1 = (float)(res_e - 1);
     T.um1 = (float)(res_u - 1);
+    // memory safety never depends on the caller's index values: out-of-range indices are clamped here (the host layer
+    // raises IndexError for them, possibly one call later - ops._check_index_range)
+    tidx = min(max(tidx, 0), tg.n_planar + tg.n_cyl - 1);
     if (tidx < tg.n_planar) {
         T.planar = 1;
         const float* n = tg.planar_normals + 4 * tidx;

@@ -163,7 +163,31 @@ trace_stats: torch.Tensor | None = None  # set to a zeroed int64[20] CUDA tensor
 # (threads on the global fallback, window cells, CTAs), [4..10] forward / [12..16] backward phase cycles (tools/phase_stats.py)
 
 
-last_blocking_overflow: torch.Tensor | None = None  # int32[1]: samples whose candidate list overflowed (should stay 0)
+last_blocking_overflow: torch.Tensor | None = None  # int32[1]: samples whose candidate list overflowed (must stay 0)
+_overflow_pending: list = []   # (pinned host int32[1], event, max_candidates) of earlier calls, checked without a sync
+
+
+def check_blocking_overflow(wait: bool = False) -> None:
+    """Raise if a blocking candidate list overflowed ``max_candidates`` (``kMaxBlockCandidates`` = 64 is the hard limit
+    of the per-point 64-bit candidate mask): the dropped rectangles would silently be missing from the flux, the
+    blocking factors and the gradients, where the reference evaluates every filtered primitive
+    (``artist/raytracing/blocking.py:212-354``).  The flag travels to pinned host memory behind the candidate kernel, so
+    the check costs no synchronisation: ``trace`` looks at the flags of EARLIER calls that have already arrived
+    (``wait=False``); ``HeliostatRayTracer.trace_rays`` callers that need the answer for the current call use ``wait=True``."""
+    still = []
+    for host, ev, cap in _overflow_pending:
+        if wait:
+            ev.synchronize()
+        if ev.query():
+            if int(host[0]) != 0:
+                _overflow_pending.clear()
+                raise _lib.Ab200Error(
+                    f"blocking: {int(host[0])} heliostat-sample(s) have more than {cap} candidate blockers between them and "
+                    f"their target; the candidate list is limited to {cap} (kMaxBlockCandidates = 64) and the flux would "
+                    "silently miss the dropped rectangles")
+        else:
+            still.append((host, ev, cap))
+    _overflow_pending[:] = still
 
 
 def _prepare_blocking(bi: BlockingInputs, opt: TraceOptions, n: int, dev):
@@ -185,6 +209,12 @@ def _prepare_blocking(bi: BlockingInputs, opt: TraceOptions, n: int, dev):
     _lib.call("ab200_blocking_candidates", _p(prims), h, _p(owner), _p(aim), _p(radius), n, spread, int(bi.max_candidates),
               _p(cand_idx), _p(cand_count), _p(overflow), _stream())
     last_blocking_overflow = overflow
+    check_blocking_overflow()                      # flags of earlier calls that have arrived by now
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(overflow, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _overflow_pending.append((host, ev, int(bi.max_candidates)))
     return prims, cand_idx, cand_count
 
 
@@ -194,6 +224,7 @@ class _TraceFn(torch.autograd.Function):
                 b_spans, b_normals, orientations):
         points, normals, incident = _f32(points, "points"), _f32(normals, "normals"), _f32(incident, "incident")
         distortions = _f32(distortions, "distortions")
+        target_idx_object = target_idx
         target_idx = _i32(target_idx, "target_area_indices")
         if orientations is not None:
             orientations = _f32(orientations, "orientations")
@@ -201,6 +232,7 @@ class _TraceFn(torch.autograd.Function):
                 raise _lib.Ab200Error("orientations must be [N,4,4] with one matrix per row of points")
         n = points.shape[0]
         dev = points.device
+        _validate_trace_inputs(points, normals, incident, distortions, trig, target_idx_object, local_rows, targets)
         flux = torch.empty(n, opt.res_u, opt.res_e, device=dev)
         intercept = torch.empty(n, device=dev)
         on_target = torch.empty(n, device=dev)
@@ -263,6 +295,28 @@ class _TraceFn(torch.autograd.Function):
                 g_ori)
 
 
+def _validate_trace_inputs(points, normals, incident, distortions, trig, target_idx, local_rows, targets) -> None:
+    """The kernels index raw pointers: every shape they assume is checked here (the reference would raise a shape or
+    index error from its eager ops).  Index VALUES are range-checked once per tensor version (cached device read)."""
+    if points.dim() != 3 or points.shape[-1] != 4:
+        raise _lib.Ab200Error(f"surface points must be [N,P,4], got {tuple(points.shape)}")
+    n, p, _ = points.shape
+    if normals.shape != points.shape:
+        raise _lib.Ab200Error(f"surface normals {tuple(normals.shape)} do not match the points {tuple(points.shape)}")
+    if distortions.dim() != 4 or distortions.shape[0] != n or distortions.shape[2] != p or distortions.shape[3] != 2:
+        raise _lib.Ab200Error(f"distortions must be [N={n},R,P={p},2], got {tuple(distortions.shape)} - was the ray tracer "
+                              "built before the heliostats were re-activated?")
+    if incident.dim() != 2 or incident.shape[0] != n or incident.shape[1] != 4:
+        raise _lib.Ab200Error(f"incident ray directions must be [N={n},4], got {tuple(incident.shape)}")
+    if target_idx.numel() != n:
+        raise _lib.Ab200Error(f"target_area_indices must have N={n} entries, got {target_idx.numel()}")
+    if trig is not None and tuple(trig.shape) != (n, distortions.shape[1], p, 4):
+        raise _lib.Ab200Error(f"trig table must be [N,R,P,4], got {tuple(trig.shape)}")
+    _check_index_range(target_idx, targets.n_planar + targets.n_cyl, "target_area_indices")
+    if local_rows is not None:
+        _check_index_range(local_rows, n, "local_rows")
+
+
 def trace(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,
           local_rows: torch.Tensor | None = None, trig: torch.Tensor | None = None,
           blocking: BlockingInputs | None = None, orientations: torch.Tensor | None = None):
@@ -289,6 +343,7 @@ def trace_debug(points, normals, incident, distortions, target_idx, targets: Tar
     points, normals, incident = _f32(points, "points"), _f32(normals, "normals"), _f32(incident, "incident")
     distortions = _f32(distortions, "distortions")
     target_idx = _i32(target_idx, "target_area_indices")
+    _validate_trace_inputs(points, normals, incident, distortions, trig, target_idx, None, targets)
     n, p, _ = points.shape
     r = distortions.shape[1]
     dev = points.device
@@ -333,29 +388,93 @@ class _PerTargetFn(torch.autograd.Function):
 _uniform_cache: dict = {}
 
 
-def _uniform_target(target_idx: torch.Tensor) -> int | None:
-    """The single target index all samples share, or None.  Costs one device->host read per distinct index tensor
-    OBJECT and version (id + weak reference, so a recycled address or an in-place update is never mistaken for a hit)."""
+_UNKNOWN = object()
+
+
+def _index_bounds(idx: torch.Tensor, wait: bool = True):
+    """``(min, max)`` of an index tensor, or None if it is empty.  Costs one device->host read per distinct tensor OBJECT
+    and version (id + weak reference, so a recycled address or an in-place update is never mistaken for a hit); the
+    side-stream check started by ``prefetch_uniform_target`` is collected here if it is on its way.  ``wait=False``
+    returns ``_UNKNOWN`` instead of synchronising."""
     import weakref
 
-    hit = _uniform_cache.get(id(target_idx))
-    if hit is not None and hit[0]() is target_idx and hit[1] == target_idx._version:
+    hit = _uniform_cache.get(id(idx))
+    if hit is not None and hit[0]() is idx and hit[1] == idx._version:
         return hit[2]
-    pend = _uniform_pending.pop(id(target_idx), None)
-    if target_idx.numel() == 0:
+    pend = _uniform_pending.get(id(idx))
+    if pend is not None and not (pend[0]() is idx and pend[1] == idx._version):
+        _uniform_pending.pop(id(idx), None)
+        pend = None
+    if idx.numel() == 0:
         result = None
-    elif pend is not None and pend[0]() is target_idx and pend[1] == target_idx._version:
-        pend[3].synchronize()   # the side-stream check started by prefetch_uniform_target: long finished by now
+    elif pend is not None:
+        if not wait and not pend[3].query():
+            return _UNKNOWN
+        _uniform_pending.pop(id(idx), None)
+        pend[3].synchronize()   # long finished by the time anybody asks
         lo_hi = pend[2].tolist()
-        result = int(lo_hi[0]) if lo_hi[0] == lo_hi[1] else None
+        result = (int(lo_hi[0]), int(lo_hi[1]))
     else:
-        lo, hi = torch.aminmax(target_idx)
+        if not wait:
+            return _UNKNOWN
+        lo, hi = torch.aminmax(idx)
         lo_hi = torch.stack([lo, hi]).tolist()
-        result = int(lo_hi[0]) if lo_hi[0] == lo_hi[1] else None
+        result = (int(lo_hi[0]), int(lo_hi[1]))
     if len(_uniform_cache) > 64:
         _uniform_cache.clear()
-    _uniform_cache[id(target_idx)] = (weakref.ref(target_idx), target_idx._version, result)
+    _uniform_cache[id(idx)] = (weakref.ref(idx), idx._version, result)
     return result
+
+
+def _uniform_target(target_idx: torch.Tensor) -> int | None:
+    """The single target index all samples share, or None."""
+    b = _index_bounds(target_idx)
+    return b[0] if b is not None and b[0] == b[1] else None
+
+
+_seen_index_tensors: dict = {}   # id -> weakref: index tensor OBJECTS that were range-checked synchronously once
+_deferred_range_checks: list = []
+
+
+def _raise_if_out_of_range(b, upper: int, what: str) -> None:
+    if b is not None and (b[0] < 0 or b[1] >= upper):
+        raise IndexError(f"{what}: values span [{b[0]}, {b[1]}] but must lie in [0, {upper})")
+
+
+def _check_index_range(idx: torch.Tensor, upper: int, what: str) -> None:
+    """Raise ``IndexError`` (as the reference's eager indexing would) if any entry is outside ``[0, upper)``.
+
+    A tensor OBJECT seen for the first time is checked at once (one device->host read, set-up time).  When a known tensor
+    was only updated in place (the steady state of an optimisation loop that uploads new indices every step) the check
+    runs on a side stream and is collected by a LATER call, so no step ever waits for a device->host read; the kernels
+    clamp the indices, so a late error never means an out-of-bounds access happened in between."""
+    import weakref
+
+    # collect deferred checks whose result has arrived
+    still = []
+    for ref, version, up, w in _deferred_range_checks:
+        t = ref()
+        if t is None or t._version != version:
+            continue
+        b = _index_bounds(t, wait=False)
+        if b is _UNKNOWN:
+            still.append((ref, version, up, w))
+        else:
+            _deferred_range_checks[:] = still
+            _raise_if_out_of_range(b, up, w)
+    _deferred_range_checks[:] = still
+    known = _seen_index_tensors.get(id(idx))
+    first_time = known is None or known() is not idx
+    b = _index_bounds(idx, wait=first_time)
+    if b is _UNKNOWN:
+        prefetch_uniform_target(idx)
+        _deferred_range_checks.append((weakref.ref(idx), idx._version, upper, what))
+    else:
+        _raise_if_out_of_range(b, upper, what)
+    if first_time:
+        if len(_seen_index_tensors) > 256:
+            _seen_index_tensors.clear()
+        _seen_index_tensors[id(idx)] = weakref.ref(idx)
 
 
 _uniform_pending: dict = {}

@@ -351,6 +351,18 @@ int32_t ab200_blocking_candidates(const float* prims, int32_t n_prims, const int
                                   int32_t n_samples, float spread_angle, int32_t max_candidates, int32_t* cand_idx,
                                   int32_t* cand_count, int32_t* overflow, void* stream);
 
+/*
+ * Sun-shape distortion sampling (artist/scene/sun.py:199-234, Sun.get_distortions): out [n_pairs, 2] = (u, e) pairs in
+ * the layout of `MultivariateNormal(mean, cov*I).sample((N, R, P))` (n_pairs = N*R*P), bit-identical to what torch's CUDA
+ * generator produces for (seed, philox_offset): out[2i+c] = mean_c + fl(sigma_c * z[2i+c]), z = the `normal_()` Philox
+ * stream (ATen/native/cuda/DistributionTemplates.h:64-89, curand_normal4).  sm_count / max_threads_per_sm decide torch's
+ * counter layout; pass 0 to use the current device's.  philox_offset_after (host, may be NULL) receives the generator
+ * offset torch would be left with.
+ */
+int32_t ab200_sample_distortions(float* out, int64_t n_pairs, uint64_t seed, uint64_t philox_offset, float sigma_u,
+                                 float sigma_e, float mean_u, float mean_e, int32_t sm_count_override,
+                                 int32_t max_threads_per_sm_override, uint64_t* philox_offset_after, void* stream);
+
 /* misc */
 int32_t ab200_abi_version(void);
 int64_t ab200_kernel_launch_count(void); /* kernels launched by this library so far (diagnostic) */

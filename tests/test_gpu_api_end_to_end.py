@@ -111,6 +111,79 @@ def test_motor_position_gradients_and_mask_assertion():
     assert torch.equal(fb, flux) and (bl == 1).all()
 
 
+@pytest.mark.parametrize("n", [6, 300])
+def test_motor_position_and_deviation_gradients_vs_oracle_autograd(n):
+    """Config 5 shape (``artist/optim/aim_point_optimizer.py:384-402``): motor positions -> ``align_surfaces_with_motor_
+    positions`` (kinematics kernel) -> fused trace -> loss; gradients w.r.t. the motor positions and the kinematic
+    rotation deviations against the oracle's autograd through the same chain.  n = 300 runs the one-CTA-per-sample trace
+    kernels (dL/dO reduced in-kernel), n = 6 the split-mode ones (dL/dO by atomics)."""
+    from artist_b200 import HeliostatRayTracer, build_synthetic_scenario, synthetic_field_tensors
+
+    ppf, rays, res = (12, 12), 6, (128, 128)
+    ft = synthetic_field_tensors(n, control_points=(6, 6), surface_bump=0.002)
+    g = torch.Generator().manual_seed(5)
+    ft["rotation_deviations"] = 0.01 * torch.randn(n, 4, generator=g)
+    scenario, group = build_synthetic_scenario(n, number_of_rays=rays, points_per_facet=ppf, device=DEV, field_tensors=ft)
+    mask, tidx, inc = scenario.index_mapping(group, single_incident_ray_direction=torch.tensor([0.0, 0.96, -0.28, 0.0]),
+                                             single_target_area_index=0)
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_incident_ray_directions(scenario.solar_tower.get_centers_of_target_areas(tidx), inc, mask)
+    motor0 = group.kinematics.active_motor_positions.detach().clone()
+    # de-tune the motors a little so that the spots sit off-centre (non-trivial gradients)
+    g2 = torch.Generator().manual_seed(9)
+    motor0 = motor0 + (40.0 * torch.randn(n, 2, generator=g2)).to(DEV)
+    motor = motor0.clone().requires_grad_(True)
+    rot = group.kinematics.rotation_deviation_parameters.detach().clone().requires_grad_(True)
+    group.kinematics.rotation_deviation_parameters = rot
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_motor_positions(motor, mask)
+    tracer = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor(res))
+    flux, *_ = tracer.trace_rays(inc, mask, tidx)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, res[1]), torch.linspace(-1, 1, res[0]), indexing="ij")
+    wgt = 1.0 + 0.6 * xx - 0.4 * yy + 0.3 * xx * yy
+    total = tracer.get_bitmaps_per_target(flux, tidx)[0]
+    (total * wgt.to(DEV)).sum().backward()
+    assert motor.grad is not None and rot.grad is not None
+    # ---- oracle: identical chain on the CPU with autograd, same distortion samples; float32 (= the reference's arithmetic)
+    # and float64 (conditioning-free gold).  The chain motor position -> law of cosines -> nine 4x4 products -> 60 m lever arm
+    # loses ~3 digits in fp32 (a last-bit change of an actuator angle moves the spot by ~1e-3 pixel), so two CORRECT fp32
+    # implementations differ from each other by about as much as each differs from the exact result: the kernel is required
+    # to be no further from the float64 result than twice the reference arithmetic's own distance (+ the fp32 trace floor).
+    def oracle(dtype):
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(dtype)
+        try:
+            cv = lambda x: x.to(dtype) if torch.is_tensor(x) and x.is_floating_point() else x
+            f = {k: cv(v) for k, v in ft.items()}
+            tg = cases.targets_from(f)
+            ev = cv(O.nurbs_evaluation_grid(*ppf))[None, None].expand(n, 4, -1, -1)
+            pts, nrm = O.nurbs_points_and_normals(f["nurbs_control_points"], 3, 3, ev, f["canting"], f["facet_translations"])
+            mo = cv(motor0.cpu()).clone().requires_grad_(True)
+            ro = f["rotation_deviations"].clone().requires_grad_(True)
+            kin = O.Kin(f["positions"], f["translation_deviations"], ro, f["actuator_non_optimizable"],
+                        f["actuator_optimizable"], True)
+            ori = O.motor_positions_to_orientations(kin, mo)
+            ap, an = O.align_surfaces(pts.reshape(n, -1, 4), nrm.reshape(n, -1, 4), ori)
+            ref, *_ = O.trace_rays(ap, an, cv(inc.cpu()), cv(tracer.distortions_dataset.distortions_u.cpu()),
+                                   cv(tracer.distortions_dataset.distortions_e.cpu()), tidx.cpu(), tg, res)
+            tot = ref.sum(0)
+            (tot * cv(wgt)).sum().backward()
+            return tot.detach().double(), mo.grad.double(), ro.grad.double()
+        finally:
+            torch.set_default_dtype(old)
+
+    t32, gm32, gr32 = oracle(torch.float32)
+    t64, gm64, gr64 = oracle(torch.float64)
+    rel = lambda x, gold: float((x.double().cpu() - gold).abs().max() / gold.abs().max())
+    own = (rel(total.detach(), t64), rel(motor.grad, gm64), rel(rot.grad, gr64))
+    ref32 = (rel(t32, t64), rel(gm32, gm64), rel(gr32, gr64))
+    floors = (1e-5, 2e-4, 2e-4)
+    for name, o, r32, fl in zip(("flux", "motor-position gradient", "rotation-deviation gradient"), own, ref32, floors):
+        assert o <= 2.0 * r32 + fl, f"{name}: error vs float64 {o:.2e}, the fp32 reference arithmetic's own {r32:.2e}"
+    # and, in absolute terms, close to the fp32 oracle as well
+    assert rel(total.detach(), t32.double()) <= 3e-3 and rel(motor.grad, gm32) <= 5e-3 and rel(rot.grad, gr32) <= 5e-3
+
+
 def test_lazy_alignment_fused_and_materialised_paths_agree():
     """``align_surfaces_with_*`` only records the orientation; the tracer fuses the rotation into its kernels.
     Reading ``active_surface_points`` materialises the aligned tensors: same flux bit for bit, and the aligned
