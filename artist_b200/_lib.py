@@ -12,7 +12,7 @@ from ._build import LIB_OVERRIDE, LIB_PATH as _DEFAULT_LIB_PATH
 
 LIB_PATH = LIB_OVERRIDE or _DEFAULT_LIB_PATH
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TRIG_SINCOSF, TRIG_TABLE, TRIG_POLY = 0, 1, 2
 FLAG_FP32_ACCUM = 1
 
@@ -47,7 +47,7 @@ class TraceArgs(C.Structure):
         ("scatter_sigma", C.c_float), ("trig_mode", C.c_int32), ("flags", C.c_int32),
         ("flux", c_float_p), ("intercept", c_float_p), ("on_target", c_float_p), ("blocking", c_float_p),
         ("dbg_be", c_float_p), ("dbg_bu", c_float_p), ("dbg_t", c_float_p), ("dbg_lambert", c_float_p),
-        ("stats", C.c_void_p), ("orientations", c_float_p), ("windows", c_int_p),
+        ("stats", C.c_void_p), ("orientations", c_float_p), ("windows", c_int_p), ("distortions_planar", c_float_p),
     ]
 
 
@@ -125,7 +125,8 @@ EXPORTS = {
     "ab200_blocking_candidates": ([c_float_p, C.c_int32, c_int_p, c_float_p, c_float_p, C.c_int32, C.c_float, C.c_int32,
                                    c_int_p, c_int_p, c_int_p, C.c_void_p], C.c_int32),
     "ab200_sample_distortions": ([c_float_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float,
-                                  C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.c_void_p], C.c_int32),
+                                  C.c_int32, C.c_int32, C.POINTER(C.c_uint64), c_float_p, C.c_void_p], C.c_int32),
+    "ab200_deinterleave_distortions": ([c_float_p, C.c_int64, c_float_p, C.c_void_p], C.c_int32),
     "ab200_abi_version": ([], C.c_int32),
     "ab200_kernel_launch_count": ([], C.c_int64),
     "ab200_error_string": ([C.c_int32], C.c_char_p),

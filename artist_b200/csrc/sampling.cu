@@ -49,7 +49,7 @@ __device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
 __global__ void __launch_bounds__(256)
 sample_distortions_kernel(float* __restrict__ out, long long numel, long long T, unsigned long long seed,
                           unsigned long long offset4 /* philox offset / 4 */, float sigma_u, float sigma_e, float mean_u,
-                          float mean_e, long long n_work) {
+                          float mean_e, long long n_work, float* __restrict__ planar, long long planar_first, long long plane_stride) {
     // T is a multiple of the block size: one (uniform, 32-bit) division per block
     const unsigned blocks_per_iter = (unsigned)(T >> 8);
     const unsigned kb = blockIdx.x / blocks_per_iter;
@@ -67,7 +67,12 @@ sample_distortions_kernel(float* __restrict__ out, long long numel, long long T,
         if (li < numel) {
             const bool e = (li & 1) != 0;
             // torch: normal_ stores fl(z * 1 + 0) = z; then loc + fl(sigma * z)
-            __stcs(out + li, __fadd_rn(e ? mean_e : mean_u, __fmul_rn(e ? sigma_e : sigma_u, z[ii])));
+            const float v = __fadd_rn(e ? mean_e : mean_u, __fmul_rn(e ? sigma_e : sigma_u, z[ii]));
+            __stcs(out + li, v);
+            if (planar) {   // global element index g = planar_first + li: pair g / 2 of plane g & 1
+                const long long g = planar_first + li;
+                __stcs(planar + (g & 1) * plane_stride + (g >> 1), v);
+            }
         }
     }
 }
@@ -90,13 +95,15 @@ static void torch_policy(long long numel, int sms, int max_threads_per_sm, long 
 // byte offset fit int32, else its first half (numel / 2), then the rest, recursively - each launch drawing its own
 // Philox offset from the generator in that order.
 static int32_t sample_range(float* out, long long numel, unsigned long long seed, unsigned long long* offset, int sms,
-                            int max_threads_per_sm, const float* sg, const float* mn, long long global_start, cudaStream_t st) {
+                            int max_threads_per_sm, const float* sg, const float* mn, long long global_start, cudaStream_t st,
+                            float* planar, long long plane_stride) {
     if (numel <= 0) return AB200_OK;
     if (numel > 536870912ll) {
         const long long first = numel / 2;
-        int32_t rc = sample_range(out, first, seed, offset, sms, max_threads_per_sm, sg, mn, global_start, st);
+        int32_t rc = sample_range(out, first, seed, offset, sms, max_threads_per_sm, sg, mn, global_start, st, planar, plane_stride);
         if (rc != AB200_OK) return rc;
-        return sample_range(out + first, numel - first, seed, offset, sms, max_threads_per_sm, sg, mn, global_start + first, st);
+        return sample_range(out + first, numel - first, seed, offset, sms, max_threads_per_sm, sg, mn, global_start + first, st,
+                            planar, plane_stride);
     }
     long long T;
     unsigned long long inc;
@@ -107,7 +114,8 @@ static int32_t sample_range(float* out, long long numel, unsigned long long seed
     // a sub-range that starts on an odd element swaps the (u, e) roles of even/odd local indices
     const bool odd = (global_start & 1) != 0;
     sample_distortions_kernel<<<(unsigned)blocks, 256, 0, st>>>(out, numel, T, seed, *offset / 4, odd ? sg[1] : sg[0],
-                                                                odd ? sg[0] : sg[1], odd ? mn[1] : mn[0], odd ? mn[0] : mn[1], n_work);
+                                                                odd ? sg[0] : sg[1], odd ? mn[1] : mn[0], odd ? mn[0] : mn[1], n_work,
+                                                                planar, global_start, plane_stride);
     note_launch();
     AB200_CUDA_TRY(cudaGetLastError());
     *offset += inc;
@@ -116,7 +124,8 @@ static int32_t sample_range(float* out, long long numel, unsigned long long seed
 
 extern "C" int32_t ab200_sample_distortions(float* out, int64_t n_pairs, uint64_t seed, uint64_t philox_offset, float sigma_u,
                                             float sigma_e, float mean_u, float mean_e, int32_t sm_count_override,
-                                            int32_t max_threads_per_sm_override, uint64_t* philox_offset_after, void* stream) {
+                                            int32_t max_threads_per_sm_override, uint64_t* philox_offset_after, float* out_planar,
+                                            void* stream) {
     AB200_REQUIRE(out != nullptr && n_pairs >= 0, AB200_EINVAL, "bad arguments");
     AB200_REQUIRE(philox_offset % 4 == 0, AB200_EINVAL, "philox_offset must be a multiple of 4 (torch's generator always is)");
     int dev = 0, sms = 148, mtps = 2048;
@@ -137,7 +146,31 @@ extern "C" int32_t ab200_sample_distortions(float* out, int64_t n_pairs, uint64_
         torch_policy(numel_all, sms, mtps, &T, &inc);
         off += inc;
     }
-    const int32_t rc = sample_range(out, (long long)n_pairs * 2, seed, &off, sms, mtps, sg, mn, 0, static_cast<cudaStream_t>(stream));
+    const int32_t rc = sample_range(out, (long long)n_pairs * 2, seed, &off, sms, mtps, sg, mn, 0, static_cast<cudaStream_t>(stream),
+                                    out_planar, (long long)n_pairs);
     if (philox_offset_after) *philox_offset_after = off;
     return rc;
+}
+
+namespace ab200 {
+__global__ void __launch_bounds__(256) deinterleave_kernel(const float2* __restrict__ in, long long n_pairs, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_pairs) return;
+    const float2 v = __ldcs(in + i);
+    out[i] = v.x;
+    out[n_pairs + i] = v.y;
+}
+}  // namespace ab200
+
+extern "C" int32_t ab200_deinterleave_distortions(const float* interleaved, int64_t n_pairs, float* out_planar, void* stream) {
+    AB200_REQUIRE(interleaved && out_planar && n_pairs >= 0, AB200_EINVAL, "bad arguments");
+    AB200_REQUIRE(reinterpret_cast<uintptr_t>(interleaved) % 8 == 0, AB200_EINVAL, "interleaved distortions must be 8-byte aligned");
+    if (n_pairs == 0) return AB200_OK;
+    const long long blocks = (n_pairs + 255) / 256;
+    AB200_REQUIRE(blocks < (1ll << 31), AB200_ELIMIT, "too many pairs");
+    deinterleave_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float2*>(interleaved),
+                                                                                       n_pairs, out_planar);
+    note_launch();
+    AB200_CUDA_TRY(cudaGetLastError());
+    return AB200_OK;
 }

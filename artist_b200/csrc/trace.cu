@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
+#include <cstdlib>
 #include "trace_device.cuh"
 #include "blocking_device.cuh"
 
@@ -1765,6 +1766,8 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     }
 }
 
+#include "trace_v3.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1904,6 +1907,31 @@ static cudaError_t launch_bwd_trig(const TraceParams& prm, const LaunchPlan& pl,
     }
 }
 
+// The v3 kernels (trace_v3.cuh) cover the benchmark-shaped case; everything else runs the general kernels above.
+static bool v3_enabled() {
+    static const bool on = [] { const char* v = getenv("AB200_TRACE_V3"); return !(v && v[0] == '0'); }();
+    return on;
+}
+static bool v3_eligible(const ab200_trace_args* a, const TraceParams& prm, const LaunchPlan& pl, bool dbg, bool fp32acc) {
+    return v3_enabled() && pl.split == 1 && !dbg && !fp32acc && a->blockers.n_blockers == 0 && a->trig_mode == AB200_TRIG_POLY &&
+           a->n_rays >= 4 && (a->n_rays & 1) == 0 && (a->n_points & 1) == 0 && a->res_e % 4 == 0 && a->res_e <= v3::kMaxE &&
+           a->distortions_planar != nullptr && reinterpret_cast<uintptr_t>(a->distortions_planar) % 8 == 0 &&
+           reinterpret_cast<uintptr_t>(a->points) % 16 == 0 &&
+           reinterpret_cast<uintptr_t>(a->normals) % 16 == 0 && prm.simple_counts && prm.fx_scale >= 1e-6f &&
+           pl.smem_bytes / 4 / v3::kPitch >= 2;
+}
+
+static cudaError_t launch_fwd_v3(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st) {
+    auto kern = trace_fwd_v3_kernel<v3::kFwdThreads>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    kern<<<prm.a.n_local, v3::kFwdThreads, pl.smem_bytes, st>>>(prm);
+    note_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace ab200
 
 using namespace ab200;
@@ -1931,8 +1959,13 @@ extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
     fill_params(prm, a, pl);
     prm.self_zero = self_zero ? 1 : 0;
     prm.quad = (pl.split == 1 && !fp32acc && a->res_e % 4 == 0 && reinterpret_cast<uintptr_t>(a->flux) % 16 == 0) ? 1 : 0;
-    cudaError_t e = (pl.threads == kFwdThreadsLarge) ? launch_fwd_trig<kFwdThreadsLarge>(prm, pl, st, dbg, fp32acc)
-                                                     : launch_fwd_trig<512>(prm, pl, st, dbg, fp32acc);
+    cudaError_t e;
+    if (v3_eligible(a, prm, pl, dbg, fp32acc) && prm.quad) {
+        e = launch_fwd_v3(prm, pl, st);
+    } else {
+        e = (pl.threads == kFwdThreadsLarge) ? launch_fwd_trig<kFwdThreadsLarge>(prm, pl, st, dbg, fp32acc)
+                                             : launch_fwd_trig<512>(prm, pl, st, dbg, fp32acc);
+    }
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_fwd launch failed: %s", cudaGetErrorString(e));
     if (pl.split > 1) {
         if (!fp32acc) {

@@ -6,6 +6,7 @@ Nothing here computes on the CPU; every function raises if its tensors are not C
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -123,6 +124,40 @@ def pack_distortions(distortions_u: torch.Tensor, distortions_e: torch.Tensor) -
     return torch.stack([distortions_u.float(), distortions_e.float()], dim=-1).contiguous()
 
 
+_planar_registry: dict = {}   # data_ptr of an interleaved [N,R,P,2] buffer -> (weakref to it, version, planar [2,N,R,P])
+
+
+def register_planar_distortions(interleaved: torch.Tensor, planar: torch.Tensor) -> None:
+    import weakref
+
+    for k in [k for k, v in _planar_registry.items() if v[0]() is None]:
+        _planar_registry.pop(k)
+    _planar_registry[interleaved.data_ptr()] = (weakref.ref(interleaved), interleaved._version, planar)
+
+
+def planar_distortions(distortions: torch.Tensor) -> torch.Tensor | None:
+    """The de-interleaved ``[2,N,R,P]`` copy of an interleaved ``[N,R,P,2]`` distortion buffer (what the v3 trace kernels
+    stream): the one ``Sun.get_distortions`` wrote next to the sample, or - for any other buffer - one made here, once per
+    tensor and version (``ab200_deinterleave_distortions``)."""
+    import weakref
+
+    if distortions.numel() == 0 or distortions.data_ptr() % 8 != 0:
+        return None
+    hit = _planar_registry.get(distortions.data_ptr())
+    if hit is not None:
+        base = hit[0]()
+        if base is not None and hit[1] == base._version and hit[2].numel() == distortions.numel() and (
+                base is distortions or (base._version == distortions._version and base.shape == distortions.shape)):
+            return hit[2]
+    n, r, p, _ = distortions.shape
+    planar = torch.empty(2, n, r, p, device=distortions.device)
+    _lib.call("ab200_deinterleave_distortions", _p(distortions), n * r * p, _p(planar), _stream())
+    for k in [k for k, v in _planar_registry.items() if v[0]() is None]:
+        _planar_registry.pop(k)
+    _planar_registry[distortions.data_ptr()] = (weakref.ref(distortions), distortions._version, planar)
+    return planar
+
+
 def _trace_args(points, normals, incident, distortions, trig, target_idx, targets: TargetTensors, opt: TraceOptions,
                 local_rows, flux, intercept, on_target, blocking, dbg=None, blk=None, orientations=None,
                 windows=None) -> _lib.TraceArgs:
@@ -156,9 +191,15 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
     a.stats = _p(trace_stats)
     a.orientations = _p(orientations)
     a.windows = _p(windows)
+    a.distortions_planar = _p(planar_distortions(distortions)) if (use_planar and dbg is None and trig is None) else None
     return a
 
 
+# Opt-in (AB200_TRACE_V3=1): hand a de-interleaved distortion copy to the library so that the experimental point-pair
+# forward kernel of csrc/trace_v3.cuh runs where it is eligible.  Bit-identical results (tests/test_gpu_trace_parity.py),
+# 97 instead of 117 thread-instructions per ray, but at 16 warps per SM it issues less often: 1.09 ms against the general
+# kernel's 1.03 ms at the bench size (profiles/r02_trace_v3_experiment.txt) - so it is off by default.
+use_planar = os.environ.get("AB200_TRACE_V3", "0") == "1"
 trace_stats: torch.Tensor | None = None  # set to a zeroed int64[20] CUDA tensor to collect diagnostics: [0..2] window use
 # (threads on the global fallback, window cells, CTAs), [4..10] forward / [12..16] backward phase cycles (tools/phase_stats.py)
 

@@ -80,14 +80,14 @@ def _dist_constants(distribution) -> tuple[float, float, float, float] | None:
     return result
 
 
-def _launch_sampler(out: torch.Tensor, n_pairs: int, seed: int, offset: int, consts) -> int:
+def _launch_sampler(out: torch.Tensor, n_pairs: int, seed: int, offset: int, consts, planar: torch.Tensor | None = None) -> int:
     import ctypes as C
 
     from .. import _lib, ops
 
     after = C.c_uint64(0)
     _lib.call("ab200_sample_distortions", out.data_ptr(), n_pairs, seed & 0xFFFFFFFFFFFFFFFF, offset, consts[0], consts[1],
-              consts[2], consts[3], 0, 0, C.byref(after), ops._stream())
+              consts[2], consts[3], 0, 0, C.byref(after), None if planar is None else planar.data_ptr(), ops._stream())
     return int(after.value)
 
 
@@ -126,10 +126,19 @@ def _cuda_sample(distribution, shape, seed: int, device) -> torch.Tensor:
     hit = _sample_cache.get(key)
     if hit is None:
         sample = torch.empty(*shape, 2, device=device)
+        # the same samples de-interleaved ([2,N,R,P]), written by the same kernel: the layout the v3 trace kernels stream
+        # (ab200_trace_args::distortions_planar); registered with ops so that the tracer finds it behind the sample
+        # (only when those opt-in kernels are enabled, ops.use_planar: it doubles the sample's footprint)
+        from .. import ops
+
+        planar = torch.empty(2, *shape, device=device) if ops.use_planar else None
         n_pairs = sample.numel() // 2
-        offset_after = _launch_sampler(sample, n_pairs, seed, 0, consts) if n_pairs else 0
-        nbytes = sample.numel() * 4
-        while _sample_cache and sum(t.numel() * 4 for t, _ in _sample_cache.values()) + nbytes > _sample_cache_bytes_limit:
+        offset_after = _launch_sampler(sample, n_pairs, seed, 0, consts, planar) if n_pairs else 0
+        if planar is not None:
+            ops.register_planar_distortions(sample, planar)
+        per = 8 if planar is not None else 4
+        nbytes = sample.numel() * per
+        while _sample_cache and sum(t.numel() * per for t, _ in _sample_cache.values()) + nbytes > _sample_cache_bytes_limit:
             _sample_cache.pop(next(iter(_sample_cache)))
         if nbytes <= _sample_cache_bytes_limit:
             _sample_cache[key] = (sample, offset_after)

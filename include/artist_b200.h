@@ -30,7 +30,7 @@ extern "C" {
 #define AB200_ECUDA (-2)    /* a CUDA runtime call or launch failed */
 #define AB200_ELIMIT (-3)   /* size beyond what the kernels support */
 
-#define AB200_ABI_VERSION 3
+#define AB200_ABI_VERSION 4
 
 /* trig source for the per-ray scatter rotation (artist/geometry/transforms.py:52-55) */
 #define AB200_TRIG_SINCOSF 0 /* libdevice sincosf (default) */
@@ -127,6 +127,11 @@ typedef struct ab200_trace_args {
                                 (e0, u0, width, height) it placed for every sample of the one-CTA-per-sample mode,
                                 ab200_trace_bwd of the same call re-uses it instead of sampling the surface and placing
                                 the window again.  Correctness never depends on it (it only selects the fast path). */
+    const float* distortions_planar; /* optional [2,N,R,P] (NULL to skip): the SAME samples as `distortions`, de-interleaved
+                                (plane 0 = u, plane 1 = e).  The benchmark-shaped kernels (trace_v3.cuh) trace two adjacent
+                                surface points per thread in packed fp32x2 registers and read each plane with one 8-byte
+                                load that IS the register pair (the interleaved layout costs two register moves per ray);
+                                ab200_sample_distortions writes both layouts in one pass.  Without it the general kernels run. */
 } ab200_trace_args;
 
 int32_t ab200_trace_fwd(const ab200_trace_args* args, void* stream);
@@ -361,7 +366,11 @@ int32_t ab200_blocking_candidates(const float* prims, int32_t n_prims, const int
  */
 int32_t ab200_sample_distortions(float* out, int64_t n_pairs, uint64_t seed, uint64_t philox_offset, float sigma_u,
                                  float sigma_e, float mean_u, float mean_e, int32_t sm_count_override,
-                                 int32_t max_threads_per_sm_override, uint64_t* philox_offset_after, void* stream);
+                                 int32_t max_threads_per_sm_override, uint64_t* philox_offset_after, float* out_planar,
+                                 void* stream);
+/* out_planar (optional, [2, n_pairs]): the same samples de-interleaved, see ab200_trace_args::distortions_planar */
+/* de-interleave an existing [n_pairs,2] buffer into [2,n_pairs] */
+int32_t ab200_deinterleave_distortions(const float* interleaved, int64_t n_pairs, float* out_planar, void* stream);
 
 /* misc */
 int32_t ab200_abi_version(void);

@@ -136,11 +136,34 @@ def reflect(incident: torch.Tensor, normals: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 
 
+# cos / sin of the scatter angles.  The reference calls torch.cos / torch.sin (transforms.py:52-55); torch's CPU kernels
+# (SLEEF, <= 1 ulp) return a value that is NOT the correctly rounded one for ~8.6 % of sun-shape angles.  Tests swap in
+# ``correctly_rounded_trig`` to attribute differences between the reference and a faithful device implementation to
+# exactly that (tests/test_gpu_large_mode_parity.py, bench.py's parity leg).
+_scatter_cos, _scatter_sin = torch.cos, torch.sin
+
+
+class correctly_rounded_trig:
+    """Context manager: the scatter matrices use float64 cos / sin rounded once to float32."""
+
+    def __enter__(self):
+        global _scatter_cos, _scatter_sin
+        self._saved = (_scatter_cos, _scatter_sin)
+        _scatter_cos = lambda x: torch.cos(x.double()).to(x.dtype)
+        _scatter_sin = lambda x: torch.sin(x.double()).to(x.dtype)
+        return self
+
+    def __exit__(self, *exc):
+        global _scatter_cos, _scatter_sin
+        _scatter_cos, _scatter_sin = self._saved
+        return False
+
+
 def rotate_distortions(e: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
     """Per-ray 4x4 rotation (first around up by ``u``, then around east by ``e``)."""
     if e.shape != u.shape:
         raise ValueError("e and u must have the same shape")
-    ce, se, cu, su = torch.cos(e), torch.sin(e), torch.cos(u), torch.sin(u)
+    ce, se, cu, su = _scatter_cos(e), _scatter_sin(e), _scatter_cos(u), _scatter_sin(u)
     m = torch.zeros(*e.shape, 4, 4, device=e.device)
     m[..., 0, 0] = cu
     m[..., 0, 1] = -su

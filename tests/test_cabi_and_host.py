@@ -26,7 +26,7 @@ def test_header_symbols_are_exported():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert set(_lib.EXPORTS) == set(declared), "ctypes binding and header disagree"
-    assert _lib.lib().ab200_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib().ab200_abi_version() == _lib.ABI_VERSION == 4
     assert _lib.lib().ab200_error_string(-1) == b"invalid argument"
 
 

@@ -307,6 +307,15 @@ def test_one_cta_per_sample_mode_at_bench_scale_equals_split_mode():
     small, gsmall = run(m)
     for a, b in zip(big, small):
         assert torch.equal(a[:m], b)
+    # the opt-in point-pair forward kernel (csrc/trace_v3.cuh, AB200_TRACE_V3=1): bit-identical outputs
+    saved = ops.use_planar
+    ops.use_planar = True
+    try:
+        v3, _ = run(n)
+    finally:
+        ops.use_planar = saved
+    for a, b in zip(big, v3):
+        assert torch.equal(a, b)
     assert big[0].sum() > 0 and torch.isfinite(big[0]).all()
     for ga, gb, name in zip(gbig, gsmall, ("points", "normals", "orientations")):
         scale = gb.abs().max()
