@@ -48,6 +48,7 @@ class TraceArgs(C.Structure):
         ("flux", c_float_p), ("intercept", c_float_p), ("on_target", c_float_p), ("blocking", c_float_p),
         ("dbg_be", c_float_p), ("dbg_bu", c_float_p), ("dbg_t", c_float_p), ("dbg_lambert", c_float_p),
         ("stats", C.c_void_p), ("orientations", c_float_p), ("windows", c_int_p), ("distortions_planar", c_float_p),
+        ("src_rows", c_int_p),
     ]
 
 
@@ -127,6 +128,7 @@ EXPORTS = {
     "ab200_sample_distortions": ([c_float_p, C.c_int64, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_float,
                                   C.c_int32, C.c_int32, C.POINTER(C.c_uint64), c_float_p, C.c_void_p], C.c_int32),
     "ab200_deinterleave_distortions": ([c_float_p, C.c_int64, c_float_p, C.c_void_p], C.c_int32),
+    "ab200_replica_sum": ([c_float_p, c_int_p, C.c_int32, C.c_int64, c_float_p, C.c_void_p], C.c_int32),
     "ab200_abi_version": ([], C.c_int32),
     "ab200_kernel_launch_count": ([], C.c_int64),
     "ab200_error_string": ([C.c_int32], C.c_char_p),

@@ -164,3 +164,49 @@ extern "C" int32_t ab200_bilinear_splatting(const float* be, const float* bu, co
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// activation index map (HeliostatGroup.activate_heliostats, artist/field/heliostat_group.py:256-315): the reference
+// replicates every per-heliostat tensor with repeat_interleave(mask); here the trace kernels read surface row
+// src_rows[sample] in place (ab200_trace_args::src_rows) and the autograd backward of that gather - the sum of the replicas'
+// gradient rows - is this kernel.  Replicas of one heliostat are contiguous (repeat_interleave), so the sum runs over a
+// row range in a fixed order: deterministic, no atomics.
+// ---------------------------------------------------------------------------------------------
+namespace ab200 {
+template <typename V>
+__global__ void __launch_bounds__(256) replica_sum_kernel(const V* __restrict__ in, const int* __restrict__ row_start, long long row_vecs,
+                                                          V* __restrict__ out) {
+    const int s = blockIdx.y;
+    const int k0 = __ldg(row_start + s), k1 = __ldg(row_start + s + 1);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < row_vecs; i += (long long)gridDim.x * blockDim.x) {
+        V acc = V();
+        for (int k = k0; k < k1; ++k) {
+            const V v = __ldcs(in + (long long)k * row_vecs + i);
+            if constexpr (sizeof(V) == 16) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+            else acc += v;
+        }
+        out[(long long)s * row_vecs + i] = acc;
+    }
+}
+}  // namespace ab200
+
+extern "C" int32_t ab200_replica_sum(const float* in, const int32_t* row_start, int32_t n_src, int64_t row_elems, float* out,
+                                     void* stream) {
+    AB200_REQUIRE(in && row_start && out && n_src >= 0 && row_elems >= 0, AB200_EINVAL, "bad arguments");
+    if (n_src == 0 || row_elems == 0) return AB200_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = row_elems % 4 == 0 && reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    const long long row_vecs = vec ? row_elems / 4 : row_elems;
+    const unsigned gx = (unsigned)std::min<long long>((row_vecs + 255) / 256, 64);
+    for (int32_t s0 = 0; s0 < n_src; s0 += 65535) {      // gridDim.y limit
+        const dim3 grid(gx, (unsigned)std::min<int32_t>(65535, n_src - s0));
+        if (vec)
+            ab200::replica_sum_kernel<float4><<<grid, 256, 0, st>>>(reinterpret_cast<const float4*>(in), row_start + s0, row_vecs,
+                                                                   reinterpret_cast<float4*>(out) + (long long)s0 * row_vecs);
+        else
+            ab200::replica_sum_kernel<float><<<grid, 256, 0, st>>>(in, row_start + s0, row_vecs, out + (long long)s0 * row_vecs);
+        ab200::note_launch();
+        AB200_CUDA_TRY(cudaGetLastError());
+    }
+    return AB200_OK;
+}

@@ -231,8 +231,9 @@ __device__ inline void set_next_sample(const float4** next_sh, const TraceParams
     next_sh[0] = nullptr; next_sh[1] = nullptr;
     if (prm.wave > 0 && li + prm.wave < prm.a.n_local) {
         const int hn = prm.a.local_rows ? prm.a.local_rows[li + prm.wave] : li + prm.wave;
-        next_sh[0] = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hn * prm.a.n_points;
-        next_sh[1] = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hn * prm.a.n_points;
+        const int sn = prm.a.src_rows ? __ldg(prm.a.src_rows + hn) : hn;
+        next_sh[0] = reinterpret_cast<const float4*>(prm.a.points) + (size_t)sn * prm.a.n_points;
+        next_sh[1] = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)sn * prm.a.n_points;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.a.incident + 4 * hn));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.a.target_idx + hn));
         if (prm.a.orientations) asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.a.orientations + (size_t)hn * 16));
@@ -789,8 +790,9 @@ trace_fwd_kernel(const TraceParams prm) {
     // 0), orientation (threads 32..47), incident direction and the window-sample rows (every thread); meanwhile the
     // whole shared-memory window is cleared
     long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
-    const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const int hs = prm.a.src_rows ? __ldg(prm.a.src_rows + h) : h;   // activation index map: surface row of this sample
+    const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hs * P;
+    const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hs * P;
     WindowSamples ws;
     load_window_samples<THREADS>(ws, pts_h, nrm_h, p_begin, p_end);
     const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1),
@@ -1224,14 +1226,18 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
         if (ONLY_IRREGULAR) {   // add to what the fast loop wrote for this point
             if (touched) {
                 orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
-                const float4 a4 = *gpp, b4 = *gnp;
-                *gpp = make_float4(a4.x + gp4.x, a4.y + gp4.y, a4.z + gp4.z, a4.w + gp4.w);
-                *gnp = make_float4(b4.x + gn4.x, b4.y + gn4.y, b4.z + gn4.z, b4.w + gn4.w);
+                if (grad_points) {
+                    const float4 a4 = *gpp, b4 = *gnp;
+                    *gpp = make_float4(a4.x + gp4.x, a4.y + gp4.y, a4.z + gp4.z, a4.w + gp4.w);
+                    *gnp = make_float4(b4.x + gn4.x, b4.y + gn4.y, b4.z + gn4.z, b4.w + gn4.w);
+                }
             }
         } else {
             orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
-            *gpp = gp4;
-            *gnp = gn4;
+            if (grad_points) {
+                *gpp = gp4;
+                *gnp = gn4;
+            }
         }
     }
 }
@@ -1339,8 +1345,10 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
         const float gn2 = -2.0f * (pc.dot * gr2 + grn * i2);
         float4 gp4 = make_float4(go0, go1, go2, 0.f), gn4 = make_float4(gn0, gn1, gn2, 0.f);
         orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
-        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = gp4;
-        reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = gn4;
+        if (grad_points) {   // NULL: the caller wants the orientation / blocker gradients only (motor-position optimisation)
+            reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = gp4;
+            reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = gn4;
+        }
     }
     n_irregular_out = n_irr;
 }
@@ -1531,8 +1539,10 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
         const float gn2 = -2.0f * (dot_in * s_gr2 + grn * i2);
         float4 gp4 = make_float4(s_go0, s_go1, s_go2, 0.f), gn4 = make_float4(gn0, gn1, gn2, 0.f);
         orient_point_backward(src, o_raw, n_raw, gp4, gn4, gori_acc);
-        reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = gp4;
-        reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = gn4;
+        if (grad_points) {   // NULL: the caller wants the orientation / blocker gradients only (motor-position optimisation)
+            reinterpret_cast<float4*>(grad_points)[(size_t)h * P + p] = gp4;
+            reinterpret_cast<float4*>(grad_normals)[(size_t)h * P + p] = gn4;
+        }
     };
     // The CTA's last, partial round (npts mod THREADS points - 16 of 10000 with 768 threads) would keep one warp busy for a
     // whole point while all others wait at the barrier: those points are split by ray PAIR instead - `slots` (a power of
@@ -1638,8 +1648,9 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
     // start-up loads issued together before the first barrier (see trace_fwd_kernel)
     PointSrc src;
-    src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const int hs = prm.a.src_rows ? __ldg(prm.a.src_rows + h) : h;   // activation index map (the GRADIENT rows stay per sample)
+    src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hs * P;
+    src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hs * P;
     src.O = prm.a.orientations ? O_sh : nullptr;
     // the forward of the same call recorded its window (ab200_trace_args::windows): no sampling, no placement
     const bool have_window = prm.a.windows != nullptr && prm.split == 1;
@@ -1986,10 +1997,13 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
     const ab200_trace_args* a = &b->fwd;
     int32_t rc = validate(a);
     if (rc != AB200_OK) return rc;
-    AB200_REQUIRE(b->grad_flux && b->grad_points && b->grad_normals, AB200_EINVAL, "NULL gradient pointer");
+    AB200_REQUIRE(b->grad_flux, AB200_EINVAL, "NULL gradient pointer");
+    AB200_REQUIRE((b->grad_points == nullptr) == (b->grad_normals == nullptr), AB200_EINVAL,
+                  "grad_points and grad_normals must both be given or both be NULL");
+    AB200_REQUIRE(b->grad_points || b->grad_orientations || b->grad_prims, AB200_EINVAL, "no gradient output requested");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t np4 = (size_t)a->n_samples * a->n_points * 4;
-    if (a->n_local < a->n_samples) {
+    if (a->n_local < a->n_samples && b->grad_points) {
         AB200_CUDA_TRY(cudaMemsetAsync(b->grad_points, 0, np4 * sizeof(float), st));
         AB200_CUDA_TRY(cudaMemsetAsync(b->grad_normals, 0, np4 * sizeof(float), st));
     }

@@ -512,8 +512,9 @@ trace_fwd_v3_kernel(const TraceParams prm) {
     const int wh = min(U, prm.win_cap / kPitch);
 
     long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
-    const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)h * P;
-    const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)h * P;
+    const int hs = prm.a.src_rows ? __ldg(prm.a.src_rows + h) : h;
+    const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hs * P;
+    const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hs * P;
     WindowSamples ws;
     load_window_samples<THREADS>(ws, pts_h, nrm_h, 0, U > wh ? P : 0);
     const float i0 = __ldg(prm.a.incident + 4 * h), i1 = __ldg(prm.a.incident + 4 * h + 1), i2 = __ldg(prm.a.incident + 4 * h + 2);

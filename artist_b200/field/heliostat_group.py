@@ -28,65 +28,107 @@ class HeliostatGroup:
         self.kinematics = Kinematics()
         self.number_of_active_heliostats = 0
         self.active_heliostats_mask = torch.zeros(self.number_of_heliostats, device=device)
-        self._asp, self._asn, self._pending_alignment = surface_points, surface_normals, None
+        self._asp, self._asn, self._pending_alignment, self._pending_gather = surface_points, surface_normals, None, None
         self.active_canting = canting
         self.active_facet_translations = facet_translations
         self.active_nurbs_control_points = nurbs_control_points
         self._reflection_inputs = None
         self._active_rows = None
 
-    # ``active_surface_points`` / ``active_surface_normals`` after an alignment (``heliostat_group_rigid_body.py:217-222,
-    # 265-270``) are LAZY: ``align_surfaces_with_*`` only records (un-aligned rows, orientations) and the ray tracer
-    # consumes that pair directly (the rotation is fused into the trace kernels, ``ab200_trace_args::orientations``).
-    # Reading either attribute materialises both aligned ``[N,P,4]`` tensors once (``ab200_align_fwd``) - same values,
-    # same autograd graph as the eager reference.
+    # ``active_surface_points`` / ``active_surface_normals`` are LAZY in two ways (same values and autograd graph as the
+    # eager reference whenever somebody reads them):
+    #  * after ``activate_heliostats`` with a selecting / replicating mask they are a pending GATHER of the group's rows
+    #    (``ops.ActivationMap``; the reference copies them with repeat_interleave, ``heliostat_group.py:256-315``);
+    #  * after an alignment (``heliostat_group_rigid_body.py:217-222,265-270``) they are a pending ROTATION
+    #    (rows, orientations).
+    # The ray tracer consumes both pending forms directly: its kernels read surface row ``rows[sample]`` and rotate it
+    # themselves (``ab200_trace_args::src_rows`` / ``::orientations``), so neither the replicated nor the aligned
+    # ``[N,P,4]`` tensors ever exist in HBM on that path.
+    def _materialise(self, which: int) -> None:
+        from .. import ops
+
+        if self._pending_alignment is not None:
+            points, normals, orientations, amap = self._pending_alignment
+            if amap is not None:
+                points, normals = points.index_select(0, amap.rows.long()), normals.index_select(0, amap.rows.long())
+            self._asp, self._asn = ops.align_surfaces(points, normals, orientations)
+            self._pending_alignment = None
+        elif self._pending_gather is not None:
+            rows = self._pending_gather.rows.long()
+            if which == 0:
+                self._asp = self.surface_points.index_select(0, rows)
+            else:
+                self._asn = self.surface_normals.index_select(0, rows)
+            if self._asp is not None and self._asn is not None:
+                self._pending_gather = None
+
     @property
     def active_surface_points(self) -> torch.Tensor:
         if self._asp is None:
-            self._materialise_alignment()
+            self._materialise(0)
         return self._asp
 
     @active_surface_points.setter
     def active_surface_points(self, value: torch.Tensor) -> None:
         if self._asn is None and self._pending_alignment is not None:
-            self._materialise_alignment()
+            self._materialise(1)
         self._asp = value
         self._pending_alignment = None
+        if self._asn is not None:
+            self._pending_gather = None
 
     @property
     def active_surface_normals(self) -> torch.Tensor:
         if self._asn is None:
-            self._materialise_alignment()
+            self._materialise(1)
         return self._asn
 
     @active_surface_normals.setter
     def active_surface_normals(self, value: torch.Tensor) -> None:
         if self._asp is None and self._pending_alignment is not None:
-            self._materialise_alignment()
+            self._materialise(0)
         self._asn = value
         self._pending_alignment = None
+        if self._asp is not None:
+            self._pending_gather = None
 
     def _set_active_surface(self, points: torch.Tensor, normals: torch.Tensor) -> None:
-        self._asp, self._asn, self._pending_alignment = points, normals, None
+        self._asp, self._asn, self._pending_alignment, self._pending_gather = points, normals, None, None
+
+    def _set_pending_gather(self, amap) -> None:
+        self._asp, self._asn, self._pending_alignment, self._pending_gather = None, None, None, amap
+
+    def _record_alignment(self, orientations: torch.Tensor) -> None:
+        """``rows @ O^T`` recorded, not executed (see above)."""
+        if self._pending_gather is not None and self._asp is None and self._asn is None:
+            pending = (self.surface_points, self.surface_normals, orientations, self._pending_gather)
+        else:
+            pending = (self.active_surface_points, self.active_surface_normals, orientations, None)
+        self._asp, self._asn, self._pending_alignment, self._pending_gather = None, None, pending, None
 
     def _set_pending_alignment(self, points: torch.Tensor, normals: torch.Tensor, orientations: torch.Tensor) -> None:
-        self._asp, self._asn, self._pending_alignment = None, None, (points, normals, orientations)
+        self._asp, self._asn, self._pending_alignment, self._pending_gather = None, None, (points, normals, orientations, None), None
 
-    def _materialise_alignment(self) -> None:
-        from .. import ops
-
-        points, normals, orientations = self._pending_alignment
-        self._asp, self._asn = ops.align_surfaces(points, normals, orientations)
-
-    def _fused_alignment(self):
-        """``(points, normals, orientations)`` if the alignment has not been materialised, else None."""
-        if self._pending_alignment is not None and self._asp is None and self._asn is None:
-            return self._pending_alignment
-        return None
+    def _fused_alignment(self, with_map: bool = False):
+        """``(points, normals, orientations)`` if the alignment has not been materialised, else None.  With ``with_map``
+        a fourth entry is the pending activation map (or None) and ``points`` / ``normals`` are then the group's
+        un-replicated rows; without it a pending map is resolved first (per-sample rows, one gather)."""
+        if self._pending_alignment is None or self._asp is not None or self._asn is not None:
+            return None
+        points, normals, orientations, amap = self._pending_alignment
+        if with_map:
+            return points, normals, orientations, amap
+        if amap is not None:
+            points, normals = points.index_select(0, amap.rows.long()), normals.index_select(0, amap.rows.long())
+            self._pending_alignment = (points, normals, orientations, None)
+        return points, normals, orientations
 
     def _active_points_per_heliostat(self) -> int:
-        fused = self._fused_alignment()
-        return int((fused[0] if fused is not None else self.active_surface_points).shape[1])
+        if self._pending_alignment is not None and self._asp is None:
+            return int(self._pending_alignment[0].shape[1])
+        if self._pending_gather is not None and self._asp is None:
+            return int(self.surface_points.shape[1])
+        return int(self.active_surface_points.shape[1])
 
     # The reference materialises ``preferred_reflection_directions`` ([N,P,4]) inside trace_rays; the fused
     # kernel never needs it in memory, so it is evaluated only if somebody reads the attribute.
@@ -131,12 +173,17 @@ class HeliostatGroup:
         if identity:
             self._active_rows = None
             pick = lambda t: t
+            self._set_active_surface(self.surface_points, self.surface_normals)
         else:
-            rows = torch.repeat_interleave(torch.arange(self.number_of_heliostats, device=active_heliostats_mask.device),
-                                           active_heliostats_mask.long())
+            from .. import ops
+
+            if getattr(self, "_amap_key", None) != key:
+                self._amap, self._amap_key = ops.ActivationMap.from_mask(active_heliostats_mask), key
+            rows = self._amap.rows.long()
             self._active_rows = rows
             pick = lambda t: t.index_select(0, rows.to(t.device))
-        self._set_active_surface(pick(self.surface_points), pick(self.surface_normals))
+            # the [N,P,4] surfaces are NOT copied: pending gather, consumed by the ray tracer as an index map
+            self._set_pending_gather(self._amap)
         self.active_canting = pick(self.canting)
         self.active_facet_translations = pick(self.facet_translations)
         self.active_nurbs_control_points = pick(self.nurbs_control_points)

@@ -29,7 +29,7 @@ class HeliostatGroupRigidBody(HeliostatGroup):
     def _apply(self, orientations: torch.Tensor) -> None:
         # points @ O^T, normals @ O^T (:217-222, :265-270) - recorded, not executed: the ray tracer fuses the rotation
         # into its kernels; reading active_surface_points / _normals materialises them (HeliostatGroup properties)
-        self._set_pending_alignment(self.active_surface_points, self.active_surface_normals, orientations)
+        self._record_alignment(orientations)
 
     def align_surfaces_with_incident_ray_directions(self, aim_points, incident_ray_directions, active_heliostats_mask,
                                                     device=None) -> None:

@@ -124,6 +124,34 @@ def pack_distortions(distortions_u: torch.Tensor, distortions_e: torch.Tensor) -
     return torch.stack([distortions_u.float(), distortions_e.float()], dim=-1).contiguous()
 
 
+@dataclass
+class ActivationMap:
+    """Index map of ``HeliostatGroup.activate_heliostats`` (``artist/field/heliostat_group.py:256-315``): sample ``k`` is
+    heliostat ``rows[k]``; the replicas of heliostat ``s`` are the contiguous samples ``row_start[s] .. row_start[s+1]-1``
+    (``repeat_interleave`` order).  Handed to ``trace`` instead of replicated ``[N,P,4]`` surface copies."""
+
+    rows: torch.Tensor        # int32 [N], non-decreasing
+    row_start: torch.Tensor   # int32 [Nh+1]
+
+    @staticmethod
+    def from_mask(mask: torch.Tensor) -> "ActivationMap":
+        counts = mask.long()
+        rows = torch.repeat_interleave(torch.arange(counts.numel(), device=mask.device), counts).to(torch.int32)
+        row_start = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=mask.device)
+        row_start[1:] = torch.cumsum(counts, 0)
+        return ActivationMap(rows.contiguous(), row_start)
+
+
+def replica_sum(per_sample: torch.Tensor, amap: ActivationMap) -> torch.Tensor:
+    """``[N,...] -> [Nh,...]``: sum of every heliostat's replica rows (``ab200_replica_sum``, fixed order)."""
+    per_sample = _f32(per_sample, "per-sample rows")
+    n_src = amap.row_start.numel() - 1
+    out = torch.empty(n_src, *per_sample.shape[1:], device=per_sample.device)
+    row_elems = per_sample[0].numel() if per_sample.shape[0] else int(torch.tensor(per_sample.shape[1:]).prod())
+    _lib.call("ab200_replica_sum", _p(per_sample), _p(amap.row_start), n_src, row_elems, _p(out), _stream())
+    return out
+
+
 _planar_registry: dict = {}   # data_ptr of an interleaved [N,R,P,2] buffer -> (weakref to it, version, planar [2,N,R,P])
 
 
@@ -160,9 +188,9 @@ def planar_distortions(distortions: torch.Tensor) -> torch.Tensor | None:
 
 def _trace_args(points, normals, incident, distortions, trig, target_idx, targets: TargetTensors, opt: TraceOptions,
                 local_rows, flux, intercept, on_target, blocking, dbg=None, blk=None, orientations=None,
-                windows=None) -> _lib.TraceArgs:
-    n, p, _ = points.shape
-    r = distortions.shape[1]
+                windows=None, src_rows=None) -> _lib.TraceArgs:
+    p = points.shape[1]
+    n, r = distortions.shape[0], distortions.shape[1]
     a = _lib.TraceArgs()
     a.abi_version = ABI_VERSION
     a.n_samples, a.n_points, a.n_rays = n, p, r
@@ -191,6 +219,7 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
     a.stats = _p(trace_stats)
     a.orientations = _p(orientations)
     a.windows = _p(windows)
+    a.src_rows = _p(src_rows)
     a.distortions_planar = _p(planar_distortions(distortions)) if (use_planar and dbg is None and trig is None) else None
     return a
 
@@ -262,18 +291,19 @@ def _prepare_blocking(bi: BlockingInputs, opt: TraceOptions, n: int, dev):
 class _TraceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, bi, b_corners,
-                b_spans, b_normals, orientations):
+                b_spans, b_normals, orientations, amap):
         points, normals, incident = _f32(points, "points"), _f32(normals, "normals"), _f32(incident, "incident")
         distortions = _f32(distortions, "distortions")
         target_idx_object = target_idx
         target_idx = _i32(target_idx, "target_area_indices")
         if orientations is not None:
             orientations = _f32(orientations, "orientations")
-            if orientations.shape != (points.shape[0], 4, 4):
-                raise _lib.Ab200Error("orientations must be [N,4,4] with one matrix per row of points")
-        n = points.shape[0]
+            if orientations.shape != (distortions.shape[0], 4, 4):
+                raise _lib.Ab200Error("orientations must be [N,4,4] with one matrix per sample")
+        n = distortions.shape[0]
         dev = points.device
-        _validate_trace_inputs(points, normals, incident, distortions, trig, target_idx_object, local_rows, targets)
+        _validate_trace_inputs(points, normals, incident, distortions, trig, target_idx_object, local_rows, targets, amap)
+        src_rows = None if amap is None else amap.rows
         flux = torch.empty(n, opt.res_u, opt.res_e, device=dev)
         intercept = torch.empty(n, device=dev)
         on_target = torch.empty(n, device=dev)
@@ -284,8 +314,10 @@ class _TraceFn(torch.autograd.Function):
         # the backward re-uses the bitmap windows the forward placed (one per sample)
         windows = torch.empty(n, 4, dtype=torch.int32, device=dev) if any(ctx.needs_input_grad) else None
         args = _trace_args(points, normals, incident, distortions, trig, target_idx, targets, opt, local_rows,
-                           flux, intercept, on_target, blocking, blk=blk, orientations=orientations, windows=windows)
+                           flux, intercept, on_target, blocking, blk=blk, orientations=orientations, windows=windows,
+                           src_rows=src_rows)
         _lib.call("ab200_trace_fwd", C.byref(args), _stream())
+        ctx.amap = amap
         ctx.save_for_backward(points, normals, incident, distortions, trig, target_idx, local_rows, orientations,
                               *(blk[1:] if blk is not None else ()))
         ctx.windows = windows
@@ -307,11 +339,18 @@ class _TraceFn(torch.autograd.Function):
         else:
             g_flux = _f32(g_flux, "grad_flux")
             g_stride = u * e
-        g_points = torch.empty_like(points)
-        g_normals = torch.empty_like(normals)
+        amap = ctx.amap
+        # surface gradients only if somebody wants them (a motor-position optimisation does not: 64 B per point saved)
+        need_surface = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        g_points = g_normals = None
+        if need_surface:
+            shape = (distortions.shape[0], *points.shape[1:])      # per SAMPLE; folded onto the source rows below
+            g_points = torch.empty(shape, device=points.device)
+            g_normals = torch.empty(shape, device=points.device)
         b = _lib.TraceBwdArgs()
         b.fwd = _trace_args(points, normals, incident, distortions, trig, target_idx, ctx.targets, ctx.opt, local_rows,
-                            None, None, None, None, blk=blk, orientations=orientations, windows=ctx.windows)
+                            None, None, None, None, blk=blk, orientations=orientations, windows=ctx.windows,
+                            src_rows=None if amap is None else amap.rows)
         b.grad_flux, b.grad_points, b.grad_normals = _p(g_flux), _p(g_points), _p(g_normals)
         b.grad_flux_stride = g_stride
         g_corners = g_spans = g_bnormals = None
@@ -322,7 +361,10 @@ class _TraceFn(torch.autograd.Function):
         if orientations is not None and ctx.needs_input_grad[13]:
             g_ori = torch.zeros_like(orientations)
         b.grad_orientations = _p(g_ori)
-        _lib.call("ab200_trace_bwd", C.byref(b), _stream())
+        if need_surface or need_blockers or g_ori is not None:
+            _lib.call("ab200_trace_bwd", C.byref(b), _stream())
+        if need_surface and amap is not None:
+            g_points, g_normals = replica_sum(g_points, amap), replica_sum(g_normals, amap)
         if need_blockers:
             cs, ss, ns = ctx.blocker_shapes
             g_corners = torch.zeros(cs, device=points.device)
@@ -333,10 +375,10 @@ class _TraceFn(torch.autograd.Function):
             g_bnormals = torch.zeros(ns, device=points.device)
             g_bnormals[:, :3] = g_prims[:, 9:12]
         return (g_points, g_normals, None, None, None, None, None, None, None, None, g_corners, g_spans, g_bnormals,
-                g_ori)
+                g_ori, None)
 
 
-def _validate_trace_inputs(points, normals, incident, distortions, trig, target_idx, local_rows, targets) -> None:
+def _validate_trace_inputs(points, normals, incident, distortions, trig, target_idx, local_rows, targets, amap=None) -> None:
     """The kernels index raw pointers: every shape they assume is checked here (the reference would raise a shape or
     index error from its eager ops).  Index VALUES are range-checked once per tensor version (cached device read)."""
     if points.dim() != 3 or points.shape[-1] != 4:
@@ -344,6 +386,11 @@ def _validate_trace_inputs(points, normals, incident, distortions, trig, target_
     n, p, _ = points.shape
     if normals.shape != points.shape:
         raise _lib.Ab200Error(f"surface normals {tuple(normals.shape)} do not match the points {tuple(points.shape)}")
+    if amap is not None:   # points / normals are the group's un-replicated surfaces; N = number of samples of the map
+        if amap.rows.dtype != torch.int32 or amap.row_start.dtype != torch.int32 or amap.row_start.numel() != n + 1:
+            raise _lib.Ab200Error("activation map: rows / row_start must be int32 with row_start of length Nh+1")
+        _check_index_range(amap.rows, n, "activation map rows")
+        n = int(amap.rows.numel())
     if distortions.dim() != 4 or distortions.shape[0] != n or distortions.shape[2] != p or distortions.shape[3] != 2:
         raise _lib.Ab200Error(f"distortions must be [N={n},R,P={p},2], got {tuple(distortions.shape)} - was the ray tracer "
                               "built before the heliostats were re-activated?")
@@ -360,7 +407,8 @@ def _validate_trace_inputs(points, normals, incident, distortions, trig, target_
 
 def trace(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,
           local_rows: torch.Tensor | None = None, trig: torch.Tensor | None = None,
-          blocking: BlockingInputs | None = None, orientations: torch.Tensor | None = None):
+          blocking: BlockingInputs | None = None, orientations: torch.Tensor | None = None,
+          activation: ActivationMap | None = None):
     """Fused forward trace -> ``(flux[N,U,E], intercept[N], on_target[N], blocking[N])``; differentiable
     w.r.t. ``points`` and ``normals`` (and, with ``blocking``, the blockers' corners / spans / normals).
 
@@ -373,9 +421,9 @@ def trace(points, normals, incident, distortions, target_idx, targets: TargetTen
         local_rows = _i32(local_rows, "local_rows")
     if blocking is None:
         return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, None,
-                              None, None, None, orientations)
+                              None, None, None, orientations, activation)
     return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, blocking,
-                          blocking.corners, blocking.spans, blocking.normals, orientations)
+                          blocking.corners, blocking.spans, blocking.normals, orientations, activation)
 
 
 def trace_debug(points, normals, incident, distortions, target_idx, targets: TargetTensors, opt: TraceOptions,

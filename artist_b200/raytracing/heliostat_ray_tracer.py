@@ -99,13 +99,15 @@ class HeliostatRayTracer:
         blocking = self._blocking_inputs(target_area_indices) if self.blocking_active else None
         if torch.is_grad_enabled() and self._targets.n_planar + self._targets.n_cyl > 1:
             ops.prefetch_uniform_target(target_area_indices)   # for get_bitmaps_per_target's backward, off the critical path
-        fused = group._fused_alignment()
-        if fused is not None:   # alignment not materialised: the kernels rotate the un-aligned rows themselves
-            points, normals, orientations = fused
+        fused = group._fused_alignment(with_map=True)
+        if fused is not None:   # alignment not materialised: the kernels rotate the un-aligned rows themselves - and, with
+            points, normals, orientations, amap = fused    # an activation map, read the group's un-replicated rows
+        elif group._pending_gather is not None and group._asp is None and group._asn is None:
+            points, normals, orientations, amap = group.surface_points, group.surface_normals, None, group._pending_gather
         else:
-            points, normals, orientations = group.active_surface_points, group.active_surface_normals, None
+            points, normals, orientations, amap = group.active_surface_points, group.active_surface_normals, None, None
         return ops.trace(points, normals, incident_ray_directions, self._packed, target_area_indices, self._targets,
-                         opt, local_rows=self._local_rows, blocking=blocking, orientations=orientations)
+                         opt, local_rows=self._local_rows, blocking=blocking, orientations=orientations, activation=amap)
 
     # ---- blocking (artist/raytracing/blocking.py, heliostat_ray_tracer.py:159-183,292-301,445-480) -----------------
     @staticmethod
@@ -128,10 +130,12 @@ class HeliostatRayTracer:
                 active_rows = getattr(g, "_active_rows", None)
                 if active_rows is None:     # all-ones mask: sample i is heliostat i
                     active_rows = torch.arange(g.number_of_heliostats, device=c.device)
-                fused = g._fused_alignment()
+                fused = g._fused_alignment(with_map=True)
                 if fused is not None:   # only the 4 corner rows are rotated; the full alignment stays lazy
-                    aligned, _ = ops.align_surfaces(fused[0].index_select(1, rows), fused[1].index_select(1, rows),
-                                                    fused[2])
+                    cp, cn = fused[0].index_select(1, rows), fused[1].index_select(1, rows)
+                    if fused[3] is not None:
+                        cp, cn = cp.index_select(0, fused[3].rows.long()), cn.index_select(0, fused[3].rows.long())
+                    aligned, _ = ops.align_surfaces(cp, cn, fused[2])
                 else:
                     aligned = g.active_surface_points.index_select(1, rows)
                 # a heliostat activated several times contributes the geometry of its last sample

@@ -132,9 +132,19 @@ typedef struct ab200_trace_args {
                                 surface points per thread in packed fp32x2 registers and read each plane with one 8-byte
                                 load that IS the register pair (the interleaved layout costs two register moves per ray);
                                 ab200_sample_distortions writes both layouts in one pass.  Without it the general kernels run. */
+    const int32_t* src_rows; /* optional [N] (NULL = identity): activation index map.  Sample h reads its surface from row
+                                src_rows[h] of `points` / `normals`, which then hold the group's UN-replicated [Nh,P,4]
+                                surfaces - replaces the repeat_interleave copies of HeliostatGroup.activate_heliostats
+                                (artist/field/heliostat_group.py:256-315; 640 MB at config-3 size).  Everything else
+                                (incident, target_idx, distortions, orientations, outputs, gradient rows) stays per sample;
+                                ab200_replica_sum folds the per-sample gradient rows back onto the source rows. */
 } ab200_trace_args;
 
 int32_t ab200_trace_fwd(const ab200_trace_args* args, void* stream);
+
+/* out[s,:] = sum of in[k,:] for k in [row_start[s], row_start[s+1]) - the backward of the activation index map (replicas of a
+ * heliostat are contiguous samples); fixed summation order.  in [N,row_elems], row_start [n_src+1], out [n_src,row_elems]. */
+int32_t ab200_replica_sum(const float* in, const int32_t* row_start, int32_t n_src, int64_t row_elems, float* out, void* stream);
 
 /*
  * ab200_trace_bwd - explicit backward of ab200_trace_fwd (replaces the autograd graph the
@@ -148,7 +158,9 @@ typedef struct ab200_trace_bwd_args {
     const float* grad_flux;   /* [N,U,E]; row n starts at grad_flux + n * grad_flux_stride */
     int64_t grad_flux_stride; /* in floats: U*E (or -1) for a dense tensor, 0 when every sample shares one [U,E] gradient
                                  (e.g. the loss is taken on the per-target sum) - no [N,U,E] expansion is materialised */
-    float* grad_points;       /* out [N,P,4] (w component 0) */
+    float* grad_points;       /* out [N,P,4] (w component 0); grad_points and grad_normals may BOTH be NULL when only
+                                 grad_orientations / grad_prims are wanted (motor-position optimisation): the kernel then
+                                 skips the 64 B per point of gradient stores */
     float* grad_normals;      /* out [N,P,4] (w component 0) */
     float* grad_prims;        /* blocking only, may be NULL: [H,12] d/d(corner0, span_u, span_v, normal), ACCUMULATED with
                                  float atomics (caller zeroes it) */

@@ -216,3 +216,58 @@ def test_lazy_alignment_fused_and_materialised_paths_agree():
     # a fresh activation drops the recorded alignment without running it
     group.activate_heliostats(mask)
     assert group._fused_alignment() is None and group.active_surface_points is raw_p
+
+
+def test_activation_index_map_equals_replicated_copies():
+    """``activate_heliostats`` with a selecting / replicating mask (``artist/field/heliostat_group.py:256-315``): the tracer
+    reads the group's un-replicated surfaces through an index map (``ab200_trace_args::src_rows``) instead of
+    ``repeat_interleave`` copies.  Flux and factors are bit-identical to tracing the materialised copies; the gradient w.r.t.
+    the group's surface points (``ab200_replica_sum`` of the per-sample rows) equals autograd's ``index_select`` backward;
+    without surface gradients (motor-position optimisation) the backward skips them and returns the same orientation
+    gradient."""
+    from artist_b200 import HeliostatRayTracer, build_synthetic_scenario, synthetic_field_tensors
+
+    n, ppf, rays, res = 6, (10, 10), 6, (64, 64)
+    ft = synthetic_field_tensors(n, control_points=(6, 6), surface_bump=0.002)
+    scenario, group = build_synthetic_scenario(n, number_of_rays=rays, points_per_facet=ppf, device=DEV, field_tensors=ft)
+    mask = torch.tensor([2, 0, 1, 3, 0, 1], dtype=torch.int32, device=DEV)
+    n_s = int(mask.sum())
+    tidx = torch.zeros(n_s, dtype=torch.int32, device=DEV)
+    inc = torch.nn.functional.normalize(torch.tensor([[0.0, 0.96, -0.28, 0.0]], device=DEV)
+                                        + 0.05 * torch.randn(n_s, 4, device=DEV) * torch.tensor([1.0, 1.0, 1.0, 0.0], device=DEV), dim=1)
+    aim = scenario.solar_tower.get_centers_of_target_areas(tidx)
+    wgt = torch.rand(n_s, res[1], res[0], device=DEV)
+    base_p, base_n = group.surface_points, group.surface_normals
+
+    def run(materialise: bool, surface_grads: bool = True):
+        group.surface_points = base_p.detach().clone().requires_grad_(surface_grads)
+        group.surface_normals = base_n.detach().clone().requires_grad_(surface_grads)
+        group.activate_heliostats(mask)
+        if materialise:
+            assert group.active_surface_points.shape[0] == n_s      # the read gathers the copies (reference behaviour)
+            assert group.active_surface_normals.shape[0] == n_s
+        else:
+            assert group._pending_gather is not None and group._asp is None
+        motors = aligned_motors.clone().requires_grad_(True)
+        group.align_surfaces_with_motor_positions(motors + 0.0, mask)
+        tracer = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor(res))
+        if not materialise:
+            assert group._fused_alignment(with_map=True)[3] is not None, "the index map was meant to reach the tracer"
+        out = tracer.trace_rays(inc, mask, tidx)
+        (out[0] * wgt).sum().backward()
+        return out, group.surface_points.grad, group.surface_normals.grad, motors.grad
+
+    group.activate_heliostats(mask)
+    group.align_surfaces_with_incident_ray_directions(aim, inc, mask)   # sets the motor positions of the samples
+    aligned_motors = group.kinematics.active_motor_positions.detach().clone()
+    lazy, gp, gn, gm = run(False)
+    eager, gp_e, gn_e, gm_e = run(True)
+    assert lazy[0].sum() > 0
+    for a, b in zip(lazy, eager):
+        assert torch.equal(a, b)
+    assert gp[1].abs().max() == 0 and gp[4].abs().max() == 0            # de-activated heliostats
+    for a, b in ((gp, gp_e), (gn, gn_e), (gm, gm_e)):
+        assert (a - b).abs().max() <= 1e-5 * b.abs().max()
+    _, none_p, none_n, gm_only = run(False, surface_grads=False)
+    assert none_p is None and none_n is None and torch.equal(gm_only, gm)
+    group.surface_points, group.surface_normals = base_p, base_n
