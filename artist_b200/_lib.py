@@ -15,6 +15,7 @@ LIB_PATH = LIB_OVERRIDE or _DEFAULT_LIB_PATH
 ABI_VERSION = 4
 TRIG_SINCOSF, TRIG_TABLE, TRIG_POLY = 0, 1, 2
 FLAG_FP32_ACCUM = 1
+FLAG_ONE_CTA_PER_SAMPLE = 2
 
 c_float_p = C.c_void_p  # raw device/host addresses (tensor.data_ptr())
 c_int_p = C.c_void_p

@@ -11,7 +11,7 @@ __global__ void blocking_pack_kernel(const float* __restrict__ corners, const fl
                                      const float* __restrict__ normals, int n, float epsilon, float* __restrict__ prims) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    BlockPrim p;
+    BlockPrimPacked p;
     for (int q = 0; q < 3; ++q) {
         p.c0[q] = corners[(size_t)i * 12 + q];
         p.su[q] = spans[(size_t)i * 6 + q];
@@ -24,7 +24,7 @@ __global__ void blocking_pack_kernel(const float* __restrict__ corners, const fl
     float det = p.uu * p.vv - p.uv * p.uv;
     if (fabsf(det) < epsilon) det = (det > 0.f ? 1.f : (det < 0.f ? -1.f : 0.f)) * epsilon;   // torch.sign(det) * eps
     p.det = det;
-    reinterpret_cast<BlockPrim*>(prims)[i] = p;
+    reinterpret_cast<BlockPrimPacked*>(prims)[i] = p;
 }
 
 // one warp per sample; primitives are scanned in index order so the list (and the summation order of the optical
@@ -37,9 +37,9 @@ __global__ void __launch_bounds__(128) blocking_candidates_kernel(const float* _
                                                                   int* __restrict__ overflow) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n_samples) return;
-    const BlockPrim* P = reinterpret_cast<const BlockPrim*>(prims);
+    const BlockPrimPacked* P = reinterpret_cast<const BlockPrimPacked*>(prims);
     const int self = sample_to_blocker[warp];
-    const BlockPrim me = P[self];
+    const BlockPrimPacked me = P[self];
     float c[3], a[3], d[3];
     for (int q = 0; q < 3; ++q) {
         c[q] = me.c0[q] + 0.5f * (me.su[q] + me.sv[q]);
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) blocking_candidates_kernel(const float* _
         const int k = base + lane;
         bool hit = false;
         if (k < n_prims && k != self) {
-            const BlockPrim p = P[k];
+            const BlockPrimPacked p = P[k];
             float m[3];
             for (int q = 0; q < 3; ++q) m[q] = p.c0[q] + 0.5f * (p.su[q] + p.sv[q]) - c[q];
             const float rho = 0.5f * sqrtf(p.uu + p.vv + 2.0f * fabsf(p.uv)) + 0.1f;

@@ -13,11 +13,77 @@ namespace ab200 {
 
 constexpr int kMaxBlockCandidates = 64;
 
-// packed primitive: 16 floats
-struct BlockPrim {
+// packed primitive: 16 floats in global memory (ab200_blocking_pack) + 8 derived ones filled in when a CTA copies its
+// candidates to shared memory (block_finish_prim)
+struct BlockPrimPacked {    // row of the global primitive table
     float c0[3], su[3], sv[3], n[3];
     float uu, vv, uv, det;  // |su|^2, |sv|^2, su.sv, safe determinant
 };
+// shared-memory copy: what the per-point cull and the per-ray classification read comes first, as four 16-byte words
+// (c0 | n | U | V | ilu ilv det uv), the rest is only touched by the out-of-line soft-mask evaluation
+struct __align__(16) BlockPrim {
+    float c0[3], n[3];
+    float U[3], V[3];       // rectangle coordinates as dot products: u = off . U, v = off . V
+    float ilu, ilv;         // 1 / |su|, 1 / |sv|
+    float det, uv;
+    float su[3], uu, sv[3], vv;
+};
+constexpr int kPrimFloats = 16, kPrimFloatsShared = 24;
+static_assert(sizeof(BlockPrimPacked) == kPrimFloats * 4 && sizeof(BlockPrim) == kPrimFloatsShared * 4, "BlockPrim layout");
+
+__device__ __forceinline__ void block_finish_prim(BlockPrim& p) {
+    const float idet = 1.0f / p.det;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        p.U[q] = (p.su[q] * p.vv - p.sv[q] * p.uv) * idet;
+        p.V[q] = (p.sv[q] * p.uu - p.su[q] * p.uv) * idet;
+    }
+    p.ilu = rsqrtf(p.uu); p.ilv = rsqrtf(p.vv);
+}
+
+// One CTA's candidate list -> shared memory (all threads of the CTA call this; ends with a barrier).
+template <int THREADS>
+__device__ __forceinline__ int block_load_candidates(BlockPrim* blk_sh, int* rows_sh, const ab200_blockers& B, int h, int tid) {
+    const int n = min(B.cand_count[h], kMaxBlockCandidates);
+    const int* cand = B.cand_idx + (size_t)h * B.max_candidates;
+    if (rows_sh) for (int i = tid; i < n; i += THREADS) rows_sh[i] = cand[i];
+    // packed row (c0 su sv n uu vv uv det) -> float index in BlockPrim
+    for (int i = tid; i < n * kPrimFloats; i += THREADS) {
+        const int c = i / kPrimFloats, k = i % kPrimFloats;
+        const int dst = k < 3 ? k : k < 6 ? 16 + (k - 3) : k < 9 ? 20 + (k - 6) : k < 12 ? 3 + (k - 9) : k == 12 ? 19 : k == 13 ? 23 : k == 14 ? 15 : 14;
+        reinterpret_cast<float*>(blk_sh)[c * kPrimFloatsShared + dst] = B.prims[(size_t)cand[c] * kPrimFloats + k];
+    }
+    __syncthreads();
+    for (int c = tid; c < n; c += THREADS) block_finish_prim(blk_sh[c]);
+    __syncthreads();
+    return n;
+}
+
+// explicit shared-memory loads of a primitive's hot words (the pointer travels through context structs and out-of-line
+// calls, where the compiler falls back to generic loads)
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+struct BlockHot {   // c0, n, U, V
+    float c0x, c0y, c0z, nx, ny, nz, Ux, Uy, Uz, Vx, Vy, Vz;
+};
+__device__ __forceinline__ BlockHot block_hot(unsigned prim_addr) {
+    const float4 a = lds128(prim_addr), b = lds128(prim_addr + 16), c = lds128(prim_addr + 32);
+    return BlockHot{a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+}
+// ray / rectangle-plane intersection in rectangle coordinates: t, u, v and d . n
+__device__ __forceinline__ void block_tuv(const BlockHot& p, float eps, float o0, float o1, float o2, float d0, float d1, float d2,
+                                          float& t, float& u, float& v, float& den) {
+    den = d0 * p.nx + d1 * p.ny + d2 * p.nz;
+    if (fabsf(den) < eps) den = den >= 0.0f ? eps : -eps;
+    const float b0 = o0 - p.c0x, b1 = o1 - p.c0y, b2 = o2 - p.c0z;
+    t = __fdividef(-(b0 * p.nx + b1 * p.ny + b2 * p.nz), den);
+    const float f0 = fmaf(t, d0, b0), f1 = fmaf(t, d1, b1), f2 = fmaf(t, d2, b2);
+    u = f0 * p.Ux + f1 * p.Uy + f2 * p.Uz;
+    v = f0 * p.Vx + f1 * p.Vy + f2 * p.Vz;
+}
 
 struct BlockParams {
     float softness, alpha, offset, epsilon;
@@ -45,6 +111,36 @@ __device__ __forceinline__ void block_geometry(BlockGeom& g, const BlockPrim& p,
     g.t = t; g.den = den;
 }
 
+// Cheap per-ray classification of the point's candidates (the hot loops call this, inline; everything else in this file is
+// out of line and only runs for the few rays inside a sigmoid transition):
+//   0  no candidate matters: blocked == 0
+//   1  some candidate shadows the ray completely: every sigmoid argument is >= 20.8, each factor rounds to 1.0f, the optical
+//      depth is >= 1 and blocked = 1 - exp(-alpha) == 1.0f in fp32 (alpha = 100: exp(-100) is below half an ulp of 1) - the
+//      ray carries no intensity and no gradient, exactly as in the reference's fp32 evaluation
+//   2  the ray is inside a transition band of some candidate: evaluate block_eval / block_backward
+// q = min(u, 1-u, v, 1-v, t - offset) is the ray's depth inside the (rectangle x half-line): relevant iff q > -m, saturated
+// iff q > m, with m = 20.8 / softness.
+__device__ __forceinline__ int block_classify(const BlockPrim* prims, unsigned long long mask, const BlockParams& bp, float o0,
+                                              float o1, float o2, float d0, float d1, float d2) {
+    const float m = 20.8f / bp.softness;
+    const bool can_saturate = bp.alpha >= 17.0f;   // exp(-alpha) < 2^-25
+    const unsigned base = (unsigned)__cvta_generic_to_shared(prims);
+    int cls = 0;
+    while (mask) {
+        const int c = __ffsll((long long)mask) - 1;
+        mask &= mask - 1;
+        const BlockHot p = block_hot(base + (unsigned)c * (kPrimFloatsShared * 4));
+        float t, u, v, den;
+        block_tuv(p, bp.epsilon, o0, o1, o2, d0, d1, d2, t, u, v, den);
+        const float q = fminf(fminf(fminf(u, 1.0f - u), fminf(v, 1.0f - v)), t - bp.offset);
+        if (q > -m) {
+            if (q > m && can_saturate) return 1;
+            cls = 2;
+        }
+    }
+    return cls;
+}
+
 // a ray this far outside the rectangle (or this close to / behind its origin) contributes < 1e-9
 __device__ __forceinline__ bool block_relevant(const BlockGeom& g, const BlockParams& bp) {
     const float m = 20.8f / bp.softness;
@@ -53,44 +149,123 @@ __device__ __forceinline__ bool block_relevant(const BlockGeom& g, const BlockPa
 
 // per-point cull of the candidate list against the undistorted reflection direction: bit c of the result is set if
 // candidate c may matter for some ray of this point
-static __device__ __noinline__ unsigned long long block_point_mask(const BlockPrim* prims, int n_cand, const BlockParams& bp,
-                                                               float o0, float o1, float o2, float r0, float r1, float r2) {
+// `dead` (optional): set when some candidate certainly shadows EVERY ray of the point completely - the undistorted
+// reflection hits it deeper inside than the scatter can reach (same margins as the keep test, mirrored), at a decent
+// incidence - so that each ray would classify as 1 (blocked == 1.0f): no intensity, no gradient.
+__device__ __forceinline__ unsigned long long block_point_mask(const BlockPrim* prims, int n_cand, const BlockParams& bp,
+                                                               float o0, float o1, float o2, float r0, float r1, float r2,
+                                                               bool* dead = nullptr) {
     unsigned long long mask = 0ull;
+    const unsigned base = (unsigned)__cvta_generic_to_shared(prims);
+    const float m = 20.8f / bp.softness;
+    bool all_dead = false;
     for (int c = 0; c < n_cand; ++c) {
-        const BlockPrim& p = prims[c];
         bool keep = true;
         if (bp.cull_angle > 0.0f) {
-            BlockGeom g;
-            block_geometry(g, p, bp, o0, o1, o2, r0, r1, r2);
-            const float cosi = fabsf(g.den);
+            const unsigned addr = base + (unsigned)c * (kPrimFloatsShared * 4);
+            const BlockHot p = block_hot(addr);
+            float t, u, v, den;
+            block_tuv(p, bp.epsilon, o0, o1, o2, r0, r1, r2, t, u, v, den);
+            const float cosi = fabsf(den);
             if (cosi > 0.05f) {
-                const float delta = fabsf(g.t) * bp.cull_angle / cosi * 1.5f + 0.02f;   // lateral reach of the scatter (m)
-                const float mu = 20.8f / bp.softness + delta * rsqrtf(p.uu), mv = 20.8f / bp.softness + delta * rsqrtf(p.vv);
-                keep = (g.t > -delta - 0.1f) && (g.u > -mu) && (g.u < 1.0f + mu) && (g.v > -mv) && (g.v < 1.0f + mv);
+                const float4 w = lds128(addr + 48);   // ilu, ilv, det, uv
+                const float delta = fabsf(t) * bp.cull_angle * __fdividef(1.5f, cosi) + 0.02f;   // lateral reach of the scatter (m)
+                const float mu = fmaf(delta, w.x, m), mv = fmaf(delta, w.y, m);
+                keep = (t > -delta - 0.1f) && (u > -mu) && (u < 1.0f + mu) && (v > -mv) && (v < 1.0f + mv);
+                all_dead |= (cosi > 0.2f) && (bp.alpha >= 17.0f) && (t > bp.offset + m + 0.15f + delta) &&
+                            (fminf(u, 1.0f - u) > mu) && (fminf(v, 1.0f - v) > mv);
             }
         }
         if (keep) mask |= (1ull << c);
     }
+    if (dead) *dead = all_dead;
     return mask;
 }
 
 // blocked = 1 - exp(-alpha * sum_k sigma_k)
 static __device__ __noinline__ float block_eval(const BlockPrim* prims, unsigned long long mask, const BlockParams& bp, float o0,
                                             float o1, float o2, float d0, float d1, float d2) {
+    const unsigned base = (unsigned)__cvta_generic_to_shared(prims);
+    const float k = bp.softness, m = 20.8f / k;
     float sum = 0.0f;
     while (mask) {
         const int c = __ffsll((long long)mask) - 1;
         mask &= mask - 1;
-        BlockGeom g;
-        block_geometry(g, prims[c], bp, o0, o1, o2, d0, d1, d2);
-        if (!block_relevant(g, bp)) continue;
-        const float k = bp.softness;
-        const float inside = sigmoidf_fast(k * g.u) * sigmoidf_fast(k * (1.0f - g.u)) * sigmoidf_fast(k * g.v) *
-                             sigmoidf_fast(k * (1.0f - g.v));
-        const float front = sigmoidf_fast(k * (g.t - bp.offset));
+        const BlockHot p = block_hot(base + (unsigned)c * (kPrimFloatsShared * 4));
+        float t, u, v, den;
+        block_tuv(p, bp.epsilon, o0, o1, o2, d0, d1, d2, t, u, v, den);
+        if (!(fminf(fminf(fminf(u, 1.0f - u), fminf(v, 1.0f - v)), t - bp.offset) > -m)) continue;   // contributes < 1e-9
+        const float inside = sigmoidf_fast(k * u) * sigmoidf_fast(k * (1.0f - u)) * sigmoidf_fast(k * v) * sigmoidf_fast(k * (1.0f - v));
+        const float front = sigmoidf_fast(k * (t - bp.offset));
         sum += fminf(fmaxf(inside * front, 0.0f), 1.0f);
     }
     return 1.0f - __expf(-bp.alpha * sum);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Deferral of shadow-affected points.  The ray loops of the trace kernels run at the register budget of the unblocked
+// kernels only if they contain no blocking code at all (measured: 68 local loads + 35 local stores per ray and a 8x slower
+// backward with the soft mask inline, profiles/r02_motor_ncu_before.txt).  So a CTA traces its sample in two passes:
+//   1. the ordinary loops (compiled without blocking) over the points whose candidate mask is EMPTY - the per-point cull
+//      (block_point_mask, out of line, once per point) decides; the other points are only recorded in a shared bit set;
+//   2. the recorded points, spread evenly over the CTA's threads whatever their position on the mirror (shadows are
+//      compact blobs: the round-robin point -> thread map of pass 1 would leave most lanes idle), through the generic
+//      loops with the per-ray classification / soft mask.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kDeferWords = 512;   // 16384 points per CTA (chunk); larger chunks evaluate the mask inline
+
+struct DeferCtx {
+    unsigned* bits;     // shared [kDeferWords]: bit (p - p_begin) set = point deferred to pass 2
+    int* prefix;        // shared [kDeferWords]: exclusive prefix sum of the words' popcounts (defer_scan)
+    int n_words, count; // words in use; number of deferred points (after defer_scan)
+    const BlockPrim* blk;
+    int n_blk;
+    BlockParams bp;
+};
+
+// pass 1, per point: kPointClear = trace it here; kPointDeferred = recorded, the caller skips the point; kPointDead = every
+// ray is completely shadowed (the caller traces it without taps / writes zero gradients)
+enum { kPointClear = 0, kPointDeferred = 1, kPointDead = 2 };
+__device__ __forceinline__ int defer_point(const DeferCtx* dc, int local_index, float o0, float o1, float o2, float r0, float r1,
+                                           float r2) {
+    if (dc == nullptr || dc->n_blk == 0) return kPointClear;
+    bool dead;
+    if (block_point_mask(dc->blk, dc->n_blk, dc->bp, o0, o1, o2, r0, r1, r2, &dead) == 0ull) return kPointClear;
+    if (dead) return kPointDead;
+    atomicOr(dc->bits + (local_index >> 5), 1u << (local_index & 31));
+    return kPointDeferred;
+}
+
+// all threads of the CTA; returns the number of deferred points
+template <int THREADS>
+__device__ __forceinline__ int defer_scan(DeferCtx& dc, int* total_sh) {
+    __syncthreads();   // pass 1 complete
+    if (threadIdx.x < 32) {
+        const int per_lane = (dc.n_words + 31) / 32, w0 = threadIdx.x * per_lane;
+        int sum = 0;
+        for (int w = w0; w < min(w0 + per_lane, dc.n_words); ++w) sum += __popc(dc.bits[w]);
+        int incl = sum;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)threadIdx.x >= d) incl += v;
+        }
+        int run = incl - sum;
+        for (int w = w0; w < min(w0 + per_lane, dc.n_words); ++w) { dc.prefix[w] = run; run += __popc(dc.bits[w]); }
+        if (threadIdx.x == 31) *total_sh = incl;
+    }
+    __syncthreads();
+    dc.count = *total_sh;
+    return dc.count;
+}
+
+// local index of the k-th deferred point (0 <= k < count)
+__device__ __forceinline__ int defer_lookup(const DeferCtx& dc, int k) {
+    int lo = 0, hi = dc.n_words - 1;
+    while (lo < hi) {   // last word with prefix <= k
+        const int mid = (lo + hi + 1) >> 1;
+        if (dc.prefix[mid] <= k) lo = mid; else hi = mid - 1;
+    }
+    return lo * 32 + (int)__fns(dc.bits[lo], 0, k - dc.prefix[lo] + 1);
 }
 
 // backward: given dL/dblocked, return blocked (recomputed) and d/d(origin), d/d(direction); d/d(primitive geometry) is
@@ -105,19 +280,21 @@ static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, 
                                                  float d2, float g_blocked_scale /* dL/dblocked */, float* grad_prims) {
     float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
     BlockBack out;
-    // first pass: optical depth
+    // first pass: optical depth (cheap rectangle coordinates; the candidates that matter are remembered)
+    const unsigned base = (unsigned)__cvta_generic_to_shared(prims);
+    const float k = bp.softness, m_rel = 20.8f / k;
     float sum = 0.0f;
-    unsigned long long m = mask;
+    unsigned long long m = mask, relevant = 0ull;
     while (m) {
         const int c = __ffsll((long long)m) - 1;
         m &= m - 1;
-        BlockGeom g;
-        block_geometry(g, prims[c], bp, o0, o1, o2, d0, d1, d2);
-        if (!block_relevant(g, bp)) continue;
-        const float k = bp.softness;
-        const float inside = sigmoidf_fast(k * g.u) * sigmoidf_fast(k * (1.0f - g.u)) * sigmoidf_fast(k * g.v) *
-                             sigmoidf_fast(k * (1.0f - g.v));
-        sum += fminf(fmaxf(inside * sigmoidf_fast(k * (g.t - bp.offset)), 0.0f), 1.0f);
+        const BlockHot p = block_hot(base + (unsigned)c * (kPrimFloatsShared * 4));
+        float t, u, v, den;
+        block_tuv(p, bp.epsilon, o0, o1, o2, d0, d1, d2, t, u, v, den);
+        if (!(fminf(fminf(fminf(u, 1.0f - u), fminf(v, 1.0f - v)), t - bp.offset) > -m_rel)) continue;
+        relevant |= 1ull << c;
+        const float inside = sigmoidf_fast(k * u) * sigmoidf_fast(k * (1.0f - u)) * sigmoidf_fast(k * v) * sigmoidf_fast(k * (1.0f - v));
+        sum += fminf(fmaxf(inside * sigmoidf_fast(k * (t - bp.offset)), 0.0f), 1.0f);
     }
     const float transmittance = __expf(-bp.alpha * sum);
     out.blocked = 1.0f - transmittance;
@@ -125,15 +302,17 @@ static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, 
     // dL/dsum = dL/dblocked * alpha * transmittance
     const float g_sum = g_blocked_scale * bp.alpha * transmittance;
     if (g_sum == 0.0f) return out;
-    m = mask;
+    m = relevant;
     while (m) {
         const int c = __ffsll((long long)m) - 1;
         m &= m - 1;
         const BlockPrim& p = prims[c];
         BlockGeom g;
-        block_geometry(g, p, bp, o0, o1, o2, d0, d1, d2);
-        if (!block_relevant(g, bp)) continue;
-        const float k = bp.softness;
+        {   // rectangle coordinates as in the first pass (and in block_eval), plus the offset vector
+            const BlockHot hp = block_hot(base + (unsigned)c * (kPrimFloatsShared * 4));
+            block_tuv(hp, bp.epsilon, o0, o1, o2, d0, d1, d2, g.t, g.u, g.v, g.den);
+            g.off[0] = fmaf(g.t, d0, o0 - hp.c0x); g.off[1] = fmaf(g.t, d1, o1 - hp.c0y); g.off[2] = fmaf(g.t, d2, o2 - hp.c0z);
+        }
         const float su0 = sigmoidf_fast(k * g.u), su1 = sigmoidf_fast(k * (1.0f - g.u));
         const float sv0 = sigmoidf_fast(k * g.v), sv1 = sigmoidf_fast(k * (1.0f - g.v));
         const float fr = sigmoidf_fast(k * (g.t - bp.offset));
@@ -144,7 +323,7 @@ static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, 
         const float g_v = g_sum * k * av * (sv1 - sv0) * au * fr;
         const float g_t0 = g_sum * k * fr * (1.0f - fr) * au * av;
         if (fabsf(g_u) + fabsf(g_v) + fabsf(g_t0) == 0.0f) continue;
-        const float idet = 1.0f / p.det;
+        const float idet = __fdividef(1.0f, p.det);
         const float pu = g.off[0] * p.su[0] + g.off[1] * p.su[1] + g.off[2] * p.su[2];
         const float pv = g.off[0] * p.sv[0] + g.off[1] * p.sv[1] + g.off[2] * p.sv[2];
         const float g_pu = (g_u * p.vv - g_v * p.uv) * idet, g_pv = (g_v * p.uu - g_u * p.uv) * idet;
@@ -153,7 +332,7 @@ static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, 
         for (int q = 0; q < 3; ++q) g_off[q] = g_pu * p.su[q] + g_pv * p.sv[q];
         const float dv[3] = {d0, d1, d2};
         const float g_t = g_t0 + g_off[0] * d0 + g_off[1] * d1 + g_off[2] * d2;
-        const float iden = 1.0f / g.den;
+        const float iden = __fdividef(1.0f, g.den);
         // t = ((c0 - o).n) / (d.n)
 #pragma unroll
         for (int q = 0; q < 3; ++q) {

@@ -288,10 +288,14 @@ __device__ __forceinline__ bool angles_regular(float u, float e) {
 }
 __device__ __forceinline__ bool cosine_regular(float a) { return !(a < 0.0f) || (a < -1e-18f && a > -1e18f); }
 
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+enum { kDeferOff = 0, kDeferRecord = 1, kDeferList = 2, kDeferSkip = 3 };
+
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR, bool BLK>
 __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h, int p_begin,
                                          int p_end, float i0, float i1, float i2, int& cnt_lam_out, int& cnt_int_out,
-                                         int& cnt_blk_out, bool& fell_back_out) {
+                                         int& cnt_blk_out, bool& fell_back_out, const DeferCtx* dc = nullptr,
+                                         int dmode = kDeferOff) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
     const float4* pts = src.pts;
@@ -304,14 +308,36 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
     int cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
     bool fell_back = false;
 
-    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+    // (blocking_device.cuh, "Deferral"): kDeferRecord = pass 1 (this instantiation has no blocking code; shadow-affected
+    // points are recorded and skipped), kDeferList = pass 2 over the recorded points, kDeferSkip = the irregular-ray pass
+    // behind a deferring fast loop (recorded points are traced completely by pass 2)
+    const int n_items = dmode == kDeferList ? dc->count : p_end - p_begin;
+    int p_list = (dmode == kDeferList && tid < n_items) ? p_begin + defer_lookup(*dc, tid) : 0;
+    for (int it = tid; it < n_items; it += THREADS) {
+        const int p = dmode == kDeferList ? p_list : p_begin + it;
+        if (dmode == kDeferList) {
+            // the recorded points are scattered over the surface: no coalescing, no streaming pattern - the rows and the R
+            // distortion pairs of the thread's NEXT point are pulled into L2 while this one is traced
+            if (it + THREADS < n_items) {
+                p_list = p_begin + defer_lookup(*dc, it + THREADS);
+                prefetch_l2(pts + p_list); prefetch_l2(nrm + p_list);
+                for (int r = 0; r < R; ++r) prefetch_l2(dist + (size_t)r * P + p_list);
+            }
+        }
         PointCtx pc;
         {
             float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
             orient_point(src, o4, n4);
             make_point(pc, T, i0, i1, i2, o4, n4);
         }
+        bool point_dead = false;   // pass 1: every ray of the point is completely shadowed (counted, not splatted)
+        if (!BLK && dmode == kDeferRecord) {
+            const int pcls = defer_point(dc, p - p_begin, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2);
+            if (pcls == kPointDeferred) continue;
+            point_dead = pcls == kPointDead;
+        }
         const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
+        if (BLK && dmode == kDeferSkip && bmask) continue;
         const float2* dp = dist + p;
         float2 d_next = __ldcs(dp);
         for (int r = 0; r < R; ++r) {
@@ -326,8 +352,14 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
             if (ONLY_IRREGULAR && point_regular(pc) && angles_regular<TRIG>(d.x, d.y) && cosine_regular(hit.a)) continue;
             float blocked = 0.0f;
             if (BLK) {
-                if (bmask) blocked = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                if (bmask) {
+                    const int cls = block_classify(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                    if (cls) blocked = cls == 1 ? 1.0f : block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                }
                 cnt_blk += (blocked < 1e-3f);
+            } else if (dmode == kDeferRecord) {
+                if (point_dead) { cnt_lam += (hit.lam > 0.0f); continue; }   // blocked == 1: no intensity
+                cnt_blk += 1;   // an unshadowed point of a blocking trace: blocked == 0
             }
             // intensities = lambert * (1 - blocked) * (1 - extinction) * reflectivity   (:482-487); lambert * 1 is exact
             const float inten = BLK ? smul(smul(smul(hit.lam, ssub(1.0f, blocked)), ome), refl) : smul(smul(hit.lam, ome), refl);
@@ -445,7 +477,10 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
             const float lam = valid ? smul(mag, -a) : 0.0f;
             float blocked = 0.0f;
             if (BLK) {
-                if (bmask) blocked = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                if (bmask) {
+                    const int cls = block_classify(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                    if (cls) blocked = cls == 1 ? 1.0f : block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                }
                 cnt_blk += (blocked < 1e-3f);
             }
             const float inten = BLK ? smul(smul(smul(lam, ssub(1.0f, blocked)), ome), refl) : smul(smul(lam, ome), refl);
@@ -508,7 +543,6 @@ __device__ __forceinline__ void fwd_rays_planar_fast(const TraceParams& prm, con
     cnt_lam_out = cnt_lam; cnt_int_out = cnt_int; cnt_blk_out = cnt_blk; fell_back_out = fell_back; n_irregular_out = n_irr;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
 // a in (-1e18, -1e-18), i.e. front-facing AND regular: ONE unsigned range test on the bit pattern
 // (bits(-1e-18f) = 0xA19392EF, bits(-1e18f) = 0xDD5E0B6B; negative floats order like their bit patterns)
@@ -534,7 +568,7 @@ template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK, bool REVEN>
 __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h,
                                                       int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
                                                       int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
-                                                      int& n_irregular_out) {
+                                                      int& n_irregular_out, const DeferCtx* dc = nullptr) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
     const float4* pts = src.pts;
@@ -563,7 +597,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     const unsigned row_bytes = (unsigned)fc.ww * 4u;
     // factor counters: valid rays = R * (regular points) - cnt_bad; invalid rays are rare, so the bookkeeping (and the
     // irregularity flag, which implies invalid) lives in a rarely taken branch
-    int cnt_bad = 0, n_reg_points = 0, cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
+    int cnt_bad = 0, n_reg_points = 0, cnt_lam = 0, cnt_int = 0, cnt_blk = 0, cnt_irr = 0, n_dead_points = 0, cnt_dead_bad = 0;
     bool fell_back = false, any_irr = false;
     // the next distortion pair of this thread: +2P inside a point, then over to the first pair of its next point
     const int n_pairs = (R + 1) >> 1;
@@ -591,6 +625,17 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             nx += THREADS;
             if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
             continue;
+        }
+        bool point_dead = false;   // pass 1 of a blocking trace: every ray of the point is completely shadowed - traced for the
+        if (!BLK && dc) {          // on-target counter, no taps
+            const int pcls = defer_point(dc, p - p_begin, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2);
+            if (pcls == kPointDeferred) {   // shadow-affected: pass 2
+                nx += THREADS;
+                if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+                continue;
+            }
+            point_dead = pcls == kPointDead;
+            n_dead_points += (int)point_dead;
         }
         const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
         ++n_reg_points;
@@ -651,12 +696,16 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             float2 lam = K.mul(a, bc2(-mag));                       // mag * (-a)
             lam.x = valid0 ? lam.x : 0.0f; lam.y = valid1 ? lam.y : 0.0f;
             float2 inten;
+            bool shadow0 = false, shadow1 = false;   // fully shadowed rays: zero intensity, no taps
             if (BLK) {
                 float2 blocked = make_float2(0.f, 0.f);
                 const bool reg0 = ang0 && (fr0 || !(a.x < 0.0f)), reg1 = two && ang1 && (fr1 || !(a.y < 0.0f));
                 if (bmask) {
-                    if (reg0) blocked.x = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.x, dy.x, dz.x);
-                    if (reg1) blocked.y = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.y, dy.y, dz.y);
+                    const int cls0 = reg0 ? block_classify(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.x, dy.x, dz.x) : 0;
+                    const int cls1 = reg1 ? block_classify(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.y, dy.y, dz.y) : 0;
+                    if (cls0) blocked.x = cls0 == 1 ? 1.0f : block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.x, dy.x, dz.x);
+                    if (cls1) blocked.y = cls1 == 1 ? 1.0f : block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.y, dy.y, dz.y);
+                    shadow0 = cls0 == 1; shadow1 = cls1 == 1;
                 }
                 cnt_blk += (reg0 && blocked.x < 1e-3f) + (reg1 && blocked.y < 1e-3f);
                 inten = K.mul(K.mul(K.mul(lam, K.sub(K.one, blocked)), bc2(ome)), bc2(refl));
@@ -667,8 +716,12 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             }
             if (!(valid0 && valid1)) {   // rare
                 cnt_bad += (int)!valid0 + (int)(two && !valid1);
-                any_irr |= !ang0 || ((a.x < 0.0f) && !fr0) || (two && (!ang1 || ((a.y < 0.0f) && !fr1)));
+                const bool irr0 = !ang0 || ((a.x < 0.0f) && !fr0), irr1 = two && (!ang1 || ((a.y < 0.0f) && !fr1));
+                any_irr |= irr0 || irr1;
+                if (!point_dead) cnt_irr += (int)irr0 + (int)irr1;
+                else cnt_dead_bad += (int)!valid0 + (int)(two && !valid1);
             }
+            if (!BLK && point_dead) continue;   // (dc != nullptr) counted above, nothing to splat
             float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
             if (DBG) {
                 const size_t q = ((size_t)h * R + r) * P + p;
@@ -715,6 +768,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
 #pragma unroll
             for (int lane = 0; lane < 2; ++lane) {
                 if (!(lane ? valid1 : valid0)) continue;
+                if (BLK && (lane ? shadow1 : shadow0)) continue;
                 const int cex = (int)(__float_as_uint(lane ? me.y : me.x) - kIdxBits);   // ie - e0
                 const int cux = (int)(__float_as_uint(lane ? mu.y : mu.x) - kIdxBits);   // iu - u0
                 const int ie = cex + e0w, iu = cux + u0w;   // only the slow paths need the absolute pixel index
@@ -758,7 +812,12 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
         }
     }
     const int cnt_valid = n_reg_points * R - cnt_bad;
-    cnt_lam_out = BLK ? cnt_lam : cnt_valid; cnt_int_out = BLK ? cnt_int : cnt_valid; cnt_blk_out = cnt_blk; fell_back_out = fell_back;
+    // (dead points of pass 1: their valid rays are on target but carry no intensity and count as blocked)
+    cnt_lam_out = BLK ? cnt_lam : cnt_valid; cnt_int_out = BLK ? cnt_int : cnt_valid - (n_dead_points * R - cnt_dead_bad);
+    fell_back_out = fell_back;
+    // pass 1 of a blocking trace: every regular ray traced here is unshadowed (blocked == 0 < 1e-3); the irregular ones are
+    // counted by the generic pass that re-traces them
+    cnt_blk_out = (!BLK && dc) ? (n_reg_points - n_dead_points) * R - cnt_irr : cnt_blk;
     n_irregular_out = any_irr ? 1 : 0;
 }
 
@@ -774,7 +833,10 @@ trace_fwd_kernel(const TraceParams prm) {
     __shared__ int cnt_sh[3];
     __shared__ int fallback_sh;
     __shared__ int fb_box[4];
-    __shared__ BlockPrim blk_sh[kMaxBlockCandidates];
+    __shared__ BlockPrim blk_sh[BLK ? kMaxBlockCandidates : 1];
+    __shared__ unsigned defer_bits_sh[BLK ? kDeferWords : 1];
+    __shared__ int defer_prefix_sh[BLK ? kDeferWords : 1];
+    __shared__ int defer_total_sh;
     __shared__ float O_sh[16];
     __shared__ const float4* next_sh[2];
 
@@ -872,37 +934,69 @@ trace_fwd_kernel(const TraceParams prm) {
     fc.n_blk = 0;
     if (BLK && prm.a.blockers.n_blockers > 0) {
         const ab200_blockers& B = prm.a.blockers;
-        fc.n_blk = min(B.cand_count[h], kMaxBlockCandidates);
         fc.bp.softness = B.softness; fc.bp.alpha = B.alpha; fc.bp.offset = B.ray_origin_offset; fc.bp.epsilon = B.epsilon;
         fc.bp.cull_angle = B.cull_angle;
-        for (int i = tid; i < fc.n_blk * 16; i += THREADS)
-            reinterpret_cast<float*>(blk_sh)[i] = B.prims[(size_t)B.cand_idx[(size_t)h * B.max_candidates + i / 16] * 16 + (i % 16)];
-        __syncthreads();
+        fc.n_blk = block_load_candidates<THREADS>(blk_sh, nullptr, B, h, tid);
     }
 
     int cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
     bool fell_back = false;
+    // Blocking: two passes (blocking_device.cuh, "Deferral") - the loops below run WITHOUT blocking code over the points no
+    // candidate can shadow and record the others, which the generic loop then traces with the soft mask, spread evenly
+    // over the CTA.  Chunks beyond the bit set's capacity evaluate the mask inline in the generic loops.
+    const bool blocking = BLK && fc.n_blk > 0;
+    const bool defer = BLK && (p_end - p_begin) <= kDeferWords * 32;
+    DeferCtx dc;
+    dc.bits = defer_bits_sh; dc.prefix = defer_prefix_sh; dc.n_words = (p_end - p_begin + 31) >> 5; dc.count = 0;
+    dc.blk = fc.blk; dc.n_blk = fc.n_blk; dc.bp = fc.bp;
+    if (BLK && defer) {
+        for (int w = tid; w < dc.n_words; w += THREADS) defer_bits_sh[w] = 0u;
+        __syncthreads();
+    }
+    const DeferCtx* rec = (BLK && defer) ? &dc : nullptr;
+    const int rec_mode = (BLK && defer) ? kDeferRecord : kDeferOff;
     // (fx_scale >= 1e-6: the packed loop's subnormal tap rounding scales it by 2^-100 and needs the result to stay normal)
-    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF && (BLK || prm.simple_counts) && (FP32ACC || prm.fx_scale >= 1e-6f)) {
+    if (BLK && !defer) {
+        if (T.planar)
+            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
+        else
+            fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
+    } else if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF && prm.simple_counts && (FP32ACC || prm.fx_scale >= 1e-6f)) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
         if ((R & 1) == 0)
-            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
+            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
         else
-            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
-#else
+            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
+#else   // tuning build without the packed loops: the scalar fast loop evaluates the mask inline, nothing is deferred
         fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #endif
         if (__syncthreads_or(n_irr != 0)) {   // never with physical inputs: the generic loop picks up the skipped rays
             int c1 = 0, c2 = 0, c3 = 0;
             bool fb = false;
-            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb);
+            const bool skip_masked = AB200_PACKED_RAYS && rec != nullptr;
+            fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb,
+                                                                         rec, skip_masked ? kDeferSkip : kDeferOff);
             cnt_lam += c1; cnt_int += c2; cnt_blk += c3; fell_back = fell_back || fb;
         }
     } else if (T.planar) {
-        fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, rec, rec_mode);
     } else {
-        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back);
+        fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, rec, rec_mode);
+    }
+    if (BLK && defer && blocking) {   // pass 2 (uniform over the CTA)
+        AB200_PHASE(4, 3);   // ray loop, pass 1
+        if (defer_scan<THREADS>(dc, &defer_total_sh) > 0) {
+            if (prm.a.stats && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(prm.a.stats) + 17, (unsigned long long)dc.count);
+            int c1 = 0, c2 = 0, c3 = 0;
+            bool fb = false;
+            if (T.planar)
+                fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb, &dc, kDeferList);
+            else
+                fwd_rays<THREADS, TRIG, DBG, FP32ACC, false, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb, &dc, kDeferList);
+            cnt_lam += c1; cnt_int += c2; cnt_blk += c3; fell_back = fell_back || fb;
+        }
+        AB200_PHASE(14, 4);   // stats[18]: pass 2 (deferred points)
     }
 
     AB200_PHASE(4, 3);   // ray loop (thread 0)
@@ -1095,7 +1189,8 @@ struct BwdCtx {
 template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR, bool BLK>
 __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc, const PointSrc& src, int h,
                                          int p_begin, int p_end, float i0, float i1, float i2, float* __restrict__ grad_points,
-                                         float* __restrict__ grad_normals, float* gori_acc) {
+                                         float* __restrict__ grad_normals, float* gori_acc, const DeferCtx* dc = nullptr,
+                                         int dmode = kDeferOff) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
     const float4* pts = src.pts;
@@ -1107,26 +1202,47 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
     const float k_int = mag * k_or;                 // d intensity / d lambert-cosine
     const float k_e = T.em1 / T.w, k_u = T.um1 / T.h;
 
-    for (int p = p_begin + tid; p < p_end; p += THREADS) {
+    // dmode: see fwd_rays
+    const int n_items = dmode == kDeferList ? dc->count : p_end - p_begin;
+    int p_list = (dmode == kDeferList && tid < n_items) ? p_begin + defer_lookup(*dc, tid) : 0;
+    for (int it = tid; it < n_items; it += THREADS) {
+        const int p = dmode == kDeferList ? p_list : p_begin + it;
+        if (dmode == kDeferList && it + THREADS < n_items) {   // scattered points: prefetch the next one's data (see fwd_rays)
+            p_list = p_begin + defer_lookup(*dc, it + THREADS);
+            prefetch_l2(pts + p_list); prefetch_l2(nrm + p_list);
+            for (int r = 0; r < R; ++r) prefetch_l2(dist + (size_t)r * P + p_list);
+        }
         const float4 o_raw = __ldg(pts + p), n_raw = __ldg(nrm + p);
         float4 o4 = o_raw, n4 = n_raw;
         orient_point(src, o4, n4);
         PointCtx pc;
         make_point(pc, T, i0, i1, i2, o4, n4);
+        bool point_dead = false;   // pass 1: every ray completely shadowed - zero gradient rows
+        if (!BLK && dmode == kDeferRecord) {
+            const int pcls = defer_point(dc, p - p_begin, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2);
+            if (pcls == kPointDeferred) continue;
+            point_dead = pcls == kPointDead;
+        }
         float go0 = 0.f, go1 = 0.f, go2 = 0.f;   // planar: grad origin (world); cylindrical: grad origin (cylinder frame)
         float gr0 = 0.f, gr1 = 0.f, gr2 = 0.f;   // grad preferred reflection direction
         float gow0 = 0.f, gow1 = 0.f, gow2 = 0.f;  // grad origin through the blocking term (always world frame)
         bool touched = false;
         const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
+        if (BLK && dmode == kDeferSkip && bmask) continue;
         const float2* dp = dist + p;
         float2 d_next = __ldcs(dp);
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < (point_dead ? 0 : R); ++r) {
             const float2 d = d_next;
             dp += P;
             if (r + 1 < R) d_next = __ldcs(dp);
             Scatter s;
             ray_trig<TRIG>(d.x, d.y, trig, (size_t)r * P + p, s.cu, s.su, s.ce, s.se);
             scatter(s, pc);
+            int bcls = 0;   // 1: fully shadowed - no intensity, no gradient (most rays of a deferred point); 2: inside a
+            if (BLK && bmask) {   // sigmoid transition
+                bcls = block_classify(bc.blk, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                if (bcls == 1) continue;
+            }
             Hit hit;
             if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
             if (ONLY_IRREGULAR && point_regular(pc) && angles_regular<TRIG>(d.x, d.y) && cosine_regular(hit.a)) continue;
@@ -1149,7 +1265,7 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
             const float g_int0 = sp.whu * (sp.wle * g1 + sp.whe * g2) + sp.wlu * (sp.whe * g3 + sp.wle * g4);
             float gdb0 = 0.f, gdb1 = 0.f, gdb2 = 0.f;
             float unblocked = 1.0f;
-            if (BLK && bmask) {   // intensity = lambert * (1 - blocked) * k_or
+            if (BLK && bcls == 2) {   // intensity = lambert * (1 - blocked) * k_or
                 const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
                                                     -g_int0 * hit.lam * k_or, bc.grad_prims);
                 unblocked = 1.0f - bb.blocked;
@@ -1300,6 +1416,11 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
                 const float fe = truncf(be), fu = truncf(bu);
                 const float fe1 = sadd(fe, 1.0f), fu1 = sadd(fu, 1.0f);
                 if (!(valid && (fe1 < e_lim) && (fu1 < u_lim))) continue;
+                int bcls = 0;   // 1: fully shadowed - no intensity, no gradient; 2: inside a sigmoid transition
+                if (BLK && bmask) {
+                    bcls = block_classify(bc.blk, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz);
+                    if (bcls == 1) continue;
+                }
                 const int ie = __float2int_rz(be), iu = __float2int_rz(bu);
                 const float wle = ssub(fe1, be), wlu = ssub(fu1, bu), whe = ssub(be, fe), whu = ssub(bu, fu);
                 float g1, g2, g3, g4;
@@ -1315,7 +1436,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
                 float g_int = whu * fmaf(wle, g1, whe * g2) + wlu * fmaf(whe, g3, wle * g4);
                 float inten = -a * k_lam;
                 float gdb0 = 0.f, gdb1 = 0.f, gdb2 = 0.f;
-                if (BLK && bmask) {   // intensity = lambert * (1 - blocked) * k_or  (rare: only shadowed points get here)
+                if (BLK && bcls == 2) {   // intensity = lambert * (1 - blocked) * k_or  (rare: rays inside a sigmoid transition)
                     const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
                                                         -g_int * inten, bc.grad_prims);
                     go0 += bb.go0; go1 += bb.go1; go2 += bb.go2;
@@ -1361,7 +1482,8 @@ template <int THREADS, int TRIG, bool BLK, bool REVEN>
 __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc,
                                                       const PointSrc& src, int h, int p_begin, int p_end, float i0, float i1,
                                                       float i2, float* __restrict__ grad_points,
-                                                      float* __restrict__ grad_normals, float* gori_acc, int& n_irregular_out) {
+                                                      float* __restrict__ grad_normals, float* gori_acc, int& n_irregular_out,
+                                                      const DeferCtx* dc = nullptr) {
     const int tid = threadIdx.x;
     const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
     const float4* pts = src.pts;
@@ -1428,14 +1550,22 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                 const float2 qe0 = K.mul(te, bc2(T.rw)), qu0 = K.mul(tu, bc2(T.rh));
                 const float2 be0 = pfma(pfma(pfma(qe0, bc2(-T.w), te), bc2(T.rw), qe0), bc2(T.em1), zero2);
                 const float2 bu0 = pfma(pfma(pfma(qu0, bc2(-T.h), tu), bc2(T.rh), qu0), bc2(T.um1), zero2);
-                const bool valid0 = ang0 && fr0 && (__float_as_uint(be0.x) <= em1_bits) && (__float_as_uint(bu0.x) <= um1_bits);
-                const bool valid1 = two && ang1 && fr1 && (__float_as_uint(be0.y) <= em1_bits) && (__float_as_uint(bu0.y) <= um1_bits);
+                const bool hit0 = ang0 && fr0 && (__float_as_uint(be0.x) <= em1_bits) && (__float_as_uint(bu0.x) <= um1_bits);
+                const bool hit1 = two && ang1 && fr1 && (__float_as_uint(be0.y) <= em1_bits) && (__float_as_uint(bu0.y) <= um1_bits);
+                // blocking class per lane (block_classify): a fully shadowed ray (1) is treated like an invalid one from here on
+                int bcls0 = 0, bcls1 = 0;
+                if (BLK && bmask) {
+                    if (hit0) bcls0 = block_classify(bc.blk, bmask, bc.bp, pc.o0, pc.o1, pc.o2, dx.x, dy_keep.x, dz.x);
+                    if (hit1) bcls1 = block_classify(bc.blk, bmask, bc.bp, pc.o0, pc.o1, pc.o2, dx.y, dy_keep.y, dz.y);
+                    if (bcls0 == 1 && bcls1 == 1) return;
+                }
+                const bool valid0 = hit0 && !(BLK && bcls0 == 1), valid1 = hit1 && !(BLK && bcls1 == 1);
                 const float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
                 const float2 me = make_float2(__fadd_rd(be.x, magic_e), __fadd_rd(be.y, magic_e));
                 const float2 mu = make_float2(__fadd_rd(bu.x, magic_u), __fadd_rd(bu.y, magic_u));
                 const int cex0 = (int)(__float_as_uint(me.x) - kIdxBits), cux0 = (int)(__float_as_uint(mu.x) - kIdxBits);   // ie - e0, iu - u0
                 const int cex1 = (int)(__float_as_uint(me.y) - kIdxBits), cux1 = (int)(__float_as_uint(mu.y) - kIdxBits);
-                if (!(valid0 && valid1))   // rare; irregular implies invalid
+                if (!(hit0 && hit1))   // rare; irregular implies invalid
                     any_irr |= !ang0 || ((a.x < 0.0f) && !fr0) || (two && (!ang1 || ((a.y < 0.0f) && !fr1)));
                 // ---- gather the four gradient taps per live lane ----
                 // window interior (implies on the bitmap: ie + 1 < E and iu + 1 < U)
@@ -1492,11 +1622,11 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                 const float2 dgz = lfma(wle, lsub(g1, g4), lmul(whe, lsub(g2, g3)));
                 float2 inten = lmul(a, bc2(-k_lam));
                 float2 gdb0 = zero2, gdb1 = zero2, gdb2 = zero2;
-                if (BLK && bmask) {   // intensity = lambert * (1 - blocked) * k_or  (rare: only shadowed points get here)
+                if (BLK && (bcls0 == 2 || bcls1 == 2)) {   // intensity = lambert * (1 - blocked) * k_or  (rare: sigmoid transitions)
                     float2 unblocked = make_float2(1.f, 1.f);
 #pragma unroll
                     for (int lane = 0; lane < 2; ++lane) {
-                        if (!(lane ? live1 : live0)) continue;
+                        if (!(lane ? live1 : live0) || (lane ? bcls1 : bcls0) != 2) continue;
                         const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2,
                                                             lane ? dx.y : dx.x, lane ? dy_keep.y : dy_keep.x, lane ? dz.y : dz.x,
                                                             -(lane ? g_int.y : g_int.x) * (lane ? inten.y : inten.x), bc.grad_prims);
@@ -1550,7 +1680,8 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     const int npts = p_end - p_begin, n_full = (npts / THREADS) * THREADS, n_tail = npts - n_full;
     int slots = 1;
     while (slots < n_pairs) slots <<= 1;
-    const bool split_tail = AB200_BWD_SPLIT_TAIL && REVEN && TRIG != AB200_TRIG_TABLE && n_full > 0 && n_tail > 0 && slots <= 32 && n_tail * slots <= THREADS;
+    const bool split_tail = AB200_BWD_SPLIT_TAIL && REVEN && TRIG != AB200_TRIG_TABLE && n_full > 0 && n_tail > 0 && slots <= 32 && n_tail * slots <= THREADS &&
+                            dc == nullptr;   // (a deferring pass records whole points)
     const int p_end_main = split_tail ? p_begin + n_full : p_end;
 
     int p = p_begin + tid;
@@ -1572,8 +1703,14 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
         }
         float2 go0 = zero2, go1 = zero2, go2 = zero2, gr0 = zero2, gr1 = zero2, gr2 = zero2;   // one partial sum per lane
         if (point_regular(pc)) {
+            const int pcls = BLK ? kPointClear : defer_point(dc, p - p_begin, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2);
+            if (pcls != kPointClear) {   // shadow-affected: pass 2 traces the point and writes its rows; completely shadowed:
+                nx += THREADS;           // zero rows from the epilogue below
+                if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+                if (pcls == kPointDeferred) continue;
+            }
             const unsigned long long bmask = (BLK && bc.n_blk) ? block_point_mask(bc.blk, bc.n_blk, bc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
-            for (int r = 0; r < R; r += 2) {
+            for (int r = 0; r < (pcls == kPointClear ? R : 0); r += 2) {
                 const bool two = REVEN || (r + 1 < R);
                 const float2 d0 = da, d1 = db;
                 {
@@ -1634,6 +1771,9 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     __shared__ float O_sh[16];
     __shared__ BlockPrim blk_sh[BLK ? kMaxBlockCandidates : 1];
     __shared__ int blk_rows_sh[BLK ? kMaxBlockCandidates : 1];
+    __shared__ unsigned defer_bits_sh[BLK ? kDeferWords : 1];
+    __shared__ int defer_prefix_sh[BLK ? kDeferWords : 1];
+    __shared__ int defer_total_sh;
     __shared__ const float4* next_sh[2];
     __shared__ __align__(8) unsigned long long stage_bar;   // mbarrier of the gradient-window staging (TMA bulk copies)
 
@@ -1730,30 +1870,57 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     bc.blk = blk_sh; bc.blk_rows = blk_rows_sh; bc.n_blk = 0; bc.grad_prims = grad_prims;
     if (BLK && prm.a.blockers.n_blockers > 0) {
         const ab200_blockers& B = prm.a.blockers;
-        bc.n_blk = min(B.cand_count[h], kMaxBlockCandidates);
         bc.bp.softness = B.softness; bc.bp.alpha = B.alpha; bc.bp.offset = B.ray_origin_offset; bc.bp.epsilon = B.epsilon;
         bc.bp.cull_angle = B.cull_angle;
-        for (int i = tid; i < bc.n_blk; i += THREADS) blk_rows_sh[i] = B.cand_idx[(size_t)h * B.max_candidates + i];
-        for (int i = tid; i < bc.n_blk * 16; i += THREADS)
-            reinterpret_cast<float*>(blk_sh)[i] = B.prims[(size_t)B.cand_idx[(size_t)h * B.max_candidates + i / 16] * 16 + (i % 16)];
+        bc.n_blk = block_load_candidates<THREADS>(blk_sh, blk_rows_sh, B, h, tid);
+    }
+    // Blocking: two passes, see trace_fwd_kernel and blocking_device.cuh ("Deferral")
+    const bool blocking = BLK && bc.n_blk > 0;
+    const bool defer = BLK && (p_end - p_begin) <= kDeferWords * 32;
+    DeferCtx dc;
+    dc.bits = defer_bits_sh; dc.prefix = defer_prefix_sh; dc.n_words = (p_end - p_begin + 31) >> 5; dc.count = 0;
+    dc.blk = bc.blk; dc.n_blk = bc.n_blk; dc.bp = bc.bp;
+    if (BLK && defer) {
+        for (int w = tid; w < dc.n_words; w += THREADS) defer_bits_sh[w] = 0u;
         __syncthreads();
     }
-    if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
+    const DeferCtx* rec = (BLK && defer) ? &dc : nullptr;
+    const int rec_mode = (BLK && defer) ? kDeferRecord : kDeferOff;
+    if (BLK && !defer) {
+        if (T.planar)
+            bwd_rays<THREADS, TRIG, true, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
+        else
+            bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
+    } else if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
         if ((prm.a.n_rays & 1) == 0)
-            bwd_rays_planar_fast2<THREADS, TRIG, BLK, true>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
+            bwd_rays_planar_fast2<THREADS, TRIG, false, true>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, rec);
         else
-            bwd_rays_planar_fast2<THREADS, TRIG, BLK, false>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
-#else
+            bwd_rays_planar_fast2<THREADS, TRIG, false, false>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, rec);
+#else   // tuning build without the packed loops: inline mask, nothing deferred
         bwd_rays_planar_fast<THREADS, TRIG, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
 #endif
-        if (__syncthreads_or(n_irr != 0))   // never with physical inputs (each thread re-reads only its own points)
-            bwd_rays<THREADS, TRIG, true, false, true, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
+        if (__syncthreads_or(n_irr != 0)) {   // never with physical inputs (each thread re-reads only its own points)
+            const bool skip_masked = AB200_PACKED_RAYS && rec != nullptr;
+            bwd_rays<THREADS, TRIG, true, false, true, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc,
+                                                            rec, skip_masked ? kDeferSkip : kDeferOff);
+        }
     } else if (T.planar) {
-        bwd_rays<THREADS, TRIG, true, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
+        bwd_rays<THREADS, TRIG, true, false, false, false>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, rec, rec_mode);
     } else {
-        bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc);
+        bwd_rays<THREADS, TRIG, false, false, false, false>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, rec, rec_mode);
+    }
+    if (BLK && defer && blocking) {   // pass 2 (uniform over the CTA)
+        AB200_PHASE(12, 3);  // ray loop, pass 1
+        const int n_def = defer_scan<THREADS>(dc, &defer_total_sh);
+        if (n_def > 0) {
+            if (T.planar)
+                bwd_rays<THREADS, TRIG, true, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, &dc, kDeferList);
+            else
+                bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, &dc, kDeferList);
+        }
+        AB200_PHASE(14, 5);  // stats[19]: pass 2 (deferred points)
     }
     AB200_PHASE(12, 3);  // ray loop (thread 0)
     if (gori_acc) {
@@ -1806,18 +1973,18 @@ struct LaunchPlan {
 
 // dynamic shared memory available to one CTA next to the kernels' static shared data (target, window, reduction
 // scratch, 64 blocking primitives: < 6 KB)
-static int max_window_bytes() {
+static int max_window_bytes(bool blocking) {
     int dev = 0, optin = 227 * 1024;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    return optin - 6 * 1024;
+    return optin - (blocking ? 14 : 6) * 1024;   // blocking: + 64 candidates x 96 B + the deferral bit set and its prefix sums
 }
 
-static LaunchPlan make_plan(int n_local, int n_points, int max_threads_large) {
+static LaunchPlan make_plan(int n_local, int n_points, int max_threads_large, bool force_large = false, bool blocking = false) {
     LaunchPlan pl;
     const int sms = sm_count();
-    if (n_local >= 2 * sms) {
+    if (n_local >= 2 * sms || force_large) {
         pl.threads = max_threads_large; pl.split = 1;
-        pl.smem_bytes = AB200_WIN_KB * 1024 < max_window_bytes() ? AB200_WIN_KB * 1024 : max_window_bytes();
+        pl.smem_bytes = AB200_WIN_KB * 1024 < max_window_bytes(blocking) ? AB200_WIN_KB * 1024 : max_window_bytes(blocking);
     } else {
         pl.threads = 512;
         const int want = (4 * sms + (n_local > 0 ? n_local : 1) - 1) / (n_local > 0 ? n_local : 1);
@@ -1954,7 +2121,7 @@ extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t ue = (size_t)a->res_u * a->res_e;
     // rows not traced by this rank stay zero; traced rows are accumulated into / overwritten
-    const LaunchPlan pl = make_plan(a->n_local, a->n_points, kFwdThreadsLarge);
+    const LaunchPlan pl = make_plan(a->n_local, a->n_points, kFwdThreadsLarge, (a->flags & AB200_FLAG_ONE_CTA_PER_SAMPLE) != 0, a->blockers.n_blockers > 0);
     const bool dbg = a->dbg_be || a->dbg_bu || a->dbg_t || a->dbg_lambert;
     const bool fp32acc = (a->flags & AB200_FLAG_FP32_ACCUM) != 0;
     // one CTA per sample and every sample traced here: each CTA clears its own bitmap row (no N*U*E memset pass)
@@ -2008,7 +2175,7 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
         AB200_CUDA_TRY(cudaMemsetAsync(b->grad_normals, 0, np4 * sizeof(float), st));
     }
     if (a->n_local == 0 || a->n_samples == 0) return AB200_OK;
-    const LaunchPlan pl = make_plan(a->n_local, a->n_points, kBwdThreadsLarge);
+    const LaunchPlan pl = make_plan(a->n_local, a->n_points, kBwdThreadsLarge, (a->flags & AB200_FLAG_ONE_CTA_PER_SAMPLE) != 0, a->blockers.n_blockers > 0);
     TraceParams prm;
     fill_params(prm, a, pl);
     const long long gstride = b->grad_flux_stride >= 0 ? b->grad_flux_stride : (long long)a->res_u * a->res_e;

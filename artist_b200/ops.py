@@ -89,6 +89,7 @@ class TraceOptions:
     scatter_sigma: float = 0.0
     trig_mode: int = _lib.TRIG_POLY
     fp32_accumulate: bool = False
+    one_cta_per_sample: bool = False   # force the kernels a full field runs (AB200_FLAG_ONE_CTA_PER_SAMPLE)
 
 
 @dataclass
@@ -212,7 +213,7 @@ def _trace_args(points, normals, incident, distortions, trig, target_idx, target
     a.reflectivity = float(opt.mirror_reflectivity)
     a.scatter_sigma = float(opt.scatter_sigma)
     a.trig_mode = int(opt.trig_mode)
-    a.flags = _lib.FLAG_FP32_ACCUM if opt.fp32_accumulate else 0
+    a.flags = (_lib.FLAG_FP32_ACCUM if opt.fp32_accumulate else 0) | (_lib.FLAG_ONE_CTA_PER_SAMPLE if opt.one_cta_per_sample else 0)
     a.flux, a.intercept, a.on_target, a.blocking = _p(flux), _p(intercept), _p(on_target), _p(blocking)
     if dbg is not None:
         a.dbg_be, a.dbg_bu, a.dbg_t, a.dbg_lambert = (_p(d) for d in dbg)

@@ -95,7 +95,8 @@ class HeliostatRayTracer:
             res_e=int(self.bitmap_resolution[indices.unbatched_bitmap_e]),
             res_u=int(self.bitmap_resolution[indices.unbatched_bitmap_u]),
             ray_magnitude=float(self.ray_magnitude), ray_extinction_factor=ray_extinction_factor,
-            mirror_reflectivity=mirror_reflectivity, scatter_sigma=sigma)
+            mirror_reflectivity=mirror_reflectivity, scatter_sigma=sigma,
+            one_cta_per_sample=getattr(self, "_force_one_cta_per_sample", False))
         blocking = self._blocking_inputs(target_area_indices) if self.blocking_active else None
         if torch.is_grad_enabled() and self._targets.n_planar + self._targets.n_cyl > 1:
             ops.prefetch_uniform_target(target_area_indices)   # for get_bitmaps_per_target's backward, off the critical path

@@ -144,85 +144,144 @@ class ClockSampler:
 
 # ---- own arm ---------------------------------------------------------------------------------------
 class Workload:
-    """Device-resident synthetic field + the fwd/bwd step through the public class API."""
+    """Device-resident synthetic field + the fwd/bwd step through the public class API.
 
-    def __init__(self, dev: torch.device, n: int, world: int, rank: int) -> None:
+    kind "surface" (headline; BASELINE.json configs 3/4): parameters = NURBS control points, planar target, blocking off.
+    kind "motor" (configs[4], tutorial 05 / AimPointOptimizer shape): parameters = motor positions, the tilted cylindrical
+    receiver, blocking ON, gradients through the trace's orientation gradient and the kinematics backward.
+    strong=True: ONE field shared by all ranks, split by the reference's sampler contract (HeliostatRayTracer(world_size,
+    rank), artist/raytracing/sampling.py:129-146); everything before the trace is replicated per rank as in the reference."""
+
+    def __init__(self, dev: torch.device, n: int, world: int, rank: int, kind: str = "surface", strong: bool = False) -> None:
         from artist_b200 import HeliostatRayTracer, NURBSSurfaces, build_synthetic_scenario
         from artist_b200.nurbs import create_nurbs_evaluation_grid
 
-        self.dev, self.n, self.world = dev, n, world
+        self.dev, self.n, self.world, self.kind, self.strong = dev, n, world, kind, strong
+        field_seed = 0 if strong else rank
         self.scenario, self.group = build_synthetic_scenario(
             n, number_of_rays=RAYS, points_per_facet=POINTS_PER_FACET, control_points=CONTROL_POINTS,
-            surface_bump=SURFACE_BUMP, seed=rank, device=dev)
+            surface_bump=SURFACE_BUMP, seed=field_seed, device=dev)
         g = self.group
-        self.mask, self.tidx, self.inc = self.scenario.index_mapping(g)
+        # index 1 = the cylindrical receiver of the synthetic tower (AB200_BENCH_MOTOR_TARGET=0: planar, diagnosis only)
+        target = int(os.environ.get("AB200_BENCH_MOTOR_TARGET", "1")) if kind == "motor" else None
+        self.mask, self.tidx, self.inc = self.scenario.index_mapping(g, single_target_area_index=target or 0)
         self.inc = self.inc.contiguous()
         self.aim = self.scenario.solar_tower.get_centers_of_target_areas(self.tidx)
-        self.cp = g.nurbs_control_points.detach().clone().requires_grad_(True)
-        g.nurbs_control_points = self.cp
         g.activate_heliostats(self.mask)
-        self.surf = NURBSSurfaces(g.nurbs_degrees, self.cp, device=dev)
-        grid = create_nurbs_evaluation_grid(torch.tensor(POINTS_PER_FACET), device=dev)
-        self.ev = grid[None, None].expand(n, g.number_of_facets_per_heliostat, -1, -1)
+        if kind == "surface":
+            self.param = g.nurbs_control_points.detach().clone().requires_grad_(True)
+            g.nurbs_control_points = self.param
+            g.activate_heliostats(self.mask)
+            self.surf = NURBSSurfaces(g.nurbs_degrees, self.param, device=dev)
+            grid = create_nurbs_evaluation_grid(torch.tensor(POINTS_PER_FACET), device=dev)
+            self.ev = grid[None, None].expand(n, g.number_of_facets_per_heliostat, -1, -1)
         g.align_surfaces_with_incident_ray_directions(self.aim, self.inc, self.mask)
-        self.tracer = HeliostatRayTracer(self.scenario, g, blocking_active=False, random_seed=7 + rank,
+        if kind == "motor":
+            self.param = g.kinematics.active_motor_positions.detach().clone().requires_grad_(True)
+        tracer_seed = 7 if strong else 7 + rank
+        self.tracer = HeliostatRayTracer(self.scenario, g, blocking_active=(kind == "motor"), random_seed=tracer_seed,
+                                         world_size=world if strong else 1, rank=rank if strong else 0,
                                          bitmap_resolution=torch.tensor(RES))
-        self.opt = torch.optim.Adam([self.cp], lr=1e-6, fused=True)
+        self.opt = torch.optim.Adam([self.param], lr=1e-6 if kind == "surface" else 1e-3, fused=True)
         self.p = g.surface_points.shape[1]
-        self.rays_per_step = n * self.p * RAYS
-        # pinned host mirrors for the end-to-end leg
-        self.h_cp = self.cp.detach().cpu().pin_memory()
+        self.n_local = len(self.tracer.distortions_sampler.rank_indices)
+        self.rays_per_step = self.n_local * self.p * RAYS
+        # pinned host mirrors + device staging of the end-to-end leg (double-buffered, see step_e2e)
+        self.h_param = self.param.detach().cpu().pin_memory()
         self.h_inc = self.inc.cpu().pin_memory()
         self.h_tidx = self.tidx.cpu().pin_memory()
         n_t = int(self.scenario.solar_tower.number_of_target_areas_per_type.sum())
-        self.h_flux = torch.empty(n_t, RES[1], RES[0]).pin_memory()
-        self.h_grad = torch.empty_like(self.h_cp).pin_memory()
-        self.h_loss = torch.empty(1).pin_memory()
+        self.h_flux = [torch.empty(n_t, RES[1], RES[0]).pin_memory() for _ in range(2)]
+        self.h_grad = [torch.empty_like(self.h_param).pin_memory() for _ in range(2)]
+        self.h_loss = [torch.empty(1).pin_memory() for _ in range(2)]
+        self.d_stage = [(torch.empty_like(self.param.detach()), torch.empty_like(self.inc), torch.empty_like(self.tidx))
+                        for _ in range(2)]
+        self.s_h2d, self.s_d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_up = [torch.cuda.Event() for _ in range(2)]
+        self.ev_used = [torch.cuda.Event() for _ in range(2)]
+        self.ev_down = [torch.cuda.Event() for _ in range(2)]
+        self.k = 0
+
+    def forward_local(self) -> torch.Tensor:
+        """This rank's per-target flux [T,U,E] (before the sum over ranks), with the autograd graph."""
+        g = self.group
+        g.activate_heliostats(self.mask)
+        if self.kind == "surface":
+            pts, nrm = self.surf.calculate_surface_points_and_normals(self.ev, g.active_canting, g.active_facet_translations)
+            g.active_surface_points = pts.reshape(self.n, -1, 4)
+            g.active_surface_normals = nrm.reshape(self.n, -1, 4)
+            g.align_surfaces_with_incident_ray_directions(self.aim, self.inc, self.mask)
+        else:
+            g.align_surfaces_with_motor_positions(self.param, self.mask)
+        flux, _, _, _ = self.tracer.trace_rays(self.inc, self.mask, self.tidx)
+        return self.tracer.get_bitmaps_per_target(flux, self.tidx)
 
     def step(self) -> torch.Tensor:
-        g = self.group
         self.opt.zero_grad(set_to_none=True)
-        g.activate_heliostats(self.mask)
-        pts, nrm = self.surf.calculate_surface_points_and_normals(self.ev, g.active_canting, g.active_facet_translations)
-        g.active_surface_points = pts.reshape(self.n, -1, 4)
-        g.active_surface_normals = nrm.reshape(self.n, -1, 4)
-        g.align_surfaces_with_incident_ray_directions(self.aim, self.inc, self.mask)
-        flux, _, _, _ = self.tracer.trace_rays(self.inc, self.mask, self.tidx)
-        total = self.tracer.get_bitmaps_per_target(flux, self.tidx)
+        total = self.forward_local()
         if self.world > 1:
             import torch.distributed.nn.functional as dist_fn
 
             total = dist_fn.all_reduce(total)  # autograd-aware SUM over ranks (NCCL, NVLink)
         loss = (total * total).mean()
         loss.backward()
+        if self.strong and self.world > 1:
+            # replicated parameters, each rank holds the gradient of its own samples (SurfaceReconstructor reduces the
+            # same way, artist/optim/surface_reconstructor.py:766-777)
+            torch.distributed.all_reduce(self.param.grad)
         self.opt.step()
         self.last_total = total
         return loss
 
     def step_e2e(self) -> None:
-        """Same step with HOST buffers: parameters/inputs come from pinned memory, flux + loss + gradient go back."""
+        """Same step with HOST buffers.  Every step uploads its parameters / incident directions / target indices from
+        pinned memory and downloads its per-target flux, loss and parameter gradient - on two copy streams, so that the
+        upload of step i and the download of step i-1 overlap the kernels of the step in flight (device staging buffers
+        and host result buffers are double-buffered; events order every re-use).  The host holds the results of step i-1
+        when step_e2e(i) returns - the one-step lag of a pipelined optimisation loop; flush_e2e() collects the last."""
+        b = self.k & 1
+        cs = torch.cuda.current_stream()
+        with torch.cuda.stream(self.s_h2d):
+            self.s_h2d.wait_event(self.ev_used[b])          # staging buffer b was consumed two steps ago
+            sp, si, st = self.d_stage[b]
+            sp.copy_(self.h_param, non_blocking=True)
+            si.copy_(self.h_inc, non_blocking=True)
+            st.copy_(self.h_tidx, non_blocking=True)
+            self.ev_up[b].record(self.s_h2d)
+        cs.wait_event(self.ev_up[b])
         with torch.no_grad():
-            self.cp.copy_(self.h_cp, non_blocking=True)
-            self.inc.copy_(self.h_inc, non_blocking=True)
-            self.tidx.copy_(self.h_tidx, non_blocking=True)
-        loss = self.step_keep_grad()
-        self.h_flux.copy_(self.last_total.detach(), non_blocking=True)
-        self.h_grad.copy_(self.cp.grad, non_blocking=True)
-        self.h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    def step_keep_grad(self) -> torch.Tensor:
+            self.param.copy_(sp)
+            self.inc.copy_(si)
+            self.tidx.copy_(st)
+        self.ev_used[b].record(cs)
         loss = self.step()
-        return loss
+        done = torch.cuda.Event()
+        done.record(cs)
+        total, grad, loss = self.last_total.detach(), self.param.grad, loss.detach().reshape(1)
+        with torch.cuda.stream(self.s_d2h):
+            self.s_d2h.wait_event(done)
+            self.h_flux[b].copy_(total, non_blocking=True)
+            self.h_grad[b].copy_(grad, non_blocking=True)
+            self.h_loss[b].copy_(loss, non_blocking=True)
+            for t in (total, grad, loss):
+                t.record_stream(self.s_d2h)
+            self.ev_down[b].record(self.s_d2h)
+        if self.k > 0:
+            self.ev_down[b ^ 1].synchronize()               # results of the previous step are on the host now
+        self.k += 1
+
+    def flush_e2e(self) -> None:
+        self.ev_down[(self.k - 1) & 1].synchronize()
+        self.s_h2d.synchronize()
 
     @property
     def e2e_bytes(self) -> tuple[int, int]:
-        h2d = self.h_cp.numel() * 4 + self.h_inc.numel() * 4 + self.h_tidx.numel() * 4
-        d2h = self.h_flux.numel() * 4 + self.h_grad.numel() * 4 + 4
+        h2d = self.h_param.numel() * 4 + self.h_inc.numel() * 4 + self.h_tidx.numel() * 4
+        d2h = self.h_flux[0].numel() * 4 + self.h_grad[0].numel() * 4 + 4
         return h2d, d2h
 
 
-def timed_loop(fn, steps: int, dev: torch.device, distributed: bool) -> float:
+def timed_loop(fn, steps: int, dev: torch.device, distributed: bool, finish=None) -> float:
     """ms per step over exactly `steps` steps: barrier + synchronize on both sides, CUDA events, max over ranks."""
     if distributed:
         torch.distributed.barrier()
@@ -231,6 +290,8 @@ def timed_loop(fn, steps: int, dev: torch.device, distributed: bool) -> float:
     e0.record()
     for _ in range(steps):
         fn()
+    if finish is not None:
+        finish()     # (end-to-end leg: the last step's download on the copy stream has reached the host)
     e1.record()
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1)
@@ -242,7 +303,7 @@ def timed_loop(fn, steps: int, dev: torch.device, distributed: bool) -> float:
     return ms / steps
 
 
-def cpu_oracle_step_factory(n: int, threads: int):
+def cpu_oracle_step_factory(n: int, threads: int, kind: str = "surface"):
     """The oracle port of the reference's eager path, same per-heliostat workload, on the host cores."""
     from artist_b200.scenario.synthetic import synthetic_field_tensors
     from oracle import artist_oracle as O
@@ -251,30 +312,45 @@ def cpu_oracle_step_factory(n: int, threads: int):
     ft = synthetic_field_tensors(n, control_points=CONTROL_POINTS, surface_bump=SURFACE_BUMP, seed=0)
     tg = O.targets_from_field_tensors(ft)
     ev = O.nurbs_evaluation_grid(*POINTS_PER_FACET)[None, None].expand(n, 4, -1, -1)
-    tidx = torch.zeros(n, dtype=torch.int32)
+    tidx = torch.full((n,), 1 if kind == "motor" else 0, dtype=torch.int32)
     inc = torch.tensor([0.0, 1.0, 0.0, 0.0]).expand(n, -1).contiguous()
     aim = O.aim_points(tg, tidx)
     kin = O.Kin(ft["positions"], ft["translation_deviations"], ft["rotation_deviations"],
                 ft["actuator_non_optimizable"], ft["actuator_optimizable"], True)
-    cp = ft["nurbs_control_points"].clone().requires_grad_(True)
-    opt = torch.optim.Adam([cp], lr=1e-6)
     p = 4 * POINTS_PER_FACET[0] * POINTS_PER_FACET[1]
     du, de = O.sun_distortions(RAYS, p, n, 7)
-
     first = {}
+    if kind == "surface":
+        param = ft["nurbs_control_points"].clone().requires_grad_(True)
+        opt = torch.optim.Adam([param], lr=1e-6)
+    else:
+        with torch.no_grad():
+            pts0, nrm0 = O.nurbs_points_and_normals(ft["nurbs_control_points"], 3, 3, ev, ft["canting"], ft["facet_translations"])
+            pts0, nrm0 = pts0.reshape(n, -1, 4), nrm0.reshape(n, -1, 4)
+            _, motor0 = O.incident_ray_directions_to_orientations(kin, inc, aim)
+        param = motor0.clone().requires_grad_(True)
+        opt = torch.optim.Adam([param], lr=1e-3)
+        owner = torch.arange(n)
 
     def step():
         opt.zero_grad(set_to_none=True)
-        pts, nrm = O.nurbs_points_and_normals(cp, 3, 3, ev, ft["canting"], ft["facet_translations"])
-        with torch.no_grad():
-            ori, _ = O.incident_ray_directions_to_orientations(kin, inc, aim)
-        ap, an = O.align_surfaces(pts.reshape(n, -1, 4), nrm.reshape(n, -1, 4), ori)
-        flux, *_ = O.trace_rays(ap, an, inc, du, de, tidx, tg, RES, batch_size=min(64, n))
+        if kind == "surface":
+            pts, nrm = O.nurbs_points_and_normals(param, 3, 3, ev, ft["canting"], ft["facet_translations"])
+            with torch.no_grad():
+                ori, _ = O.incident_ray_directions_to_orientations(kin, inc, aim)
+            ap, an = O.align_surfaces(pts.reshape(n, -1, 4), nrm.reshape(n, -1, 4), ori)
+            blocking = None
+        else:
+            ori = O.motor_positions_to_orientations(kin, param)
+            ap, an = O.align_surfaces(pts0, nrm0, ori)
+            corners, spans, bn = O.blocking_primitives(ap)
+            blocking = dict(corners=corners, spans=spans, normals=bn, sample_to_blocker=owner)
+        flux, *_ = O.trace_rays(ap, an, inc, du, de, tidx, tg, RES, batch_size=min(64, n), blocking=blocking)
         total = O.bitmaps_per_target(flux, tidx, tg.n_total)
         loss = (total * total).mean()
         loss.backward()
-        if not first:   # outputs of the very first step (initial control points): the parity reference of the own arm
-            first.update(total=total.detach().clone(), grad=cp.grad.detach().clone(), du=du, de=de)
+        if not first:   # outputs of the very first step (initial parameters): the parity reference of the own arm
+            first.update(total=total.detach().clone(), grad=param.grad.detach().clone(), du=du, de=de)
         opt.step()
         return loss
 
@@ -282,23 +358,38 @@ def cpu_oracle_step_factory(n: int, threads: int):
     return step, n * p * RAYS
 
 
-def parity_against_cpu_step(dev: torch.device, first: dict) -> dict:
+def parity_against_cpu_step(dev: torch.device, first: dict, kind: str, first_crt: dict | None) -> dict:
     """The own arm on the CPU baseline's sample (same field, same distortion samples, first step): per-target flux and
-    control-point gradient against the oracle's - the 'flux max rel err' half of BASELINE.json's metric."""
+    parameter gradient against the oracle's - the 'flux max rel err' half of BASELINE.json's metric.  The GPU side is forced
+    onto the one-CTA-per-sample kernels the full field runs (AB200_FLAG_ONE_CTA_PER_SAMPLE), not the split-mode kernels a
+    48-heliostat slice would otherwise pick.  `first_crt` = the same oracle step with correctly rounded cos / sin
+    (oracle.correctly_rounded_trig): the reference's own sensitivity to the last bit of torch-CPU trig, reported beside."""
     from artist_b200 import ops
 
     n = first["du"].shape[0]
-    wl = Workload(dev, n, 1, 0)
+    wl = Workload(dev, n, 1, 0, kind=kind)
+    wl.tracer._force_one_cta_per_sample = True
     ds = wl.tracer.distortions_dataset
     ds.distortions_u, ds.distortions_e = first["du"].to(dev), first["de"].to(dev)
     wl.tracer._packed = ops.pack_distortions(ds.distortions_u, ds.distortions_e)
+    ops.trace_stats = torch.zeros(20, dtype=torch.int64, device=dev)
     wl.step()
-    total, grad = wl.last_total.detach().cpu(), wl.cp.grad.detach().cpu()
-    return {"flux_max_rel_err": float((total - first["total"]).abs().max() / first["total"].max()),
-            "grad_max_rel_err": float((grad - first["grad"]).abs().max() / first["grad"].abs().max()),
-            "sample": f"{n} heliostats of the bench field, first step, distortion samples of the CPU baseline step; "
-                      "per-target flux relative to its peak, control-point gradient relative to its largest entry; "
-                      "CPU side = oracle port (pinned bit-exact to the reference), GPU side = device trig + fixed-point bitmap"}
+    one_cta = int(ops.trace_stats[2]) == n
+    ops.trace_stats = None
+    total, grad = wl.last_total.detach().cpu(), wl.param.grad.detach().cpu()
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    out = {"flux_max_rel_err": rel(total, first["total"]), "grad_max_rel_err": rel(grad, first["grad"]),
+           "kernels": "one-CTA-per-sample (as the full field)" if one_cta else "split mode",
+           "sample": f"{n} heliostats of the bench field, first step, distortion samples of the CPU baseline step; "
+                     "per-target flux relative to its peak, parameter gradient relative to its largest entry; "
+                     "CPU side = oracle port (pinned bit-exact to the reference), GPU side = device trig + fixed-point bitmap"}
+    if first_crt:
+        out["vs_oracle_with_correctly_rounded_trig"] = {
+            "flux_max_rel_err": rel(total, first_crt["total"]), "grad_max_rel_err": rel(grad, first_crt["grad"]),
+            "oracle_own_shift": {"flux": rel(first_crt["total"], first["total"]), "grad": rel(first_crt["grad"], first["grad"])},
+            "note": "torch-CPU cos/sin (SLEEF) are not correctly rounded for ~8.6 % of sun-shape angles; the kernels' polynomial "
+                    "is; oracle_own_shift = how far that last bit alone moves the ORACLE"}
+    return out
 
 
 def run_reference(args) -> None:
@@ -306,7 +397,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    step, rays = cpu_oracle_step_factory(CPU_SAMPLE_HELIOSTATS, threads)
+    step, rays = cpu_oracle_step_factory(CPU_SAMPLE_HELIOSTATS, threads, args.workload)
     for _ in range(max(1, args.warmup)):
         step()
     t0 = time.perf_counter()
@@ -320,39 +411,95 @@ def run_reference(args) -> None:
     out = {
         "impl": "reference", "metric": "rays/s forward+backward", "value": value, "unit": "rays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus, note="bounded CPU sample, see cpu_baseline.sample"),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus, args.workload, args.scaling),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
 
 
-def workload_config(gpus: int, note: str | None = None) -> dict:
+def workload_config(gpus: int, kind: str = "surface", scaling: str = "weak") -> dict:
+    per = "per GPU" if scaling == "weak" else f"in ONE field split over {gpus} GPU(s) by the sampler contract"
+    if kind == "surface":
+        what = ("planar 8x8 m target, blocking off; step = NURBS eval + alignment + fused trace + per-target flux + loss + "
+                "backward to control points + Adam")
+    else:
+        what = ("tilted cylindrical receiver (r 4.14 m), blocking ON; step = motor positions -> orientations + fused trace + "
+                "per-target flux + loss + backward to the motor positions + Adam (BASELINE.json configs[4])")
     cfg = {
-        "workload": (f"synthetic Juelich-scale field, {N_HELIOSTATS} heliostats per GPU x 4 facets x "
-                     f"{POINTS_PER_FACET[0]}x{POINTS_PER_FACET[1]} surface points x {RAYS} rays, planar 8x8 m target, "
-                     f"bitmap {RES[0]}x{RES[1]}, blocking off; step = NURBS eval + alignment + fused trace + "
-                     "per-target flux + loss + backward to control points + Adam"),
-        "heliostats_per_gpu": N_HELIOSTATS, "surface_points": 4 * POINTS_PER_FACET[0] * POINTS_PER_FACET[1], "rays_per_point": RAYS,
-        "bitmap": list(RES), "control_points": list(CONTROL_POINTS), "parallelism": f"heliostat-sharded x{gpus}, NCCL all-reduce of the [T,U,E] flux",
+        "workload": (f"synthetic Juelich-scale field, {N_HELIOSTATS} heliostats {per} x 4 facets x "
+                     f"{POINTS_PER_FACET[0]}x{POINTS_PER_FACET[1]} surface points x {RAYS} rays, bitmap {RES[0]}x{RES[1]}, {what}"),
+        "heliostats_per_gpu": N_HELIOSTATS if scaling == "weak" else N_HELIOSTATS / gpus,
+        "surface_points": 4 * POINTS_PER_FACET[0] * POINTS_PER_FACET[1], "rays_per_point": RAYS,
+        "bitmap": list(RES), "control_points": list(CONTROL_POINTS),
+        "parallelism": (f"heliostat-sharded x{gpus}, NCCL all-reduce of the [T,U,E] flux" if scaling == "weak" else
+                        f"one field, samples h -> rank h % {gpus} (HeliostatRayTracer(world_size, rank)), NCCL all-reduce of the "
+                        "[T,U,E] flux and of the replicated parameters' gradient; NURBS + alignment replicated per rank as in "
+                        "the reference"),
         "l2_policy": "inputs larger than L2 (2.9 GB of distortions/points/normals per step per GPU vs 126 MB L2)",
         "trig": "polynomial sin/cos (<= 1 ulp), FMA-free coordinate path", "accumulate": "fixed-point (deterministic)",
         "alignment": "fused into the trace kernels (orientation applied per point; aligned [N,P,4] tensors never materialised)",
     }
-    if note:
-        cfg["note"] = note
     return cfg
+
+
+def verify_reduced_flux(wl: "Workload", dev: torch.device, world: int, rank: int, n: int, kind: str, strong: bool) -> dict | None:
+    """N > 1, before the timed region, initial parameters: the NCCL-reduced per-target flux and rank 0's parameter gradient
+    against a single-process replay on rank 0 (every rank's part traced one after the other, summed in rank order)."""
+    wl.opt.zero_grad(set_to_none=True)
+    local = wl.forward_local()
+    import torch.distributed.nn.functional as dist_fn
+
+    total = dist_fn.all_reduce(local)
+    (total * total).mean().backward()
+    if strong:
+        torch.distributed.all_reduce(wl.param.grad)
+    got_total, got_grad = total.detach().clone(), wl.param.grad.detach().clone()
+    wl.opt.zero_grad(set_to_none=True)
+    out = None
+    if rank == 0:
+        wl.opt.zero_grad(set_to_none=True)
+        mine = wl.forward_local()
+        others, grads = [], []
+        for r in range(1, world):
+            other = Workload(dev, n, world, r, kind=kind, strong=strong)
+            part = other.forward_local()
+            others.append(part)
+            grads.append(other)
+        total1 = mine
+        for part in others:
+            total1 = total1 + (part if strong else part.detach())
+        (total1 * total1).mean().backward()
+        want_grad = wl.param.grad.detach().clone()
+        if strong:      # replicated parameters: sum of the per-rank gradients
+            for other in grads:
+                want_grad += other.param.grad
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        out = {"flux_max_rel_err": rel(got_total, total1.detach()), "grad_max_rel_err": rel(got_grad, want_grad),
+               "what": f"all-reduced [T,U,E] flux over {world} ranks and rank 0's parameter gradient vs a one-process replay of "
+                       "every rank's part on rank 0 (same seeds, initial parameters), relative to the peak / largest entry"}
+        wl.opt.zero_grad(set_to_none=True)
+        del others, grads
+        torch.cuda.empty_cache()
+    torch.distributed.barrier()
+    return out
 
 
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--heliostats", type=int, default=None, help="override heliostats per GPU (debug)")
+    ap.add_argument("--workload", default="surface", choices=["surface", "motor"],
+                    help="surface = headline (control-point gradients, planar target); motor = BASELINE.json configs[4] "
+                         "(motor-position gradients, cylindrical receiver, blocking on)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak = one field per GPU; strong = ONE field split over the ranks by the sampler contract")
+    ap.add_argument("--heliostats", type=int, default=None, help="override heliostats per GPU / per field (debug)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-verify", action="store_true", help="N > 1: skip the one-process replay of the reduced flux")
     args = ap.parse_args()
     global N_HELIOSTATS
     if args.heliostats:
@@ -370,13 +517,17 @@ def main() -> None:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     distributed = world > 1
+    strong = args.scaling == "strong"
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if distributed:
         torch.distributed.init_process_group(backend="nccl", init_method="env://", device_id=dev)
     warmup = max(3, args.warmup)
 
-    wl = Workload(dev, N_HELIOSTATS, world, rank)
+    wl = Workload(dev, N_HELIOSTATS, world, rank, kind=args.workload, strong=strong)
+    verify = None
+    if distributed and not args.skip_verify:
+        verify = verify_reduced_flux(wl, dev, world, rank, N_HELIOSTATS, args.workload, strong)
     for _ in range(warmup):
         wl.step()
     # --- device-resident timed region (value) with per-kernel CUDA-event timing and clock sampling ---
@@ -394,27 +545,36 @@ def main() -> None:
     # --- end-to-end leg (host buffers) ---
     for _ in range(2):
         wl.step_e2e()
-    ms_e2e = timed_loop(wl.step_e2e, args.steps, dev, distributed)
+    wl.flush_e2e()
+    ms_e2e = timed_loop(wl.step_e2e, args.steps, dev, distributed, finish=wl.flush_e2e)
+    rays = torch.tensor([float(wl.rays_per_step)], device=dev)
+    if distributed:
+        torch.distributed.all_reduce(rays)
 
     if rank == 0:
-        rays_total = wl.rays_per_step * world
+        rays_total = float(rays.item())
         value = rays_total / (ms_step * 1e-3)
         e2e_value = rays_total / (ms_e2e * 1e-3)
         h2d, d2h = wl.e2e_bytes
         peak, peak_src = measured_peak_hbm()
         bf, bb = bytes_per_ray(RAYS, wl.p, RES[0] * RES[1])
+        if args.workload == "motor":    # no surface gradients are written: 8 + 32/R + bitmap
+            bb = bf
         dom = max(("ab200_trace_fwd", "ab200_trace_bwd"), key=lambda k: kern_ms.get(k, 0.0))
         bpr = bf if dom == "ab200_trace_fwd" else bb
         achieved = wl.rays_per_step * bpr / (kern_ms[dom] * 1e-3) / 1e9
+        step_bytes = wl.rays_per_step * (bf + bb)
         out = {
             "metric": "rays/s forward+backward", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world, args.workload, args.scaling),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e,
-                    "note": "control points, incident directions and target indices uploaded from pinned host memory every "
-                            "step; per-target flux, loss and control-point gradient read back; distortion samples are the "
-                            "tracer's seeded device state (as in the reference, which samples them on the device)"},
+                    "note": "every step uploads its parameters, incident directions and target indices from pinned host memory "
+                            "and downloads its per-target flux, loss and parameter gradient; uploads and downloads run on two "
+                            "copy streams and overlap the kernels of the step in flight (double-buffered; the host holds step "
+                            "i-1's results when step i has been issued); distortion samples are the tracer's seeded device "
+                            "state (as in the reference, which samples them on the device)"},
             "gpu_launches": int(launches),
             "kernel_ms": {k: round(v, 4) for k, v in sorted(kern_ms.items())},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -423,24 +583,32 @@ def main() -> None:
                                          "profiles/trace_traffic.json)",
                          "algorithmic_bytes_per_launch": wl.rays_per_step * bpr, "peak_source": peak_src,
                          "bytes_per_ray": bpr, "rays_per_launch": wl.rays_per_step,
-                         "fwd_bwd_trace_frac": (wl.rays_per_step * (bf + bb) / ((kern_ms["ab200_trace_fwd"] + kern_ms["ab200_trace_bwd"]) * 1e-3) / 1e9) / peak},
+                         "fwd_bwd_trace_frac": (step_bytes / ((kern_ms["ab200_trace_fwd"] + kern_ms["ab200_trace_bwd"]) * 1e-3) / 1e9) / peak,
+                         "whole_step_frac": (step_bytes / (ms_step * 1e-3) / 1e9) / peak},
             "clocks": clocks,
         }
         second = issue_roof(dom, wl.rays_per_step, kern_ms[dom], (clocks or {}).get("sm_mhz"))
         if second is not None:
             out["roofline"]["second_roof"] = second
+        if verify is not None:
+            out["multi_gpu_check"] = verify
         if world == 1 and not args.skip_cpu_baseline:
+            from oracle import artist_oracle as O
+
             threads = os.cpu_count() or 1
-            step, rays = cpu_oracle_step_factory(CPU_SAMPLE_HELIOSTATS, threads)
+            step, rays_cpu = cpu_oracle_step_factory(CPU_SAMPLE_HELIOSTATS, threads, args.workload)
             step()
             t0 = time.perf_counter()
             reps = 2
             for _ in range(reps):
                 step()
             dt = (time.perf_counter() - t0) / reps
-            out["parity"] = parity_against_cpu_step(dev, step.first)
-            out["cpu_baseline"] = {"value": rays / dt, "unit": "rays/s", "cores": threads, "kind": "port",
-                                   "sample": f"{CPU_SAMPLE_HELIOSTATS} heliostats ({rays} rays) of the same field per step, "
+            with O.correctly_rounded_trig():
+                step_crt, _ = cpu_oracle_step_factory(CPU_SAMPLE_HELIOSTATS, threads, args.workload)
+                step_crt()
+            out["parity"] = parity_against_cpu_step(dev, step.first, args.workload, step_crt.first)
+            out["cpu_baseline"] = {"value": rays_cpu / dt, "unit": "rays/s", "cores": threads, "kind": "port",
+                                   "sample": f"{CPU_SAMPLE_HELIOSTATS} heliostats ({rays_cpu} rays) of the same field per step, "
                                              f"{reps} timed steps after 1 warm-up, torch CPU oracle port with {threads} threads"}
         print(json.dumps(out), flush=True)
     if distributed:

@@ -40,6 +40,9 @@ extern "C" {
 /* flags */
 #define AB200_FLAG_FP32_ACCUM 1 /* accumulate the bitmap with fp32 shared-memory atomics instead of the
                                    deterministic fixed-point histogram (order-dependent rounding) */
+#define AB200_FLAG_ONE_CTA_PER_SAMPLE 2 /* run the one-CTA-per-sample kernels (normally chosen when n_local >= 2 x SM count)
+                                           whatever the sample count: lets a small case exercise the kernels a full field
+                                           runs (parity tests, bench.py's parity leg) */
 
 /* Target-area SoA tensors: artist/field/tower_target_areas_planar.py:45-74 and
  * tower_target_areas_cylindrical.py:56-102. */
