@@ -229,6 +229,7 @@ class Workload:
             # replicated parameters, each rank holds the gradient of its own samples (SurfaceReconstructor reduces the
             # same way, artist/optim/surface_reconstructor.py:766-777)
             torch.distributed.all_reduce(self.param.grad)
+            self.param.grad /= self.world
         self.opt.step()
         self.last_total = total
         return loss
@@ -475,10 +476,15 @@ def verify_reduced_flux(wl: "Workload", dev: torch.device, world: int, rank: int
         if strong:      # replicated parameters: sum of the per-rank gradients
             for other in grads:
                 want_grad += other.param.grad
+        # the autograd-aware all-reduce sums the ranks' (identical) upstream gradients too: every rank's parameter gradient
+        # is world x the one-process gradient (the reference divides by the world size after its reduction,
+        # artist/optim/surface_reconstructor.py:777)
+        want_grad = want_grad * world
         rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
         out = {"flux_max_rel_err": rel(got_total, total1.detach()), "grad_max_rel_err": rel(got_grad, want_grad),
                "what": f"all-reduced [T,U,E] flux over {world} ranks and rank 0's parameter gradient vs a one-process replay of "
-                       "every rank's part on rank 0 (same seeds, initial parameters), relative to the peak / largest entry"}
+                       "every rank's part on rank 0 (same seeds, initial parameters; gradient x world, the all-reduce's autograd "
+                       "rule), relative to the peak / largest entry"}
         wl.opt.zero_grad(set_to_none=True)
         del others, grads
         torch.cuda.empty_cache()
