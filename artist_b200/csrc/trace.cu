@@ -1982,7 +1982,10 @@ static int max_window_bytes(bool blocking) {
 static LaunchPlan make_plan(int n_local, int n_points, int max_threads_large, bool force_large = false, bool blocking = false) {
     LaunchPlan pl;
     const int sms = sm_count();
-    if (n_local >= 2 * sms || force_large) {
+    // one CTA per sample from half a wave of samples on: measured on a B200 (bench field, 10^4 points x 10 rays), forward /
+    // backward ms with several CTAs per sample vs one: 64 samples 0.084 / 0.103 vs 0.079 / 0.097, 148: 0.124 / 0.160 vs
+    // 0.086 / 0.102, 256: 0.208 / 0.293 vs 0.152 / 0.188 (profiles/r02_mode_threshold.txt)
+    if (2 * n_local >= sms || force_large) {
         pl.threads = max_threads_large; pl.split = 1;
         pl.smem_bytes = AB200_WIN_KB * 1024 < max_window_bytes(blocking) ? AB200_WIN_KB * 1024 : max_window_bytes(blocking);
     } else {

@@ -182,6 +182,8 @@ class Workload:
         self.tracer = HeliostatRayTracer(self.scenario, g, blocking_active=(kind == "motor"), random_seed=tracer_seed,
                                          world_size=world if strong else 1, rank=rank if strong else 0,
                                          bitmap_resolution=torch.tensor(RES))
+        if os.environ.get("AB200_FORCE_ONE_CTA") == "1":     # tuning: the one-CTA-per-sample kernels whatever the sample count
+            self.tracer._force_one_cta_per_sample = True
         self.opt = torch.optim.Adam([self.param], lr=1e-6 if kind == "surface" else 1e-3, fused=True)
         self.p = g.surface_points.shape[1]
         self.n_local = len(self.tracer.distortions_sampler.rank_indices)

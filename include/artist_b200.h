@@ -40,7 +40,7 @@ extern "C" {
 /* flags */
 #define AB200_FLAG_FP32_ACCUM 1 /* accumulate the bitmap with fp32 shared-memory atomics instead of the
                                    deterministic fixed-point histogram (order-dependent rounding) */
-#define AB200_FLAG_ONE_CTA_PER_SAMPLE 2 /* run the one-CTA-per-sample kernels (normally chosen when n_local >= 2 x SM count)
+#define AB200_FLAG_ONE_CTA_PER_SAMPLE 2 /* run the one-CTA-per-sample kernels (normally chosen when 2 x n_local >= SM count)
                                            whatever the sample count: lets a small case exercise the kernels a full field
                                            runs (parity tests, bench.py's parity leg) */
 
@@ -344,7 +344,8 @@ int32_t ab200_flux_loss_bwd(const float* prediction, const float* ground_truth, 
  * ab200_trace_host - end-to-end convenience entry with HOST buffers: uploads the per-call inputs
  * (incident directions, target indices, aligned points/normals if given on the host), traces,
  * and downloads the per-target bitmaps.  Device scratch is supplied by the caller.
- * Used by bench.py's e2e leg; see INTEGRATION.md.
+ * Synchronises `stream` before it returns.  Exercised by tests/test_gpu_trace_parity.py (bit-identical to the
+ * device-pointer path); bench.py's e2e leg goes through the class API with pinned torch tensors instead.
  */
 typedef struct ab200_host_trace_args {
     ab200_trace_args dev;            /* device-side argument block; points/normals/incident/target_idx are

@@ -321,3 +321,46 @@ def test_one_cta_per_sample_mode_at_bench_scale_equals_split_mode():
         scale = gb.abs().max()
         assert scale > 0, name
         assert (ga - gb).abs().max() <= 2e-5 * scale, f"{name}: {(ga - gb).abs().max() / scale:.2e}"
+
+
+def test_host_buffer_entry_point_matches_the_device_path():
+    """``ab200_trace_host`` (include/artist_b200.h): surfaces, incident directions and target indices come from HOST
+    memory, the per-target bitmaps and the three factors go back to HOST memory - bit-identical to ``ops.trace`` +
+    ``ops.bitmaps_per_target`` on device tensors, and within 1e-4 of the oracle's peak."""
+    import ctypes as C
+
+    from artist_b200 import _lib, ops
+
+    dev = torch.device("cuda:0")
+    case = cases.make_case(n=5, points_per_facet=(12, 12), rays=6, target_pattern=(0, 1))
+    res = (64, 48)
+    tg = _dev_targets(case["targets"], dev)
+    opt = ops.TraceOptions(res_e=res[0], res_u=res[1], scatter_sigma=(4.3681e-06) ** 0.5)
+    dist = ops.pack_distortions(case["dist_u"].to(dev), case["dist_e"].to(dev))
+    n, p, _ = case["points"].shape
+    n_t = tg.n_planar + tg.n_cyl
+    flux, ic, ot, bl = ops.trace(case["points"].to(dev), case["normals"].to(dev), case["incident"].to(dev), dist,
+                                 case["target_idx"].to(dev), tg, opt)
+    per_target = ops.bitmaps_per_target(flux, case["target_idx"].to(dev), n_t)
+    # host side: pinned inputs and outputs, device scratch supplied by the caller
+    h_pts, h_nrm = case["points"].float().contiguous().pin_memory(), case["normals"].float().contiguous().pin_memory()
+    h_inc, h_tidx = case["incident"].float().contiguous().pin_memory(), case["target_idx"].to(torch.int32).contiguous().pin_memory()
+    h_out = torch.empty(n_t, res[1], res[0]).pin_memory()
+    h_fac = torch.empty(3, n).pin_memory()
+    d_pts, d_nrm = torch.empty(n, p, 4, device=dev), torch.empty(n, p, 4, device=dev)
+    d_inc, d_tidx = torch.empty(n, 4, device=dev), torch.empty(n, dtype=torch.int32, device=dev)
+    d_flux, d_fac = torch.empty(n, res[1], res[0], device=dev), [torch.empty(n, device=dev) for _ in range(3)]
+    d_targets = torch.empty(n_t, res[1], res[0], device=dev)
+    h = _lib.HostTraceArgs()
+    h.dev = ops._trace_args(d_pts, d_nrm, d_inc, dist, None, d_tidx, tg, opt, None, d_flux, *d_fac)
+    fp = lambda t: t.data_ptr()                     # the binding takes raw addresses
+    h.h_points, h.h_normals, h.h_incident = fp(h_pts), fp(h_nrm), fp(h_inc)
+    h.h_target_idx = fp(h_tidx)
+    h.d_target_bitmaps, h.h_target_bitmaps, h.h_factors = fp(d_targets), fp(h_out), fp(h_fac)
+    _lib.call("ab200_trace_host", C.byref(h), ops._stream())       # synchronises its stream before returning
+    assert torch.equal(h_out, per_target.cpu())
+    assert torch.equal(h_fac[0], ic.cpu()) and torch.equal(h_fac[1], ot.cpu()) and torch.equal(h_fac[2], bl.cpu())
+    ref, *_ = O.trace_rays(case["points"], case["normals"], case["incident"], case["dist_u"], case["dist_e"],
+                           case["target_idx"], case["targets"], res)
+    want = O.bitmaps_per_target(ref, case["target_idx"], n_t)
+    assert (h_out - want).abs().max() <= 1e-4 * want.max()
