@@ -251,7 +251,8 @@ __global__ void kinematics_bwd_kernel(const ab200_kinematics_args k, const float
     }
 }
 
-// ---- inverse kinematics + fixed-point alignment (one CTA, loops over heliostats) ------------------
+// ---- inverse kinematics + fixed-point alignment (2 x max_iterations small multi-block launches; the convergence vote
+// of all heliostats stays on the device, no host sync) ------------------
 __device__ inline void motor_from_normal(const ab200_kinematics_args& k, int i, const float* nrm /*3*/, float* motor_out) {
     const float eps = 1e-8f;
     const float* rd = k.rotation_dev + (size_t)i * 4;

@@ -15,7 +15,28 @@ from . import _lib
 from ._lib import ABI_VERSION
 
 
+_warned_no_graph: set = set()
+
+
+def warn_no_graph(what: str, hint: str = "") -> None:
+    """One warning per call site: an input requires grad but this step returns tensors without an autograd graph."""
+    if what in _warned_no_graph:
+        return
+    _warned_no_graph.add(what)
+    import warnings
+
+    warnings.warn(f"artist_b200: {what} is forward-only here (its inputs require grad, the result carries no autograd graph); "
+                  f"gradients flow through HeliostatRayTracer.trace_rays / the fused ops instead. {hint}", stacklevel=3)
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """Handle of torch's current CUDA stream (the raw getter is ~20x cheaper than building a ``torch.cuda.Stream`` object:
+    at small sample counts the step is bound by host time, tools/host_profile.py)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -857,7 +878,13 @@ def kinematics_orientations(motor, rot_dev, trans_dev, act_opt, positions, act_n
 
 def kinematics_align_incident(incident, aim_points, rot_dev, trans_dev, act_opt, positions, act_non_opt, offset,
                               linear: bool, max_iterations: int = 4, min_eps: float = 1e-4):
-    """Forward-only (the reference never differentiates through this loop)."""
+    """Forward-only: the orientations carry no autograd graph.  The reference's loop IS differentiable w.r.t. the kinematic
+    deviations and actuator parameters (``kinematics_rigid_body.py:540-634``) although none of its callers uses that; a
+    caller who does gets a warning here instead of silently missing gradients - ``kinematics_orientations`` on the
+    converged motor positions (``RigidBody.motor_positions_to_orientations``) is the differentiable route."""
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (rot_dev, trans_dev, act_opt)):
+        warn_no_graph("incident_ray_directions_to_orientations",
+                      "align with motor_positions_to_orientations(kinematics.active_motor_positions) for gradients")
     with torch.no_grad():
         incident, aim_points = _f32(incident, "incident"), _f32(aim_points, "aim_points")
         rot_dev, trans_dev = _f32(rot_dev.detach(), "rotation_deviation"), _f32(trans_dev.detach(), "translation_deviation")

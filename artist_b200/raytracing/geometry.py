@@ -15,8 +15,17 @@ from .. import _lib, ops
 from ..scene.rays import Rays
 
 
+def _warn_if_grad(what: str, *tensors) -> None:
+    """The reference's step functions are differentiable; these stand-alone forms are forward-only (API parity and
+    step-wise checks - the differentiable path is the fused ``trace_rays``).  Say so once instead of silently dropping
+    the graph."""
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in tensors):
+        ops.warn_no_graph(what)
+
+
 def reflect(incident_ray_directions: torch.Tensor, reflection_surface_normals: torch.Tensor) -> torch.Tensor:
     """``r = i - 2 (i . n) n`` (``geometry.py:11-41``): incident ``[N,1,4]``, normals ``[N,P,4]`` -> ``[N,P,4]``."""
+    _warn_if_grad("reflect", incident_ray_directions, reflection_surface_normals)
     normals = ops._f32(reflection_surface_normals.detach(), "reflection_surface_normals")
     n, p, _ = normals.shape
     incident = ops._f32(incident_ray_directions.detach().expand(n, 1, 4).reshape(n, 4), "incident_ray_directions")
@@ -27,6 +36,8 @@ def reflect(incident_ray_directions: torch.Tensor, reflection_surface_normals: t
 
 def _intersections(rays: Rays, points_at_ray_origins, targets: ops.TargetTensors, target_area_indices, bitmap_resolution,
                    cylindrical: bool):
+    _warn_if_grad("line_cylinder_intersections" if cylindrical else "line_plane_intersections", rays.ray_directions,
+                  rays.ray_magnitudes, points_at_ray_origins)
     dirs = ops._f32(rays.ray_directions.detach(), "ray_directions")
     mags = ops._f32(rays.ray_magnitudes.detach(), "ray_magnitudes")
     origins = ops._f32(points_at_ray_origins.detach(), "points_at_ray_origins")
@@ -74,6 +85,7 @@ def bilinear_splatting(bitmap_intersections_e: torch.Tensor, bitmap_intersection
                        absolute_intensities: torch.Tensor, bitmap_resolution) -> torch.Tensor:
     """``heliostat_ray_tracer.py:610-778``: three ``[N,...]`` tensors -> flux bitmaps ``[N,U,E]``."""
     n = absolute_intensities.shape[0]
+    _warn_if_grad("bilinear_splatting", bitmap_intersections_e, bitmap_intersections_u, absolute_intensities)
     be = ops._f32(bitmap_intersections_e.detach().reshape(n, -1), "bitmap_intersections_e")
     bu = ops._f32(bitmap_intersections_u.detach().reshape(n, -1), "bitmap_intersections_u")
     v = ops._f32(absolute_intensities.detach().reshape(n, -1), "absolute_intensities")

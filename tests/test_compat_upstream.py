@@ -12,6 +12,21 @@ from tools.ref_import import import_reference, reference_available
 pytestmark = pytest.mark.skipif(not reference_available(), reason="upstream package not present (GPU box)")
 
 
+@pytest.fixture(autouse=True)
+def _leave_no_trace():
+    """The upstream tree has its own top-level ``tests`` package: take it off ``sys.path`` again (spawned workers of later
+    tests inherit the path) and drop the imported upstream modules."""
+    import sys
+
+    from tools import ref_import
+
+    path_before = list(sys.path)
+    yield
+    sys.path[:] = [p for p in path_before if p != ref_import.REFERENCE_ROOT]
+    for name in [m for m in sys.modules if m == "artist" or m.startswith("artist.")]:
+        del sys.modules[name]
+
+
 def test_install_rebinds_the_callers_bindings_and_uninstall_restores_them():
     import_reference()
     import artist.optim.aim_point_optimizer as apo
