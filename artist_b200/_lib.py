@@ -56,7 +56,7 @@ class TraceArgs(C.Structure):
 class TraceBwdArgs(C.Structure):
     _fields_ = [("fwd", TraceArgs), ("grad_flux", c_float_p), ("grad_flux_stride", C.c_int64),
                 ("grad_points", c_float_p), ("grad_normals", c_float_p), ("grad_prims", c_float_p),
-                ("grad_orientations", c_float_p)]
+                ("grad_orientations", c_float_p), ("grad_prims_scratch", c_float_p), ("grad_prims_scratch_floats", C.c_int64)]
 
 
 class NurbsArgs(C.Structure):

@@ -275,9 +275,13 @@ struct BlockBack {
     float blocked, go0, go1, go2, gd0, gd1, gd2;
 };
 
-static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, const int* cand_rows, unsigned long long mask,
+// `gacc` (shared, may be NULL): the CTA's accumulators of d/d(corner0, span_u, span_v, normal) per candidate SLOT
+// ([n_cand][12] doubles; double so that the order of the adds - the one order-dependent step - practically never reaches
+// the float the sums are rounded to).
+static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, unsigned long long mask,
                                                  const BlockParams bp, float o0, float o1, float o2, float d0, float d1,
-                                                 float d2, float g_blocked_scale /* dL/dblocked */, float* grad_prims) {
+                                                 float d2, float g_blocked_scale /* dL/dblocked */, double* gacc,
+                                                 int gacc_copies, int gacc_stride) {
     float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f};
     BlockBack out;
     // first pass: optical depth (cheap rectangle coordinates; the candidates that matter are remembered)
@@ -339,17 +343,20 @@ static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, 
             go[q] += g_off[q] - g_t * p.n[q] * iden;
             gd[q] += g.t * g_off[q] - g_t * g.t * p.n[q] * iden;
         }
-        if (grad_prims) {
-            float* gp = grad_prims + (size_t)cand_rows[c] * 12;
+        if (gacc) {
+            // `gacc` holds `gacc_copies` interleaved copies of the [n_slots][12] accumulators (the 64 x 12 cells are shared out
+            // among as many copies as fit): threads spread over the copies, because every band ray of a CTA adds to the same
+            // dozen cells and shared-memory double adds are compare-and-swap loops
+            double* gp = gacc + ((threadIdx.x ^ (threadIdx.x >> 5)) & (gacc_copies - 1)) * gacc_stride + c * 12;
             const float g_vv = g_u * pu * idet, g_uu = g_v * pv * idet, g_det = -(g_u * g.u + g_v * g.v) * idet;
             const float g_uv = -(g_u * pv + g_v * pu) * idet - 2.0f * p.uv * g_det;
             const float g_uu2 = g_uu + g_det * p.vv, g_vv2 = g_vv + g_det * p.uu;
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                atomicAdd(gp + q, -g_off[q] + g_t * p.n[q] * iden);                                   // corner 0
-                atomicAdd(gp + 3 + q, g_pu * g.off[q] + 2.0f * g_uu2 * p.su[q] + g_uv * p.sv[q]);      // span u
-                atomicAdd(gp + 6 + q, g_pv * g.off[q] + 2.0f * g_vv2 * p.sv[q] + g_uv * p.su[q]);      // span v
-                atomicAdd(gp + 9 + q, -g_t * g.off[q] * iden);                                        // normal
+                atomicAdd(gp + q, (double)(-g_off[q] + g_t * p.n[q] * iden));                                   // corner 0
+                atomicAdd(gp + 3 + q, (double)(g_pu * g.off[q] + 2.0f * g_uu2 * p.su[q] + g_uv * p.sv[q]));      // span u
+                atomicAdd(gp + 6 + q, (double)(g_pv * g.off[q] + 2.0f * g_vv2 * p.sv[q] + g_uv * p.su[q]));      // span v
+                atomicAdd(gp + 9 + q, (double)(-g_t * g.off[q] * iden));                                        // normal
             }
             (void)dv;
         }

@@ -603,13 +603,25 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     const int n_pairs = (R + 1) >> 1;
     const long long step_inner = 2 * (long long)P, step_last = (long long)THREADS - (long long)(n_pairs - 1) * 2 * (long long)P;
 
-    int p = p_begin + tid;
+    // BLK instantiation = pass 2 of a blocking trace: the points are the recorded (shadow-edge) ones, looked up in the
+    // deferral list `dc` instead of walked round-robin; everything else is the same software pipeline
+    int it = tid;
+    const int n_items = BLK ? dc->count : 0;
+    int p = BLK ? (it < n_items ? p_begin + defer_lookup(*dc, it) : p_end) : p_begin + tid;
+    int pn = 0;
     float2 da = make_float2(0.f, 0.f), db = da;
     const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
     if (p < p_end) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
-    for (; p < p_end; p += THREADS) {
-        const int pn = p + THREADS;
-        const bool more = pn < p_end;
+    for (; p < p_end; p = pn) {
+        bool more;
+        if (BLK) {
+            it += THREADS;
+            more = it < n_items;
+            pn = more ? p_begin + defer_lookup(*dc, it) : p_end;
+        } else {
+            pn = p + THREADS;
+            more = pn < p_end;
+        }
         if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
         else if (tid * kWindowSampleStride < P && src.next && src.next[0]) {
             prefetch_l2(src.next[0] + tid * kWindowSampleStride); prefetch_l2(src.next[1] + tid * kWindowSampleStride);
@@ -622,7 +634,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
         }
         if (!point_regular(pc)) {   // never with physical inputs: the generic loop re-traces the whole point
             any_irr = true;
-            nx += THREADS;
+            if (BLK) nx = dist + pn; else nx += THREADS;
             if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
             continue;
         }
@@ -644,7 +656,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             const float2 d0 = da, d1 = db;
             {
                 const bool inner = r + 2 < R;
-                nx += inner ? step_inner : step_last;
+                if (BLK) nx = inner ? nx + step_inner : dist + pn; else nx += inner ? step_inner : step_last;
                 if (inner || more) {
                     da = __ldcs(nx);
                     if (REVEN || (inner ? (r + 3 < R) : (R > 1))) db = __ldcs(nx + P);
@@ -990,6 +1002,22 @@ trace_fwd_kernel(const TraceParams prm) {
             if (prm.a.stats && tid == 0) atomicAdd(reinterpret_cast<unsigned long long*>(prm.a.stats) + 17, (unsigned long long)dc.count);
             int c1 = 0, c2 = 0, c3 = 0;
             bool fb = false;
+#if AB200_PACKED_RAYS
+            if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF && (FP32ACC || prm.fx_scale >= 1e-6f)) {
+                // the packed loop with the per-ray classification inline, over the recorded points only
+                int n_irr = 0;
+                if ((R & 1) == 0)
+                    fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb, n_irr, &dc);
+                else
+                    fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, BLK, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb, n_irr, &dc);
+                if (__syncthreads_or(n_irr != 0)) {   // never with physical inputs
+                    int d1 = 0, d2 = 0, d3 = 0;
+                    bool fb2 = false;
+                    fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, true, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, d1, d2, d3, fb2, &dc, kDeferList);
+                    c1 += d1; c2 += d2; c3 += d3; fb = fb || fb2;
+                }
+            } else
+#endif
             if (T.planar)
                 fwd_rays<THREADS, TRIG, DBG, FP32ACC, true, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, c1, c2, c3, fb, &dc, kDeferList);
             else
@@ -1183,7 +1211,8 @@ struct BwdCtx {
     const int* blk_rows;  // shared: their rows in the primitive table
     int n_blk;
     BlockParams bp;
-    float* grad_prims;
+    double* gacc;         // shared: the CTA's blocker-gradient accumulators per candidate slot (NULL: not wanted)
+    int gacc_copies, gacc_stride;   // ... as `gacc_copies` (a power of two) copies, `gacc_stride` doubles apart
 };
 
 template <int THREADS, int TRIG, bool PLANAR, bool FASTDIV, bool ONLY_IRREGULAR, bool BLK>
@@ -1266,8 +1295,8 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
             float gdb0 = 0.f, gdb1 = 0.f, gdb2 = 0.f;
             float unblocked = 1.0f;
             if (BLK && bcls == 2) {   // intensity = lambert * (1 - blocked) * k_or
-                const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
-                                                    -g_int0 * hit.lam * k_or, bc.grad_prims);
+                const BlockBack bb = block_backward(bc.blk, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
+                                                    -g_int0 * hit.lam * k_or, bc.gacc, bc.gacc_copies, bc.gacc_stride);
                 unblocked = 1.0f - bb.blocked;
                 gow0 += bb.go0; gow1 += bb.go1; gow2 += bb.go2;
                 gdb0 = bb.gd0; gdb1 = bb.gd1; gdb2 = bb.gd2;
@@ -1437,8 +1466,8 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
                 float inten = -a * k_lam;
                 float gdb0 = 0.f, gdb1 = 0.f, gdb2 = 0.f;
                 if (BLK && bcls == 2) {   // intensity = lambert * (1 - blocked) * k_or  (rare: rays inside a sigmoid transition)
-                    const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
-                                                        -g_int * inten, bc.grad_prims);
+                    const BlockBack bb = block_backward(bc.blk, bmask, bc.bp, pc.o0, pc.o1, pc.o2, s.dx, s.dy, s.dz,
+                                                        -g_int * inten, bc.gacc, bc.gacc_copies, bc.gacc_stride);
                     go0 += bb.go0; go1 += bb.go1; go2 += bb.go2;
                     gdb0 = bb.gd0; gdb1 = bb.gd1; gdb2 = bb.gd2;
                     g_int *= 1.0f - bb.blocked;
@@ -1627,9 +1656,9 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
 #pragma unroll
                     for (int lane = 0; lane < 2; ++lane) {
                         if (!(lane ? live1 : live0) || (lane ? bcls1 : bcls0) != 2) continue;
-                        const BlockBack bb = block_backward(bc.blk, bc.blk_rows, bmask, bc.bp, pc.o0, pc.o1, pc.o2,
+                        const BlockBack bb = block_backward(bc.blk, bmask, bc.bp, pc.o0, pc.o1, pc.o2,
                                                             lane ? dx.y : dx.x, lane ? dy_keep.y : dy_keep.x, lane ? dz.y : dz.x,
-                                                            -(lane ? g_int.y : g_int.x) * (lane ? inten.y : inten.x), bc.grad_prims);
+                                                            -(lane ? g_int.y : g_int.x) * (lane ? inten.y : inten.x), bc.gacc, bc.gacc_copies, bc.gacc_stride);
                         if (lane) { go0.y += bb.go0; go1.y += bb.go1; go2.y += bb.go2; gdb0.y = bb.gd0; gdb1.y = bb.gd1; gdb2.y = bb.gd2; unblocked.y = 1.0f - bb.blocked; }
                         else      { go0.x += bb.go0; go1.x += bb.go1; go2.x += bb.go2; gdb0.x = bb.gd0; gdb1.x = bb.gd1; gdb2.x = bb.gd2; unblocked.x = 1.0f - bb.blocked; }
                     }
@@ -1684,13 +1713,24 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                             dc == nullptr;   // (a deferring pass records whole points)
     const int p_end_main = split_tail ? p_begin + n_full : p_end;
 
-    int p = p_begin + tid;
+    // BLK instantiation = pass 2 of a blocking trace over the deferral list `dc` (see fwd_rays_planar_fast2)
+    int it = tid;
+    const int n_items = BLK ? dc->count : 0;
+    int p = BLK ? (it < n_items ? p_begin + defer_lookup(*dc, it) : p_end_main) : p_begin + tid;
+    int pn = 0;
     float2 da = zero2, db = zero2;
     const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
     if (p < p_end_main) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
-    for (; p < p_end_main; p += THREADS) {
-        const int pn = p + THREADS;
-        const bool more = pn < p_end_main;
+    for (; p < p_end_main; p = pn) {
+        bool more;
+        if (BLK) {
+            it += THREADS;
+            more = it < n_items;
+            pn = more ? p_begin + defer_lookup(*dc, it) : p_end_main;
+        } else {
+            pn = p + THREADS;
+            more = pn < p_end_main;
+        }
         if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
         else if (tid * kWindowSampleStride < P && src.next && src.next[0]) {
             prefetch_l2(src.next[0] + tid * kWindowSampleStride); prefetch_l2(src.next[1] + tid * kWindowSampleStride);
@@ -1715,7 +1755,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
                 const float2 d0 = da, d1 = db;
                 {
                     const bool inner = r + 2 < R;
-                    nx += inner ? step_inner : step_last;
+                    if (BLK) nx = inner ? nx + step_inner : dist + pn; else nx += inner ? step_inner : step_last;
                     if (inner || more) {
                         da = __ldcs(nx);
                         if (REVEN || (inner ? (r + 3 < R) : (R > 1))) db = __ldcs(nx + P);
@@ -1725,7 +1765,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
             }
         } else {
             any_irr = true;
-            nx += THREADS;
+            if (BLK) nx = dist + pn; else nx += THREADS;
             if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
         }
         point_epilogue(p, go0.x + go0.y, go1.x + go1.y, go2.x + go2.y, gr0.x + gr0.y, gr1.x + gr1.y, gr2.x + gr2.y);
@@ -1762,7 +1802,7 @@ template <int THREADS, int TRIG, bool BLK>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
                  float* __restrict__ grad_points, float* __restrict__ grad_normals, float* __restrict__ grad_prims,
-                 float* __restrict__ grad_orientations) {
+                 float* __restrict__ grad_orientations, float* __restrict__ grad_prims_scratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* win_g = reinterpret_cast<float*>(smem_raw);
     __shared__ TargetCtx T_sh;
@@ -1771,6 +1811,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     __shared__ float O_sh[16];
     __shared__ BlockPrim blk_sh[BLK ? kMaxBlockCandidates : 1];
     __shared__ int blk_rows_sh[BLK ? kMaxBlockCandidates : 1];
+    __shared__ double gacc_sh[BLK ? kMaxBlockCandidates * 12 : 1];
     __shared__ unsigned defer_bits_sh[BLK ? kDeferWords : 1];
     __shared__ int defer_prefix_sh[BLK ? kDeferWords : 1];
     __shared__ int defer_total_sh;
@@ -1867,12 +1908,19 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     BwdCtx bc;
     bc.win_g = win_g; bc.gf = gf; bc.e0 = W.e0; bc.u0 = W.u0; bc.ww = W.ww;
     bc.wwm1 = W.ww > 1 ? W.ww - 1 : 0; bc.whm1 = W.wh > 1 ? W.wh - 1 : 0;
-    bc.blk = blk_sh; bc.blk_rows = blk_rows_sh; bc.n_blk = 0; bc.grad_prims = grad_prims;
+    bc.blk = blk_sh; bc.blk_rows = blk_rows_sh; bc.n_blk = 0; bc.gacc = (BLK && grad_prims) ? gacc_sh : nullptr;
+    bc.gacc_copies = 1; bc.gacc_stride = 0;
+    if (BLK && grad_prims)
+        for (int i = tid; i < kMaxBlockCandidates * 12; i += THREADS) gacc_sh[i] = 0.0;   // (barriers follow before any use)
     if (BLK && prm.a.blockers.n_blockers > 0) {
         const ab200_blockers& B = prm.a.blockers;
         bc.bp.softness = B.softness; bc.bp.alpha = B.alpha; bc.bp.offset = B.ray_origin_offset; bc.bp.epsilon = B.epsilon;
         bc.bp.cull_angle = B.cull_angle;
         bc.n_blk = block_load_candidates<THREADS>(blk_sh, blk_rows_sh, B, h, tid);
+        int slots = 1;
+        while (slots < bc.n_blk) slots <<= 1;
+        bc.gacc_copies = kMaxBlockCandidates / slots;    // 4 candidates: 16 copies
+        bc.gacc_stride = slots * 12;
     }
     // Blocking: two passes, see trace_fwd_kernel and blocking_device.cuh ("Deferral")
     const bool blocking = BLK && bc.n_blk > 0;
@@ -1915,12 +1963,36 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
         AB200_PHASE(12, 3);  // ray loop, pass 1
         const int n_def = defer_scan<THREADS>(dc, &defer_total_sh);
         if (n_def > 0) {
+#if AB200_PACKED_RAYS
+            if (T.planar && T.fastdiv && TRIG != AB200_TRIG_SINCOSF) {
+                int n_irr = 0;
+                if ((prm.a.n_rays & 1) == 0)
+                    bwd_rays_planar_fast2<THREADS, TRIG, BLK, true>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, &dc);
+                else
+                    bwd_rays_planar_fast2<THREADS, TRIG, BLK, false>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, &dc);
+                if (__syncthreads_or(n_irr != 0))   // never with physical inputs
+                    bwd_rays<THREADS, TRIG, true, false, true, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, &dc, kDeferList);
+            } else
+#endif
             if (T.planar)
                 bwd_rays<THREADS, TRIG, true, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, &dc, kDeferList);
             else
                 bwd_rays<THREADS, TRIG, false, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, &dc, kDeferList);
         }
         AB200_PHASE(14, 5);  // stats[19]: pass 2 (deferred points)
+    }
+    if (BLK && grad_prims && bc.n_blk > 0) {
+        // blocker gradients of this CTA: one row per candidate slot into the caller's scratch (summed over the samples in a
+        // fixed order by blocker_grad_reduce_kernel), or - without scratch - float atomics on the primitive table's rows
+        __syncthreads();
+        const int max_cand = prm.a.blockers.max_candidates;
+        for (int i = tid; i < bc.n_blk * 12; i += THREADS) {
+            double sum = 0.0;
+            for (int k = 0; k < bc.gacc_copies; ++k) sum += gacc_sh[k * bc.gacc_stride + i];   // fixed order
+            const float v = (float)sum;
+            if (grad_prims_scratch) grad_prims_scratch[((size_t)blockIdx.x * max_cand + i / 12) * 12 + i % 12] = v;
+            else if (v != 0.0f) atomicAdd(grad_prims + (size_t)blk_rows_sh[i / 12] * 12 + i % 12, v);
+        }
     }
     AB200_PHASE(12, 3);  // ray loop (thread 0)
     if (gori_acc) {
@@ -1941,6 +2013,38 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
             if (prm.split == 1) *dst = sum; else atomicAdd(dst, sum);   // caller zeroes the buffer (row 3 stays 0)
         }
         AB200_PHASE(12, 4);  // waiting for the last warp + dL/dO reduction
+    }
+}
+
+// Blocker gradients, second stage: row k of the primitive table = the sum of the per-CTA rows of every CTA whose sample has
+// primitive k in its candidate list, in a fixed order (one warp per primitive: lane l takes CTAs l, l + 32, ... in
+// ascending order, then a shuffle tree) - no atomics, reproducible.  OVERWRITES grad_prims.
+__global__ void __launch_bounds__(256) blocker_grad_reduce_kernel(const float* __restrict__ partial, const int* __restrict__ cand_idx,
+                                                                  const int* __restrict__ cand_count,
+                                                                  const int* __restrict__ local_rows, int n_ctas, int split,
+                                                                  int max_cand, int n_prims, float* __restrict__ grad_prims) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (k >= n_prims) return;
+    float acc[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) acc[q] = 0.0f;
+    for (int cta = lane; cta < n_ctas; cta += 32) {
+        const int li = cta / split;
+        const int h = local_rows ? local_rows[li] : li;
+        const int cnt = min(cand_count[h], max_cand);
+        const int* cand = cand_idx + (size_t)h * max_cand;
+        for (int c = 0; c < cnt; ++c) {
+            if (__ldg(cand + c) != k) continue;
+            const float* row = partial + ((size_t)cta * max_cand + c) * 12;
+#pragma unroll
+            for (int q = 0; q < 12; ++q) acc[q] += row[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+        float v = acc[q];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) grad_prims[(size_t)k * 12 + q] = v;
     }
 }
 
@@ -1976,7 +2080,8 @@ struct LaunchPlan {
 static int max_window_bytes(bool blocking) {
     int dev = 0, optin = 227 * 1024;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    return optin - (blocking ? 14 : 6) * 1024;   // blocking: + 64 candidates x 96 B + the deferral bit set and its prefix sums
+    return optin - (blocking ? 20 : 6) * 1024;   // blocking: + 64 candidates x 96 B, the deferral bit set and its prefix sums,
+                                                 // 64 x 12 double gradient accumulators (backward)
 }
 
 static LaunchPlan make_plan(int n_local, int n_points, int max_threads_large, bool force_large = false, bool blocking = false) {
@@ -2058,21 +2163,21 @@ static cudaError_t launch_fwd_trig(const TraceParams& prm, const LaunchPlan& pl,
 
 template <int THREADS, int TRIG>
 static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                              long long gstride, float* gpts, float* gnrm, float* gprims, float* gori) {
+                              long long gstride, float* gpts, float* gnrm, float* gprims, float* gori, float* gscratch) {
     if (prm.a.blockers.n_blockers > 0) {
         auto kern = trace_bwd_kernel<THREADS, TRIG, true>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori);
+        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori, gscratch);
     } else {
         auto kern = trace_bwd_kernel<THREADS, TRIG, false>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori);
+        kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori, gscratch);
     }
     note_launch();
     return cudaGetLastError();
@@ -2080,11 +2185,11 @@ static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cuda
 
 template <int THREADS>
 static cudaError_t launch_bwd_trig(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
-                                   long long gstride, float* gpts, float* gnrm, float* gprims, float* gori) {
+                                   long long gstride, float* gpts, float* gnrm, float* gprims, float* gori, float* gscratch) {
     switch (prm.a.trig_mode) {
-        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori);
-        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori);
-        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori);
+        case AB200_TRIG_TABLE: return launch_bwd<THREADS, AB200_TRIG_TABLE>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori, gscratch);
+        case AB200_TRIG_POLY: return launch_bwd<THREADS, AB200_TRIG_POLY>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori, gscratch);
+        default: return launch_bwd<THREADS, AB200_TRIG_SINCOSF>(prm, pl, st, gflux, gstride, gpts, gnrm, gprims, gori, gscratch);
     }
 }
 
@@ -2183,10 +2288,25 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
     fill_params(prm, a, pl);
     const long long gstride = b->grad_flux_stride >= 0 ? b->grad_flux_stride : (long long)a->res_u * a->res_e;
     prm.quad = (pl.split == 1 && a->res_e % 4 == 0 && gstride % 4 == 0 && reinterpret_cast<uintptr_t>(b->grad_flux) % 16 == 0) ? 1 : 0;
+    // blocker gradients: per-CTA rows in the caller's scratch + an ordered reduction, if the scratch is large enough
+    const long long n_ctas = (long long)a->n_local * pl.split;
+    const bool blk_grad = a->blockers.n_blockers > 0 && b->grad_prims != nullptr;
+    float* scratch = (blk_grad && b->grad_prims_scratch &&
+                      b->grad_prims_scratch_floats >= n_ctas * a->blockers.max_candidates * 12) ? b->grad_prims_scratch : nullptr;
     cudaError_t e = (pl.threads == kBwdThreadsLarge)
-                        ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations)
-                        : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations);
+                        ? launch_bwd_trig<kBwdThreadsLarge>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations, scratch)
+                        : launch_bwd_trig<512>(prm, pl, st, b->grad_flux, gstride, b->grad_points, b->grad_normals, b->grad_prims, b->grad_orientations, scratch);
     AB200_REQUIRE(e == cudaSuccess, AB200_ECUDA, "trace_bwd launch failed: %s", cudaGetErrorString(e));
+    if (scratch) {
+        const int warps_per_block = 8;
+        const unsigned blocks = (unsigned)((a->blockers.n_blockers + warps_per_block - 1) / warps_per_block);
+        blocker_grad_reduce_kernel<<<blocks, warps_per_block * 32, 0, st>>>(scratch, a->blockers.cand_idx, a->blockers.cand_count,
+                                                                            a->local_rows, (int)n_ctas, pl.split,
+                                                                            a->blockers.max_candidates, a->blockers.n_blockers,
+                                                                            b->grad_prims);
+        note_launch();
+        AB200_CUDA_TRY(cudaGetLastError());
+    }
     return AB200_OK;
 }
 

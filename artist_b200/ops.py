@@ -301,6 +301,10 @@ def _prepare_blocking(bi: BlockingInputs, opt: TraceOptions, n: int, dev):
     _lib.call("ab200_blocking_candidates", _p(prims), h, _p(owner), _p(aim), _p(radius), n, spread, int(bi.max_candidates),
               _p(cand_idx), _p(cand_count), _p(overflow), _stream())
     last_blocking_overflow = overflow
+    if torch.cuda.is_current_stream_capturing():
+        # CUDA-graph capture: no pinned allocation / event bookkeeping inside the graph; the eager warm-up steps every
+        # capture needs have checked this geometry, and `last_blocking_overflow` stays readable after a replay
+        return prims, cand_idx, cand_count
     check_blocking_overflow()                      # flags of earlier calls that have arrived by now
     host = torch.empty(1, dtype=torch.int32, pin_memory=True)
     host.copy_(overflow, non_blocking=True)
@@ -376,9 +380,13 @@ class _TraceFn(torch.autograd.Function):
         b.grad_flux, b.grad_points, b.grad_normals = _p(g_flux), _p(g_points), _p(g_normals)
         b.grad_flux_stride = g_stride
         g_corners = g_spans = g_bnormals = None
-        need_blockers = blk is not None and any(ctx.needs_input_grad[10:13])
+        need_blockers = blk is not None and any(ctx.needs_input_grad[10:13]) and os.environ.get("AB200_NO_BLOCKER_GRAD") != "1"
         g_prims = torch.zeros(blk[1].shape[0], 12, device=points.device) if need_blockers else None
         b.grad_prims = _p(g_prims)
+        g_scratch = None
+        if need_blockers:   # per-CTA rows for the ordered (reproducible) reduction of the blocker gradients
+            g_scratch = torch.empty((distortions.shape[0] + 1024) * int(ctx.bi.max_candidates) * 12, device=points.device)
+            b.grad_prims_scratch, b.grad_prims_scratch_floats = _p(g_scratch), g_scratch.numel()
         g_ori = None
         if orientations is not None and ctx.needs_input_grad[13]:
             g_ori = torch.zeros_like(orientations)

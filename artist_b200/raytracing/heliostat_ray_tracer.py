@@ -124,10 +124,16 @@ class HeliostatRayTracer:
         active sample.  Only the 4 corner points per heliostat are gathered; the reference concatenates all surfaces."""
         corners, owner, offset = [], None, 0
         for g in self.scenario.heliostat_field.heliostat_groups:
-            rows = torch.tensor(self._corner_rows(g.surface_points.shape[1]), device=g.surface_points.device)
+            # (no host->device copy and no device->host read per call: the corner-row indices are cached, "is any heliostat of
+            # the group active" is the count activate_heliostats already holds on the host - keeps trace_rays capturable
+            # in a CUDA graph and off the launch pipeline's critical path)
+            key = (g.surface_points.shape[1], g.surface_points.device)
+            cache = self.__dict__.setdefault("_corner_rows_cache", {})
+            rows = cache.get(key)
+            if rows is None:
+                rows = cache[key] = torch.tensor(self._corner_rows(key[0]), device=key[1])
             c = g.surface_points.index_select(1, rows) + g.positions.unsqueeze(1)
-            mask = g.active_heliostats_mask
-            if bool((mask > 0).any()):
+            if g.number_of_active_heliostats > 0:
                 active_rows = getattr(g, "_active_rows", None)
                 if active_rows is None:     # all-ones mask: sample i is heliostat i
                     active_rows = torch.arange(g.number_of_heliostats, device=c.device)

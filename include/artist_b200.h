@@ -165,10 +165,15 @@ typedef struct ab200_trace_bwd_args {
                                  grad_orientations / grad_prims are wanted (motor-position optimisation): the kernel then
                                  skips the 64 B per point of gradient stores */
     float* grad_normals;      /* out [N,P,4] (w component 0) */
-    float* grad_prims;        /* blocking only, may be NULL: [H,12] d/d(corner0, span_u, span_v, normal), ACCUMULATED with
-                                 float atomics (caller zeroes it) */
+    float* grad_prims;        /* blocking only, may be NULL: [H,12] d/d(corner0, span_u, span_v, normal).  With
+                                 grad_prims_scratch: OVERWRITTEN with sums taken in a fixed order (every CTA adds the few rays
+                                 inside a sigmoid transition into shared-memory double accumulators, writes one row per
+                                 candidate slot to the scratch, a second kernel sums the rows per primitive).  Without:
+                                 accumulated with float atomics (caller zeroes it). */
     float* grad_orientations; /* fwd.orientations only, may be NULL: [N,4,4] dL/dO (caller zeroes it; row 3 stays 0).
                                  With fwd.orientations set, grad_points / grad_normals are w.r.t. the UN-aligned rows. */
+    float* grad_prims_scratch;        /* device scratch for grad_prims, may be NULL: >= (N + 1024) * max_candidates * 12 floats */
+    int64_t grad_prims_scratch_floats; /* its capacity in floats (too small: the atomics path runs) */
 } ab200_trace_bwd_args;
 
 int32_t ab200_trace_bwd(const ab200_trace_bwd_args* args, void* stream);

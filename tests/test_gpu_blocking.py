@@ -94,3 +94,30 @@ def test_distant_heliostats_do_not_block():
     a = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor([64, 64])).trace_rays(inc, mask, tidx)
     b = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor([64, 64])).trace_rays(inc, mask, tidx)
     assert torch.equal(a[0], b[0]) and torch.equal(a[3], torch.ones_like(a[3]))
+
+
+def test_blocker_gradients_are_reproducible_run_to_run():
+    """The gradient w.r.t. the blockers' geometry is summed per CTA in shared-memory double accumulators and across the
+    samples in a fixed order (``blocker_grad_reduce_kernel``), not with global float atomics: two runs give the same bits
+    (as do the bitmaps and every other gradient)."""
+    from artist_b200 import HeliostatRayTracer
+
+    res = (64, 64)
+    ft, scenario, group, mask, tidx, inc = _scene(n=16, ppf=(16, 16), rays=8)
+    base_p, base_n = group.active_surface_points.detach().clone(), group.active_surface_normals.detach().clone()
+    torch.manual_seed(3)
+    wgt = torch.rand(16, res[1], res[0], device=DEV)
+    runs = []
+    for _ in range(3):
+        p, n = base_p.clone().requires_grad_(True), base_n.clone().requires_grad_(True)
+        group.active_surface_points, group.active_surface_normals = p, n
+        tracer = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor(res))
+        flux, ic, ot, bl = tracer.trace_rays(inc, mask, tidx)
+        (flux * wgt).sum().backward()
+        runs.append((flux.detach().clone(), p.grad.clone(), n.grad.clone()))
+    assert float(bl.min()) < 0.95, "the scene was meant to be shadowed"
+    rows = torch.tensor(HeliostatRayTracer._corner_rows(base_p.shape[1]), device=DEV)
+    assert runs[0][1][:, rows].abs().max() > 0
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert torch.equal(a, b)

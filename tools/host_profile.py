@@ -33,4 +33,38 @@ for _ in range(steps):
 torch.cuda.synchronize()
 pr.disable()
 st = pstats.Stats(pr)
-st.sort_stats("cumulative").print_stats(45)
+st.sort_stats("cumulative").print_stats(int(os.environ.get("AB200_PROFILE_ROWS", "45")))
+
+# ---- the same forward+backward captured once into a CUDA graph (tests/test_gpu_cuda_graph.py) ----
+def fb():
+    wl.param.grad = None
+    total = wl.forward_local()
+    (total * total).mean().backward()
+
+
+wl.last_total = None   # (drop the last eager step's autograd graph: a live AccumulateGrad node of the default stream would
+                       # invalidate the capture - torch's rule, not the kernels')
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3):
+        fb()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(steps):
+    fb()
+torch.cuda.synchronize()
+eager = (time.perf_counter() - t0) / steps * 1e3
+wl.param.grad = None
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    total = wl.forward_local()
+    (total * total).mean().backward()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(steps):
+    graph.replay()
+torch.cuda.synchronize()
+replay = (time.perf_counter() - t0) / steps * 1e3
+print(f"{n} heliostats, forward+backward: eager {eager:.3f} ms/step, CUDA-graph replay {replay:.3f} ms/step ({eager / replay:.1f}x)")
