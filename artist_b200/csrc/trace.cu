@@ -564,7 +564,9 @@ __device__ __forceinline__ bool front_regular(float a) {
 // DRAM round trips.
 // REVEN: the number of rays per point is even (every scenario of the reference: 4, 10, 100, 170, 180, 200), so both
 // lanes of every pair are live and the loads of the software pipeline need no per-lane conditions.
-template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK, bool REVEN>
+// DEFER: pass 1 of a blocking trace (BLK is false then): shadow-affected points are recorded in `dc` and skipped,
+// completely shadowed ones counted without taps.  A compile-time switch so that the plain kernels carry none of it.
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK, bool REVEN, bool DEFER = false>
 __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h,
                                                       int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
                                                       int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
@@ -612,7 +614,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     float2 da = make_float2(0.f, 0.f), db = da;
     const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
     if (p < p_end) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
-    for (; p < p_end; p = pn) {
+    for (; p < p_end; p = BLK ? pn : p + THREADS) {   // (plain kernels: no `pn` alive across the body)
         bool more;
         if (BLK) {
             it += THREADS;
@@ -639,7 +641,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
             continue;
         }
         bool point_dead = false;   // pass 1 of a blocking trace: every ray of the point is completely shadowed - traced for the
-        if (!BLK && dc) {          // on-target counter, no taps
+        if (DEFER) {               // on-target counter, no taps
             const int pcls = defer_point(dc, p - p_begin, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2);
             if (pcls == kPointDeferred) {   // shadow-affected: pass 2
                 nx += THREADS;
@@ -730,10 +732,12 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
                 cnt_bad += (int)!valid0 + (int)(two && !valid1);
                 const bool irr0 = !ang0 || ((a.x < 0.0f) && !fr0), irr1 = two && (!ang1 || ((a.y < 0.0f) && !fr1));
                 any_irr |= irr0 || irr1;
-                if (!point_dead) cnt_irr += (int)irr0 + (int)irr1;
-                else cnt_dead_bad += (int)!valid0 + (int)(two && !valid1);
+                if (DEFER) {
+                    if (!point_dead) cnt_irr += (int)irr0 + (int)irr1;
+                    else cnt_dead_bad += (int)!valid0 + (int)(two && !valid1);
+                }
             }
-            if (!BLK && point_dead) continue;   // (dc != nullptr) counted above, nothing to splat
+            if (DEFER && point_dead) continue;   // counted above, nothing to splat
             float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
             if (DBG) {
                 const size_t q = ((size_t)h * R + r) * P + p;
@@ -825,11 +829,11 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     }
     const int cnt_valid = n_reg_points * R - cnt_bad;
     // (dead points of pass 1: their valid rays are on target but carry no intensity and count as blocked)
-    cnt_lam_out = BLK ? cnt_lam : cnt_valid; cnt_int_out = BLK ? cnt_int : cnt_valid - (n_dead_points * R - cnt_dead_bad);
+    cnt_lam_out = BLK ? cnt_lam : cnt_valid; cnt_int_out = BLK ? cnt_int : (DEFER ? cnt_valid - (n_dead_points * R - cnt_dead_bad) : cnt_valid);
     fell_back_out = fell_back;
     // pass 1 of a blocking trace: every regular ray traced here is unshadowed (blocked == 0 < 1e-3); the irregular ones are
     // counted by the generic pass that re-traces them
-    cnt_blk_out = (!BLK && dc) ? (n_reg_points - n_dead_points) * R - cnt_irr : cnt_blk;
+    cnt_blk_out = DEFER ? (n_reg_points - n_dead_points) * R - cnt_irr : cnt_blk;
     n_irregular_out = any_irr ? 1 : 0;
 }
 
@@ -864,7 +868,11 @@ trace_fwd_kernel(const TraceParams prm) {
     // 0), orientation (threads 32..47), incident direction and the window-sample rows (every thread); meanwhile the
     // whole shared-memory window is cleared
     long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
+#ifdef AB200_NO_SRC_ROWS
+    const int hs = h;
+#else
     const int hs = prm.a.src_rows ? __ldg(prm.a.src_rows + h) : h;   // activation index map: surface row of this sample
+#endif
     const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hs * P;
     const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hs * P;
     WindowSamples ws;
@@ -977,9 +985,9 @@ trace_fwd_kernel(const TraceParams prm) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
         if ((R & 1) == 0)
-            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
+            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, true, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
         else
-            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
+            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
 #else   // tuning build without the packed loops: the scalar fast loop evaluates the mask inline, nothing is deferred
         fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #endif
@@ -1507,7 +1515,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast(const TraceParams& prm, con
 // ray (which decides the pixels) repeats the forward's strict operation sequence exactly; the gradient math behind it
 // is ordinary packed FMA arithmetic.  A pair with one dead lane (invalid / off-bitmap ray) zeroes that lane's inputs,
 // so it contributes exact zeros; a pair with two dead lanes is skipped.
-template <int THREADS, int TRIG, bool BLK, bool REVEN>
+template <int THREADS, int TRIG, bool BLK, bool REVEN, bool DEFER = false>   // DEFER: see fwd_rays_planar_fast2
 __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, const TargetCtx& T, const BwdCtx& bc,
                                                       const PointSrc& src, int h, int p_begin, int p_end, float i0, float i1,
                                                       float i2, float* __restrict__ grad_points,
@@ -1710,7 +1718,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     int slots = 1;
     while (slots < n_pairs) slots <<= 1;
     const bool split_tail = AB200_BWD_SPLIT_TAIL && REVEN && TRIG != AB200_TRIG_TABLE && n_full > 0 && n_tail > 0 && slots <= 32 && n_tail * slots <= THREADS &&
-                            dc == nullptr;   // (a deferring pass records whole points)
+                            !DEFER && !BLK;   // (the passes of a blocking trace handle whole points)
     const int p_end_main = split_tail ? p_begin + n_full : p_end;
 
     // BLK instantiation = pass 2 of a blocking trace over the deferral list `dc` (see fwd_rays_planar_fast2)
@@ -1721,7 +1729,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     float2 da = zero2, db = zero2;
     const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
     if (p < p_end_main) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
-    for (; p < p_end_main; p = pn) {
+    for (; p < p_end_main; p = BLK ? pn : p + THREADS) {
         bool more;
         if (BLK) {
             it += THREADS;
@@ -1743,7 +1751,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
         }
         float2 go0 = zero2, go1 = zero2, go2 = zero2, gr0 = zero2, gr1 = zero2, gr2 = zero2;   // one partial sum per lane
         if (point_regular(pc)) {
-            const int pcls = BLK ? kPointClear : defer_point(dc, p - p_begin, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2);
+            const int pcls = DEFER ? defer_point(dc, p - p_begin, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : kPointClear;
             if (pcls != kPointClear) {   // shadow-affected: pass 2 traces the point and writes its rows; completely shadowed:
                 nx += THREADS;           // zero rows from the epilogue below
                 if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
@@ -1943,9 +1951,9 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
         int n_irr = 0;
 #if AB200_PACKED_RAYS
         if ((prm.a.n_rays & 1) == 0)
-            bwd_rays_planar_fast2<THREADS, TRIG, false, true>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, rec);
+            bwd_rays_planar_fast2<THREADS, TRIG, false, true, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, rec);
         else
-            bwd_rays_planar_fast2<THREADS, TRIG, false, false>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, rec);
+            bwd_rays_planar_fast2<THREADS, TRIG, false, false, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr, rec);
 #else   // tuning build without the packed loops: inline mask, nothing deferred
         bwd_rays_planar_fast<THREADS, TRIG, BLK>(prm, T, bc, src, h, p_begin, p_end, i0, i1, i2, grad_points, grad_normals, gori_acc, n_irr);
 #endif

@@ -15,7 +15,7 @@ while [ $# -ge 2 ]; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $flags \
       -c artist_b200/csrc/$SRC.cu -o artist_b200/lib/variants/${SRC}_$name.o &&
     nvcc -shared -gencode arch=compute_100a,code=sm_100a -o artist_b200/lib/variants/$name.so \
-      artist_b200/lib/variants/${SRC}_$name.o $(for o in trace nurbs kinematics blocking geometry flux; do [ $o = $SRC ] || echo artist_b200/lib/$o.o; done) &&
+      artist_b200/lib/variants/${SRC}_$name.o $(for o in trace nurbs kinematics blocking geometry flux sampling; do [ $o = $SRC ] || echo artist_b200/lib/$o.o; done) &&
     rm artist_b200/lib/variants/${SRC}_$name.o && echo "built $name ($flags)"
   ) &
   pids+=($!)
