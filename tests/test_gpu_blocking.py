@@ -121,3 +121,34 @@ def test_blocker_gradients_are_reproducible_run_to_run():
     for other in runs[1:]:
         for a, b in zip(runs[0], other):
             assert torch.equal(a, b)
+
+
+def test_blocking_one_cta_per_sample_kernels_equal_split_mode():
+    """The kernels a full field runs (one CTA per sample: both blocking passes, the packed second pass, per-CTA blocker-gradient
+    rows) against the several-CTAs-per-sample kernels a small scene picks: identical bitmaps and factors (integer
+    accumulation), gradients equal up to summation order - incl. the blockers' corner rows - and both within the usual bars
+    of the oracle (asserted for the split mode by the tests above)."""
+    from artist_b200 import HeliostatRayTracer
+
+    res = (96, 80)
+    ft, scenario, group, mask, tidx, inc = _scene(n=16, ppf=(20, 20), rays=6)
+    base_p, base_n = group.active_surface_points.detach().clone(), group.active_surface_normals.detach().clone()
+    torch.manual_seed(4)
+    wgt = torch.rand(16, res[1], res[0], device=DEV)
+    out = {}
+    for force in (False, True):
+        p, n = base_p.clone().requires_grad_(True), base_n.clone().requires_grad_(True)
+        group.active_surface_points, group.active_surface_normals = p, n
+        tracer = HeliostatRayTracer(scenario, group, blocking_active=True, bitmap_resolution=torch.tensor(res))
+        tracer._force_one_cta_per_sample = force
+        flux, ic, ot, bl = tracer.trace_rays(inc, mask, tidx)
+        (flux * wgt).sum().backward()
+        out[force] = (flux.detach(), ic, ot, bl, p.grad, n.grad)
+    assert float(out[True][3].min()) < 0.95 and out[True][0].sum() > 0
+    for a, b in zip(out[True][:4], out[False][:4]):
+        assert torch.equal(a, b)
+    for a, b, name in ((out[True][4], out[False][4], "points"), (out[True][5], out[False][5], "normals")):
+        assert (a - b).abs().max() <= 2e-5 * b.abs().max(), name
+    rows = torch.tensor(HeliostatRayTracer._corner_rows(base_p.shape[1]), device=DEV)
+    ca, cb = out[True][4][:, rows], out[False][4][:, rows]
+    assert cb.abs().max() > 0 and (ca - cb).abs().max() <= 1e-4 * cb.abs().max()
