@@ -141,3 +141,34 @@ def test_bitmap_loss_at_bench_size_matches_the_oracle():
         pd = pred.detach().double().requires_grad_(True)
         fn(pd, gt.double()).sum().backward()
         assert (p.grad.cpu().double() - pd.grad).abs().max() <= 2e-5 * pd.grad.abs().max()
+
+
+@pytest.mark.parametrize("res", [(256, 256), (48, 64), (50, 37)])
+def test_column_marching_crop_kernels_equal_the_per_pixel_kernels(res, monkeypatch):
+    """Round-2 crop kernels (one thread walks a column, source rows kept in registers) against the per-pixel kernels of
+    round 1 (``AB200_FLUX_PER_PIXEL``), which the tests above pin to the real reference: forward bit-identical, gradients
+    equal up to summation order - for crops smaller and larger than the target, strong magnification (the per-bitmap
+    fallback), and centres of mass near the bitmap's corners."""
+    from artist_b200 import ops
+
+    u, e = res
+    gen = torch.Generator().manual_seed(9)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, u), torch.linspace(-1, 1, e), indexing="ij")
+    centres = [(0.0, 0.0), (0.6, -0.5), (-0.85, 0.8), (0.1, 0.95), (-0.3, 0.2), (0.9, 0.9)]
+    flux = torch.stack([torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / 0.05) + 0.01 * torch.rand(u, e, generator=gen)
+                        for cx, cy in centres]).to(DEV)
+    scale = torch.tensor([[0.75, 0.75], [1.3, 0.6], [0.45, 1.7], [0.3, 0.3], [1.0, 1.0], [2.5, 0.9]], device=DEV)
+    wgt = torch.rand(flux.shape, generator=gen).to(DEV)
+
+    def run():
+        x = flux.clone().requires_grad_(True)
+        out = ops.flux_crop_around_center(x, scale)
+        (out * wgt).sum().backward()
+        return out.detach(), x.grad
+
+    new_out, new_grad = run()
+    monkeypatch.setenv("AB200_FLUX_PER_PIXEL", "1")
+    old_out, old_grad = run()
+    assert old_out.abs().max() > 0
+    assert torch.equal(new_out, old_out)
+    assert (new_grad - old_grad).abs().max() <= 2e-6 * old_grad.abs().max()
