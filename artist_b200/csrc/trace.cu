@@ -227,11 +227,15 @@ __device__ void place_window(Window& win_out, const TraceParams& prm, const Targ
 
 // The sample the CTA one wave later will trace (one-CTA-per-sample mode): its rows for the window placement are pulled into
 // L2 by this CTA's threads during their last surface point (fwd_/bwd_rays_planar_fast2), its per-sample scalars here.
+// MAP (compile time): the kernel reads its surface rows through ab200_trace_args::src_rows.  Looked up at run time behind a
+// NULL test, the row index - and every address derived from it - left the uniform datapath, and the forward of the plain
+// kernels was 2.6 % slower even without a map (found by bisection, tools/time_fwd.py): so the map is its own instantiation.
+template <bool MAP>
 __device__ inline void set_next_sample(const float4** next_sh, const TraceParams& prm, int li) {
     next_sh[0] = nullptr; next_sh[1] = nullptr;
-    if (prm.wave > 0 && li + prm.wave < prm.a.n_local) {
+    if (!MAP && prm.wave > 0 && li + prm.wave < prm.a.n_local) {   // (with a map the next sample's rows are not prefetched)
         const int hn = prm.a.local_rows ? prm.a.local_rows[li + prm.wave] : li + prm.wave;
-        const int sn = prm.a.src_rows ? __ldg(prm.a.src_rows + hn) : hn;
+        const int sn = hn;
         next_sh[0] = reinterpret_cast<const float4*>(prm.a.points) + (size_t)sn * prm.a.n_points;
         next_sh[1] = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)sn * prm.a.n_points;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.a.incident + 4 * hn));
@@ -564,6 +568,242 @@ __device__ __forceinline__ bool front_regular(float a) {
 // DRAM round trips.
 // REVEN: the number of rays per point is even (every scenario of the reference: 4, 10, 100, 170, 180, 200), so both
 // lanes of every pair are live and the loads of the software pipeline need no per-lane conditions.
+// The loop of the plain (no blocking) kernels, exactly as round 1 left it.  The blocking trace uses the variant below
+// (fwd_rays_planar_fast2: deferral hooks of pass 1, list walk of pass 2); keeping the two apart keeps the register
+// allocation and address arithmetic of the headline kernel out of reach of the blocking bookkeeping (with the hooks merged
+// in behind compile-time switches the loop still came out 2.6 instructions per ray longer: 1.055 instead of 1.02 ms).
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK, bool REVEN>
+__device__ __forceinline__ void fwd_rays_planar_fast2_plain(const TraceParams& prm, const TargetCtx& T, const FwdCtx& fc, const PointSrc& src, int h,
+                                                      int p_begin, int p_end, float i0, float i1, float i2, int& cnt_lam_out,
+                                                      int& cnt_int_out, int& cnt_blk_out, bool& fell_back_out,
+                                                      int& n_irregular_out) {
+    const int tid = threadIdx.x;
+    const int P = prm.a.n_points, R = prm.a.n_rays, E = prm.a.res_e, U = prm.a.res_u;
+    const float4* pts = src.pts;
+    const float4* nrm = src.nrm;
+    const float2* dist = reinterpret_cast<const float2*>(prm.a.distortions) + (size_t)h * R * P;
+    const float4* trig = (TRIG == AB200_TRIG_TABLE) ? reinterpret_cast<const float4*>(prm.a.trig) + (size_t)h * R * P : nullptr;
+    unsigned* out_u = reinterpret_cast<unsigned*>(fc.out_f);
+    const Packed K(prm.ident);
+    const float mag = prm.a.ray_magnitude, ome = prm.a.one_minus_extinction, refl = prm.a.reflectivity;
+    const float fxs_sub = prm.fx_scale * 0x1p-100f;   // (exact) see the tap rounding below
+    const float kTwoM49 = 0x1p-49f;
+    const unsigned em1_bits = __float_as_uint(T.em1), um1_bits = __float_as_uint(T.um1);
+    const bool axis_n = (T.n0 == 0.0f) && (T.n2 == 0.0f);
+    // Pixel indices relative to the window come straight out of the floor() trick: be + (1.5 * 2^23 - e0), rounded down,
+    // has the bit pattern 0x4B400000 + (floor(be) - e0) (two's complement wrap-around for negative differences), so
+    // cex = bits - 0x4B400000 costs ONE integer instruction with an immediate operand.  The window's shared-memory
+    // address is kept opaque so that it stays in a register instead of being re-derived for every tap.
+    const int e0w = fc.ww > 0 ? fc.e0 : 0, u0w = fc.ww > 0 ? fc.u0 : 0;   // (an empty window has a huge origin)
+    float magic_e = 12582912.0f - (float)e0w, magic_u = 12582912.0f - (float)u0w;
+    asm volatile("" : "+f"(magic_e), "+f"(magic_u));   // loop invariants: kept in registers, not re-derived per pair
+    const unsigned kIdxBits = 0x4B400000u;
+    unsigned wwm1 = (unsigned)max(fc.ww, 1) - 1u, whm1 = (unsigned)max(fc.wh, 1) - 1u;   // empty window: nothing is "inside"
+    asm volatile("" : "+r"(wwm1), "+r"(whm1));
+    unsigned win_base = (unsigned)__cvta_generic_to_shared(fc.win_u);
+    asm volatile("" : "+r"(win_base));
+    const unsigned row_bytes = (unsigned)fc.ww * 4u;
+    // factor counters: valid rays = R * (regular points) - cnt_bad; invalid rays are rare, so the bookkeeping (and the
+    // irregularity flag, which implies invalid) lives in a rarely taken branch
+    int cnt_bad = 0, n_reg_points = 0, cnt_lam = 0, cnt_int = 0, cnt_blk = 0;
+    bool fell_back = false, any_irr = false;
+    // the next distortion pair of this thread: +2P inside a point, then over to the first pair of its next point
+    const int n_pairs = (R + 1) >> 1;
+    const long long step_inner = 2 * (long long)P, step_last = (long long)THREADS - (long long)(n_pairs - 1) * 2 * (long long)P;
+
+    int p = p_begin + tid;
+    float2 da = make_float2(0.f, 0.f), db = da;
+    const float2* nx = dist + p;      // address of the pair loaded NEXT (always one pair ahead of the math)
+    if (p < p_end) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+    for (; p < p_end; p += THREADS) {
+        const int pn = p + THREADS;
+        const bool more = pn < p_end;
+        if (more) { prefetch_l2(pts + pn); prefetch_l2(nrm + pn); }
+        else if (tid * kWindowSampleStride < P && src.next && src.next[0]) {
+            prefetch_l2(src.next[0] + tid * kWindowSampleStride); prefetch_l2(src.next[1] + tid * kWindowSampleStride);
+        }
+        PointCtx pc;
+        {
+            float4 o4 = __ldg(pts + p), n4 = __ldg(nrm + p);
+            orient_point(src, o4, n4);
+            make_point(pc, T, i0, i1, i2, o4, n4);
+        }
+        if (!point_regular(pc)) {   // never with physical inputs: the generic loop re-traces the whole point
+            any_irr = true;
+            nx += THREADS;
+            if (more) { da = __ldcs(nx); if (R > 1) db = __ldcs(nx + P); }
+            continue;
+        }
+        const unsigned long long bmask = (BLK && fc.n_blk) ? block_point_mask(fc.blk, fc.n_blk, fc.bp, pc.o0, pc.o1, pc.o2, pc.r0, pc.r1, pc.r2) : 0ull;
+        ++n_reg_points;
+        for (int r = 0; r < R; r += 2) {
+            const bool two = REVEN || (r + 1 < R);   // an odd R leaves the second lane of the last pair idle
+            const float2 d0 = da, d1 = db;
+            {
+                const bool inner = r + 2 < R;
+                nx += inner ? step_inner : step_last;
+                if (inner || more) {
+                    da = __ldcs(nx);
+                    if (REVEN || (inner ? (r + 3 < R) : (R > 1))) db = __ldcs(nx + P);
+                }
+            }
+            float2 cu, su, ce, se;
+            bool ang0 = true, ang1 = true;
+            if (TRIG == AB200_TRIG_TABLE) {
+                const float4 ta = __ldg(trig + (size_t)r * P + p);
+                const float4 tb = two ? __ldg(trig + (size_t)(r + 1) * P + p) : ta;
+                cu = make_float2(ta.x, tb.x); su = make_float2(ta.y, tb.y); ce = make_float2(ta.z, tb.z); se = make_float2(ta.w, tb.w);
+            } else {
+                const float m0 = fmaxf(fabsf(d0.x), fabsf(d0.y)), m1 = fmaxf(fabsf(d1.x), fabsf(d1.y));
+                if (fmaxf(m0, m1) <= kTinyAngle) {   // always, for a physical sun shape (decided per PAIR, identically
+                    sincos_tiny2(make_float2(d0.x, d1.x), &su, &cu, K);   // in the forward and the backward kernel)
+                    sincos_tiny2(make_float2(d0.y, d1.y), &se, &ce, K);
+                } else {
+                    sincos_poly_core2(make_float2(d0.x, d1.x), &su, &cu, K);
+                    sincos_poly_core2(make_float2(d0.y, d1.y), &se, &ce, K);
+                    ang0 = m0 <= 0.785f;
+                    ang1 = m1 <= 0.785f;
+                }
+            }
+            // scatter: d = M(e,u) r   ((-su) * r1 == su * (-r1), (-se) * r2 == se * (-r2) exactly)
+            const float2 m10 = K.mul(ce, su), m11 = K.mul(ce, cu), m20 = K.mul(se, su), m21 = K.mul(se, cu);
+            const float2 dx = K.add(K.mul(cu, bc2(pc.r0)), K.mul(su, bc2(-pc.r1)));
+            const float2 dy = K.add(K.add(K.mul(m10, bc2(pc.r0)), K.mul(m11, bc2(pc.r1))), K.mul(se, bc2(-pc.r2)));
+            const float2 dz = K.add(K.add(K.mul(m20, bc2(pc.r0)), K.mul(m21, bc2(pc.r1))), K.mul(ce, bc2(pc.r2)));
+            // a = d . n_t; for a target facing exactly +-north (n_e = n_u = 0, every scenario of the reference) the two
+            // zero products only add +-0, so the strict sum IS RN(dy * n_n) whenever it is non-zero (a == 0 is invalid anyway)
+            const float2 a = axis_n ? K.mul(dy, bc2(T.n1))
+                                    : K.add(K.add(K.mul(dx, bc2(T.n0)), K.mul(dy, bc2(T.n1))), K.mul(dz, bc2(T.n2)));
+            // regular = angles in the polynomial's range and (a >= 0  or  a in (-1e18, -1e-18)); irregular rays are
+            // left to the generic loop (same predicate there: angles_regular && cosine_regular)
+            const bool fr0 = front_regular(a.x), fr1 = front_regular(a.y);
+            const bool front0 = ang0 && fr0, front1 = two && ang1 && fr1;   // regular and front-facing: may be valid
+            const float2 t = div_regular2(bc2(pc.num), a, K);
+            const float2 X = K.add(bc2(pc.o0), K.mul(dx, t));
+            const float2 Z = K.add(bc2(pc.o2), K.mul(dz, t));
+            const float2 te = K.sub(K.add(X, bc2(T.half_w)), bc2(T.c0));
+            const float2 tu = K.sub(K.add(Z, bc2(T.half_h)), bc2(T.c2));
+            // exact constant-divisor quotients (const_div): q0 = te*rw; r = te - q0*w; q = q0 + r*rw.  The last
+            // product adds +0 instead of -0: identical except that a -0 product becomes +0 (same validity, see above)
+            const float2 qe0 = K.mul(te, bc2(T.rw)), qu0 = K.mul(tu, bc2(T.rh));
+            const float2 be0 = pfma(pfma(pfma(qe0, bc2(-T.w), te), bc2(T.rw), qe0), bc2(T.em1), bc2(0.0f));
+            const float2 bu0 = pfma(pfma(pfma(qu0, bc2(-T.h), tu), bc2(T.rh), qu0), bc2(T.um1), bc2(0.0f));
+            const bool valid0 = front0 && (__float_as_uint(be0.x) <= em1_bits) && (__float_as_uint(bu0.x) <= um1_bits);
+            const bool valid1 = front1 && (__float_as_uint(be0.y) <= em1_bits) && (__float_as_uint(bu0.y) <= um1_bits);
+            float2 lam = K.mul(a, bc2(-mag));                       // mag * (-a)
+            lam.x = valid0 ? lam.x : 0.0f; lam.y = valid1 ? lam.y : 0.0f;
+            float2 inten;
+            if (BLK) {
+                float2 blocked = make_float2(0.f, 0.f);
+                const bool reg0 = ang0 && (fr0 || !(a.x < 0.0f)), reg1 = two && ang1 && (fr1 || !(a.y < 0.0f));
+                if (bmask) {
+                    if (reg0) blocked.x = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.x, dy.x, dz.x);
+                    if (reg1) blocked.y = block_eval(fc.blk, bmask, fc.bp, pc.o0, pc.o1, pc.o2, dx.y, dy.y, dz.y);
+                }
+                cnt_blk += (reg0 && blocked.x < 1e-3f) + (reg1 && blocked.y < 1e-3f);
+                inten = K.mul(K.mul(K.mul(lam, K.sub(K.one, blocked)), bc2(ome)), bc2(refl));
+                cnt_lam += (lam.x > 0.0f) + (lam.y > 0.0f);
+                cnt_int += (inten.x > 0.0f) + (inten.y > 0.0f);
+            } else {
+                inten = K.mul(K.mul(lam, bc2(ome)), bc2(refl));
+            }
+            if (!(valid0 && valid1)) {   // rare
+                cnt_bad += (int)!valid0 + (int)(two && !valid1);
+                any_irr |= !ang0 || ((a.x < 0.0f) && !fr0) || (two && (!ang1 || ((a.y < 0.0f) && !fr1)));
+            }
+            float2 be = K.sub(bc2(T.em1), be0), bu = bu0;
+            if (DBG) {
+                const size_t q = ((size_t)h * R + r) * P + p;
+                const bool reg0 = ang0 && (fr0 || !(a.x < 0.0f)), reg1 = two && ang1 && (fr1 || !(a.y < 0.0f));
+                if (reg0) {
+                    if (prm.a.dbg_be) prm.a.dbg_be[q] = valid0 ? be.x : T.em1;
+                    if (prm.a.dbg_bu) prm.a.dbg_bu[q] = valid0 ? bu.x : 0.0f;
+                    if (prm.a.dbg_t) prm.a.dbg_t[q] = valid0 ? t.x : 0.0f;
+                    if (prm.a.dbg_lambert) prm.a.dbg_lambert[q] = lam.x;
+                }
+                if (reg1) {
+                    if (prm.a.dbg_be) prm.a.dbg_be[q + P] = valid1 ? be.y : T.em1;
+                    if (prm.a.dbg_bu) prm.a.dbg_bu[q + P] = valid1 ? bu.y : 0.0f;
+                    if (prm.a.dbg_t) prm.a.dbg_t[q + P] = valid1 ? t.y : 0.0f;
+                    if (prm.a.dbg_lambert) prm.a.dbg_lambert[q + P] = lam.y;
+                }
+            }
+            // splat weights (valid rays have 0 <= be <= E-1, 0 <= bu <= U-1).  floor() and the integer pixel index come
+            // from one round-down add of 2^23 (FMA pipe) instead of FRND + F2I (XU pipe): for 0 <= x < 2^23 the sum's
+            // low mantissa bits ARE floor(x).
+            const float2 me = make_float2(__fadd_rd(be.x, magic_e), __fadd_rd(be.y, magic_e));
+            const float2 mu = make_float2(__fadd_rd(bu.x, magic_u), __fadd_rd(bu.y, magic_u));
+            // high weights = fractional parts (exact); low weights = 1 - high, the same real number as the reference's
+            // (ie + 1) - be with its single rounding placed differently (<= 1 ulp of the weight, 1e-7 of a tap)
+            const float2 whe = K.sub(be, K.sub(me, bc2(magic_e))), whu = K.sub(bu, K.sub(mu, bc2(magic_u)));
+            const float2 wlu = K.sub(K.one, whu);
+            float2 v1, v2, v3, v4;   // tap values (fp32 accumulate) or the rounded scaled tap value as a SUBNORMAL float (fixed point)
+            if (FP32ACC) {
+                const float2 wle = K.sub(K.one, whe);
+                v1 = K.mul(K.mul(wle, whu), inten); v2 = K.mul(K.mul(whe, whu), inten);
+                v3 = K.mul(K.mul(whe, wlu), inten); v4 = K.mul(K.mul(wle, wlu), inten);
+            } else {
+                // round(w_e * w_u * scaled intensity) to an integer WITHOUT a float->int step: the factors carry 2^-49 and
+                // 2^-100 (exact: powers of two, no underflow before a tap is far below one count), so the product of the
+                // last multiplication is tap * 2^-149 - a subnormal float, whose bit pattern IS the integer, rounded to
+                // nearest even by the multiplier itself (the same rounding as adding 2^23 to the unscaled product)
+                float2 sc = K.mul(inten, bc2(fxs_sub));
+                sc.x = fabsf(sc.x); sc.y = fabsf(sc.y);
+                const float2 ahi = K.mul(whu, sc), alo = K.mul(wlu, sc);
+                const float2 whes = K.mul(whe, bc2(kTwoM49)), wles = K.sub(bc2(kTwoM49), whes);
+                v1 = pfma(wles, ahi, bc2(0.0f)); v2 = pfma(whes, ahi, bc2(0.0f));
+                v3 = pfma(whes, alo, bc2(0.0f)); v4 = pfma(wles, alo, bc2(0.0f));
+            }
+#pragma unroll
+            for (int lane = 0; lane < 2; ++lane) {
+                if (!(lane ? valid1 : valid0)) continue;
+                const int cex = (int)(__float_as_uint(lane ? me.y : me.x) - kIdxBits);   // ie - e0
+                const int cux = (int)(__float_as_uint(lane ? mu.y : mu.x) - kIdxBits);   // iu - u0
+                const int ie = cex + e0w, iu = cux + u0w;   // only the slow paths need the absolute pixel index
+                // inside the window interior: implies ie + 1 < E and iu + 1 < U (the window lies on the bitmap)
+                const bool fast = ((unsigned)cex < wwm1) && ((unsigned)cux < whm1);
+                const float a1 = lane ? v1.y : v1.x, a2 = lane ? v2.y : v2.x, a3 = lane ? v3.y : v3.x, a4 = lane ? v4.y : v4.x;
+                if (FP32ACC) {
+                    if (fast) {
+                        float* b = fc.win_f + cux * fc.ww + cex;
+                        atomicAdd(b + fc.ww, a1); atomicAdd(b + fc.ww + 1, a2); atomicAdd(b + 1, a3); atomicAdd(b, a4);
+                    } else if (ie + 1 < E && iu + 1 < U) {
+                        float* row_hi = fc.out_f + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                        float* row_lo = row_hi + E;
+                        atomicAdd(row_hi, a1); atomicAdd(row_hi + 1, a2); atomicAdd(row_lo + 1, a3); atomicAdd(row_lo, a4);
+                    }
+                } else {
+                    const unsigned q1 = __float_as_uint(a1), q2 = __float_as_uint(a2), q3 = __float_as_uint(a3), q4 = __float_as_uint(a4);
+                    if (fast) {
+                        // 32-bit shared-window addresses + red.shared: no generic->shared conversion per tap
+                        const unsigned lo = win_base + (unsigned)(cux * fc.ww + cex) * 4u, hi = lo + row_bytes;
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hi), "r"(q1) : "memory");
+                        asm volatile("red.shared.add.u32 [%0+4], %1;" ::"r"(hi), "r"(q2) : "memory");
+                        asm volatile("red.shared.add.u32 [%0+4], %1;" ::"r"(lo), "r"(q3) : "memory");
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(lo), "r"(q4) : "memory");
+                    } else if (ie + 1 < E && iu + 1 < U) {
+                        fell_back = true;
+                        atomicMin(fc.fb_box + 0, U - 2 - iu); atomicMax(fc.fb_box + 1, U - 1 - iu);
+                        atomicMin(fc.fb_box + 2, ie); atomicMax(fc.fb_box + 3, ie + 1);
+                        const bool e_in0 = (unsigned)cex < (unsigned)fc.ww, e_in1 = (unsigned)(cex + 1) < (unsigned)fc.ww;
+                        const bool u_in0 = (unsigned)cux < (unsigned)fc.wh, u_in1 = (unsigned)(cux + 1) < (unsigned)fc.wh;
+                        unsigned* g_hi = out_u + (size_t)(U - 1 - (iu + 1)) * E + ie;
+                        unsigned* g_lo = g_hi + E;
+                        unsigned* b = fc.win_u + cux * fc.ww + cex;
+                        if (u_in1 && e_in0) atomicAdd(b + fc.ww, q1); else atomicAdd(g_hi, q1);
+                        if (u_in1 && e_in1) atomicAdd(b + fc.ww + 1, q2); else atomicAdd(g_hi + 1, q2);
+                        if (u_in0 && e_in1) atomicAdd(b + 1, q3); else atomicAdd(g_lo + 1, q3);
+                        if (u_in0 && e_in0) atomicAdd(b, q4); else atomicAdd(g_lo, q4);
+                    }
+                }
+            }
+        }
+    }
+    const int cnt_valid = n_reg_points * R - cnt_bad;
+    cnt_lam_out = BLK ? cnt_lam : cnt_valid; cnt_int_out = BLK ? cnt_int : cnt_valid; cnt_blk_out = cnt_blk; fell_back_out = fell_back;
+    n_irregular_out = any_irr ? 1 : 0;
+}
+
 // DEFER: pass 1 of a blocking trace (BLK is false then): shadow-affected points are recorded in `dc` and skipped,
 // completely shadowed ones counted without taps.  A compile-time switch so that the plain kernels carry none of it.
 template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK, bool REVEN, bool DEFER = false>
@@ -837,7 +1077,7 @@ __device__ __forceinline__ void fwd_rays_planar_fast2(const TraceParams& prm, co
     n_irregular_out = any_irr ? 1 : 0;
 }
 
-template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK>
+template <int THREADS, int TRIG, bool DBG, bool FP32ACC, bool BLK, bool MAP = false>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_fwd_kernel(const TraceParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -868,11 +1108,7 @@ trace_fwd_kernel(const TraceParams prm) {
     // 0), orientation (threads 32..47), incident direction and the window-sample rows (every thread); meanwhile the
     // whole shared-memory window is cleared
     long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
-#ifdef AB200_NO_SRC_ROWS
-    const int hs = h;
-#else
-    const int hs = prm.a.src_rows ? __ldg(prm.a.src_rows + h) : h;   // activation index map: surface row of this sample
-#endif
+    const int hs = MAP ? __ldg(prm.a.src_rows + h) : h;   // activation index map: surface row of this sample
     const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hs * P;
     const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hs * P;
     WindowSamples ws;
@@ -886,7 +1122,7 @@ trace_fwd_kernel(const TraceParams prm) {
         fb_box[0] = 1 << 30; fb_box[1] = -1; fb_box[2] = 1 << 30; fb_box[3] = -1;
     }
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
-    if (tid == 64) set_next_sample(next_sh, prm, li);
+    if (tid == 64) set_next_sample<MAP>(next_sh, prm, li);
     {
         uint4* w4 = reinterpret_cast<uint4*>(smem_raw);
         const int n4 = prm.win_cap >> 2;
@@ -985,9 +1221,11 @@ trace_fwd_kernel(const TraceParams prm) {
         int n_irr = 0;
 #if AB200_PACKED_RAYS
         if ((R & 1) == 0)
-            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, true, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
+            if (BLK) fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, true, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
+            else fwd_rays_planar_fast2_plain<THREADS, TRIG, DBG, FP32ACC, false, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
         else
-            fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, false, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
+            if (BLK) fwd_rays_planar_fast2<THREADS, TRIG, DBG, FP32ACC, false, false, true>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr, rec);
+            else fwd_rays_planar_fast2_plain<THREADS, TRIG, DBG, FP32ACC, false, false>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #else   // tuning build without the packed loops: the scalar fast loop evaluates the mask inline, nothing is deferred
         fwd_rays_planar_fast<THREADS, TRIG, DBG, FP32ACC, BLK>(prm, T, fc, src, h, p_begin, p_end, i0, i1, i2, cnt_lam, cnt_int, cnt_blk, fell_back, n_irr);
 #endif
@@ -1806,7 +2044,7 @@ __device__ __forceinline__ void bwd_rays_planar_fast2(const TraceParams& prm, co
     n_irregular_out = any_irr ? 1 : 0;
 }
 
-template <int THREADS, int TRIG, bool BLK>
+template <int THREADS, int TRIG, bool BLK, bool MAP = false>
 __global__ void __launch_bounds__(THREADS, (THREADS > 512 ? 1 : 2))
 trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, const long long grad_stride,
                  float* __restrict__ grad_points, float* __restrict__ grad_normals, float* __restrict__ grad_prims,
@@ -1837,7 +2075,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
     // start-up loads issued together before the first barrier (see trace_fwd_kernel)
     PointSrc src;
-    const int hs = prm.a.src_rows ? __ldg(prm.a.src_rows + h) : h;   // activation index map (the GRADIENT rows stay per sample)
+    const int hs = MAP ? __ldg(prm.a.src_rows + h) : h;   // activation index map (the GRADIENT rows stay per sample)
     src.pts = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hs * P;
     src.nrm = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hs * P;
     src.O = prm.a.orientations ? O_sh : nullptr;
@@ -1850,7 +2088,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
                 i2 = __ldg(prm.a.incident + 4 * h + 2);
     if (tid == 0) load_target(T_sh, prm.a.targets, prm.a.target_idx[h], E, U);
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
-    if (tid == 64) set_next_sample(next_sh, prm, li);
+    if (tid == 64) set_next_sample<MAP>(next_sh, prm, li);
     const unsigned stage_bar_s = (unsigned)__cvta_generic_to_shared(&stage_bar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(stage_bar_s), "r"(THREADS) : "memory");
@@ -2151,6 +2389,23 @@ static cudaError_t launch_fwd(const TraceParams& prm, const LaunchPlan& pl, cuda
         kern<<<grid, THREADS, pl.smem_bytes, st>>>(prm);                                                     \
         note_launch();                                                                                       \
     } while (0)
+    if (prm.a.src_rows != nullptr) {   // activation map: production variants with the polynomial trig only
+        if (dbg || fp32acc || TRIG != AB200_TRIG_POLY) return cudaErrorNotSupported;
+        if (TRIG == AB200_TRIG_POLY) {   // (compile-time guard: no MAP instantiations for the other trig modes)
+            auto launch_map = [&](auto kern) -> cudaError_t {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+                if (e != cudaSuccess) return e;
+                e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                if (e != cudaSuccess) return e;
+                kern<<<grid, THREADS, pl.smem_bytes, st>>>(prm);
+                note_launch();
+                return cudaGetLastError();
+            };
+            constexpr int T2 = TRIG == AB200_TRIG_POLY ? TRIG : AB200_TRIG_POLY;
+            return prm.a.blockers.n_blockers > 0 ? launch_map(trace_fwd_kernel<THREADS, T2, false, false, true, true>)
+                                                 : launch_map(trace_fwd_kernel<THREADS, T2, false, false, false, true>);
+        }
+    }
     if (prm.a.blockers.n_blockers > 0) {   // blocking: production variant only
         if (dbg || fp32acc) return cudaErrorNotSupported;
         AB200_LAUNCH_FWD(false, false, true);
@@ -2172,6 +2427,21 @@ static cudaError_t launch_fwd_trig(const TraceParams& prm, const LaunchPlan& pl,
 template <int THREADS, int TRIG>
 static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
                               long long gstride, float* gpts, float* gnrm, float* gprims, float* gori, float* gscratch) {
+    if (prm.a.src_rows != nullptr) {   // activation map: polynomial trig only (see launch_fwd)
+        if (TRIG != AB200_TRIG_POLY) return cudaErrorNotSupported;
+        constexpr int T2 = TRIG == AB200_TRIG_POLY ? TRIG : AB200_TRIG_POLY;
+        auto launch_map = [&](auto kern) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            kern<<<prm.a.n_local * pl.split, THREADS, pl.smem_bytes, st>>>(prm, gflux, gstride, gpts, gnrm, gprims, gori, gscratch);
+            note_launch();
+            return cudaGetLastError();
+        };
+        return prm.a.blockers.n_blockers > 0 ? launch_map(trace_bwd_kernel<THREADS, T2, true, true>)
+                                             : launch_map(trace_bwd_kernel<THREADS, T2, false, true>);
+    }
     if (prm.a.blockers.n_blockers > 0) {
         auto kern = trace_bwd_kernel<THREADS, TRIG, true>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pl.smem_bytes);
@@ -2207,7 +2477,7 @@ static bool v3_enabled() {
     return on;
 }
 static bool v3_eligible(const ab200_trace_args* a, const TraceParams& prm, const LaunchPlan& pl, bool dbg, bool fp32acc) {
-    return v3_enabled() && pl.split == 1 && !dbg && !fp32acc && a->blockers.n_blockers == 0 && a->trig_mode == AB200_TRIG_POLY &&
+    return v3_enabled() && pl.split == 1 && !dbg && !fp32acc && a->blockers.n_blockers == 0 && a->src_rows == nullptr && a->trig_mode == AB200_TRIG_POLY &&
            a->n_rays >= 4 && (a->n_rays & 1) == 0 && (a->n_points & 1) == 0 && a->res_e % 4 == 0 && a->res_e <= v3::kMaxE &&
            a->distortions_planar != nullptr && reinterpret_cast<uintptr_t>(a->distortions_planar) % 8 == 0 &&
            reinterpret_cast<uintptr_t>(a->points) % 16 == 0 &&

@@ -512,7 +512,7 @@ trace_fwd_v3_kernel(const TraceParams prm) {
     const int wh = min(U, prm.win_cap / kPitch);
 
     long long t_phase = (prm.a.stats && tid == 0) ? clock64() : 0;
-    const int hs = prm.a.src_rows ? __ldg(prm.a.src_rows + h) : h;
+    const int hs = h;   // (no activation map on this path: v3_eligible)
     const float4* pts_h = reinterpret_cast<const float4*>(prm.a.points) + (size_t)hs * P;
     const float4* nrm_h = reinterpret_cast<const float4*>(prm.a.normals) + (size_t)hs * P;
     WindowSamples ws;
@@ -524,7 +524,7 @@ trace_fwd_v3_kernel(const TraceParams prm) {
         fb_box[0] = 1 << 30; fb_box[1] = -1; fb_box[2] = 1 << 30; fb_box[3] = -1;
     }
     if (prm.a.orientations && tid >= 32 && tid < 48) O_sh[tid - 32] = __ldg(prm.a.orientations + (size_t)h * 16 + (tid - 32));
-    if (tid == 64) set_next_sample(next_sh, prm, li);
+    if (tid == 64) set_next_sample<false>(next_sh, prm, li);
     {
         uint4* w4 = reinterpret_cast<uint4*>(smem_raw);
         const int n4 = (wh * kPitch) >> 2;

@@ -449,6 +449,11 @@ def trace(points, normals, incident, distortions, target_idx, targets: TargetTen
         trig = _f32(trig, "trig")
     if local_rows is not None:
         local_rows = _i32(local_rows, "local_rows")
+    if activation is not None and (trig is not None or opt.trig_mode != _lib.TRIG_POLY or opt.fp32_accumulate):
+        # the in-kernel index map exists for the production kernels only (polynomial trig, fixed-point bitmap): the strict /
+        # diagnostic modes trace gathered copies, as the reference does (autograd's index_select sums the replicas)
+        rows = activation.rows.long()
+        points, normals, activation = points.index_select(0, rows), normals.index_select(0, rows), None
     if blocking is None:
         return _TraceFn.apply(points, normals, incident, distortions, trig, target_idx, local_rows, targets, opt, None,
                               None, None, None, orientations, activation)
