@@ -11,6 +11,6 @@ python bench.py --steps 2 --warmup 1 --skip-cpu-baseline > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_ncu_launch_list.csv \
     python bench.py --steps 2 --warmup 1 --skip-cpu-baseline > gpurun_out/r2_ncu_launch.log 2>&1
 python tools/profile_trace.py 2048 2 > /dev/null 2>&1 && \
-ncu --set full --import-source on --clock-control none -k regex:'ab200|trace_|nurbs_|bitmaps_' --launch-skip 9 --launch-count 9 \
+ncu --set full --import-source on --clock-control none -k regex:'trace_|nurbs_|bitmaps_per' --launch-skip 5 --launch-count 5 \
     -o gpurun_out/r2_final_all -f python tools/profile_trace.py 2048 2 > gpurun_out/r2_ncu_full.log 2>&1
-tail -2 gpurun_out/r2_ncu_full.log
+grep "Profiling" gpurun_out/r2_ncu_full.log | cut -c1-80
