@@ -14,7 +14,7 @@ LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libartist_b200.so")
 # tuning only: AB200_LIB points at a pre-built variant of the library (tools/build_variants.sh)
 LIB_OVERRIDE = os.environ.get("AB200_LIB")
-SOURCES = ["trace.cu", "nurbs.cu", "kinematics.cu", "blocking.cu", "geometry.cu", "flux.cu", "sampling.cu"]
+SOURCES = ["trace.cu", "trace_bwd.cu", "nurbs.cu", "kinematics.cu", "blocking.cu", "geometry.cu", "flux.cu", "sampling.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

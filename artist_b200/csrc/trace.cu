@@ -10,6 +10,9 @@
 // bit-reproducible run to run.  Rays that fall outside the window use integer REDG atomics on
 // the (pre-zeroed) output row itself, which is converted to fp32 in place afterwards.
 #include <cstdint>
+#ifndef AB200_TU_BWD
+#define AB200_TU_FWD 1   // this file alone = the forward half (see trace_bwd.cu)
+#endif
 #include <atomic>
 #include <cstdarg>
 #include <cstring>
@@ -19,6 +22,7 @@
 
 namespace ab200 {
 
+#ifndef AB200_TU_BWD   // (defined once: the forward translation unit; trace_bwd.cu compiles this file with AB200_TU_BWD)
 static thread_local char g_error_detail[512] = "";
 
 void set_error_detail(const char* fmt, ...) {
@@ -30,12 +34,15 @@ void set_error_detail(const char* fmt, ...) {
 
 static std::atomic<long long> g_kernel_launches{0};
 void note_launch(int n) { g_kernel_launches.fetch_add(n, std::memory_order_relaxed); }
+#endif
 
+#ifndef AB200_TU_BWD
 int sm_count() {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
 }
+#endif
 
 struct TraceParams {
     ab200_trace_args a;
@@ -1411,6 +1418,7 @@ trace_fwd_kernel(const TraceParams prm) {
     }
 }
 
+#ifndef AB200_TU_BWD   // (forward half only)
 // split mode only: integer bitmap / counters -> fp32, in place
 __global__ void finalize_split_kernel(const TraceParams prm) {
     const int li = blockIdx.y;
@@ -1445,6 +1453,7 @@ __global__ void finalize_split_fp32_kernel(const TraceParams prm) {
     prm.a.intercept[h] = sdiv((float)c1, rp);
     prm.a.blocking[h] = sdiv((float)c2, rp);
 }
+#endif  // !AB200_TU_BWD
 
 // ---------------------------------------------------------------------------------------------
 // backward
@@ -2262,6 +2271,7 @@ trace_bwd_kernel(const TraceParams prm, const float* __restrict__ grad_flux, con
     }
 }
 
+#ifndef AB200_TU_FWD
 // Blocker gradients, second stage: row k of the primitive table = the sum of the per-CTA rows of every CTA whose sample has
 // primitive k in its candidate list, in a fixed order (one warp per primitive: lane l takes CTAs l, l + 32, ... in
 // ascending order, then a shuffle tree) - no atomics, reproducible.  OVERWRITES grad_prims.
@@ -2294,7 +2304,11 @@ __global__ void __launch_bounds__(256) blocker_grad_reduce_kernel(const float* _
     }
 }
 
+#endif  // !AB200_TU_FWD
+
+#ifndef AB200_TU_BWD
 #include "trace_v3.cuh"
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -2376,6 +2390,7 @@ static void fill_params(TraceParams& prm, const ab200_trace_args* a, const Launc
                          a->ray_magnitude <= 1e6f && a->one_minus_extinction <= 1e6f && a->reflectivity <= 1e6f) ? 1 : 0;
 }
 
+#ifndef AB200_TU_BWD
 template <int THREADS, int TRIG>
 static cudaError_t launch_fwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, bool dbg, bool fp32acc) {
     const int grid = prm.a.n_local * pl.split;
@@ -2424,6 +2439,9 @@ static cudaError_t launch_fwd_trig(const TraceParams& prm, const LaunchPlan& pl,
     }
 }
 
+#endif  // !AB200_TU_BWD
+
+#ifndef AB200_TU_FWD
 template <int THREADS, int TRIG>
 static cudaError_t launch_bwd(const TraceParams& prm, const LaunchPlan& pl, cudaStream_t st, const float* gflux,
                               long long gstride, float* gpts, float* gnrm, float* gprims, float* gori, float* gscratch) {
@@ -2471,6 +2489,9 @@ static cudaError_t launch_bwd_trig(const TraceParams& prm, const LaunchPlan& pl,
     }
 }
 
+#endif  // !AB200_TU_FWD
+
+#ifndef AB200_TU_BWD
 // The v3 kernels (trace_v3.cuh) cover the benchmark-shaped case; everything else runs the general kernels above.
 static bool v3_enabled() {
     static const bool on = [] { const char* v = getenv("AB200_TRACE_V3"); return !(v && v[0] == '0'); }();
@@ -2496,10 +2517,13 @@ static cudaError_t launch_fwd_v3(const TraceParams& prm, const LaunchPlan& pl, c
     return cudaGetLastError();
 }
 
+#endif  // !AB200_TU_BWD
+
 }  // namespace ab200
 
 using namespace ab200;
 
+#ifndef AB200_TU_BWD
 extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
     int32_t rc = validate(a);
     if (rc != AB200_OK) return rc;
@@ -2545,6 +2569,9 @@ extern "C" int32_t ab200_trace_fwd(const ab200_trace_args* a, void* stream) {
     return AB200_OK;
 }
 
+#endif  // !AB200_TU_BWD
+
+#ifndef AB200_TU_FWD
 extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) {
     AB200_REQUIRE(b != nullptr, AB200_EINVAL, "args is NULL");
     const ab200_trace_args* a = &b->fwd;
@@ -2588,6 +2615,9 @@ extern "C" int32_t ab200_trace_bwd(const ab200_trace_bwd_args* b, void* stream) 
     return AB200_OK;
 }
 
+#endif  // !AB200_TU_FWD
+
+#ifndef AB200_TU_BWD
 extern "C" int32_t ab200_abi_version(void) { return AB200_ABI_VERSION; }
 
 extern "C" int64_t ab200_kernel_launch_count(void) { return ab200::g_kernel_launches.load(); }
@@ -2659,3 +2689,4 @@ extern "C" int32_t ab200_debug_trig(const float* angles, int32_t n, int32_t mode
     AB200_CUDA_TRY(cudaGetLastError());
     return AB200_OK;
 }
+#endif  // !AB200_TU_BWD

@@ -12,11 +12,17 @@ pids=()
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   (
+    extra=""
+    if [ $SRC = trace ]; then   # the trace kernels are two translation units (trace.cu = forward half, trace_bwd.cu)
+      nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $flags \
+        -c artist_b200/csrc/trace_bwd.cu -o artist_b200/lib/variants/trace_bwd_$name.o &
+      extra=artist_b200/lib/variants/trace_bwd_$name.o
+    fi
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $flags \
-      -c artist_b200/csrc/$SRC.cu -o artist_b200/lib/variants/${SRC}_$name.o &&
+      -c artist_b200/csrc/$SRC.cu -o artist_b200/lib/variants/${SRC}_$name.o && wait &&
     nvcc -shared -gencode arch=compute_100a,code=sm_100a -o artist_b200/lib/variants/$name.so \
-      artist_b200/lib/variants/${SRC}_$name.o $(for o in trace nurbs kinematics blocking geometry flux sampling; do [ $o = $SRC ] || echo artist_b200/lib/$o.o; done) &&
-    rm artist_b200/lib/variants/${SRC}_$name.o && echo "built $name ($flags)"
+      artist_b200/lib/variants/${SRC}_$name.o $extra $(for o in trace trace_bwd nurbs kinematics blocking geometry flux sampling; do [ $o = $SRC ] || { [ $SRC = trace ] && [ $o = trace_bwd ]; } || echo artist_b200/lib/$o.o; done) &&
+    rm -f artist_b200/lib/variants/${SRC}_$name.o $extra && echo "built $name ($flags)"
   ) &
   pids+=($!)
 done
