@@ -152,3 +152,37 @@ def test_blocking_one_cta_per_sample_kernels_equal_split_mode():
     rows = torch.tensor(HeliostatRayTracer._corner_rows(base_p.shape[1]), device=DEV)
     ca, cb = out[True][4][:, rows], out[False][4][:, rows]
     assert cb.abs().max() > 0 and (ca - cb).abs().max() <= 1e-4 * cb.abs().max()
+
+
+@pytest.mark.parametrize("one_cta", [False, True])
+def test_blocking_with_the_sampler_sharding_adds_up_to_the_unsharded_trace(one_cta):
+    """``HeliostatRayTracer(world_size=2, rank=r)`` with blocking on: each rank traces its rows (the blockers are ALL
+    heliostats on every rank), rows of the other rank are zero, and the two ranks together give exactly the unsharded
+    bitmaps, factors and - summed - gradients (incl. the blockers' corner rows)."""
+    from artist_b200 import HeliostatRayTracer
+
+    res = (64, 64)
+    ft, scenario, group, mask, tidx, inc = _scene(n=9, ppf=(12, 12), rays=6)
+    base_p, base_n = group.active_surface_points.detach().clone(), group.active_surface_normals.detach().clone()
+    torch.manual_seed(6)
+    wgt = torch.rand(9, res[1], res[0], device=DEV)
+
+    def run(world, rank):
+        p, n = base_p.clone().requires_grad_(True), base_n.clone().requires_grad_(True)
+        group.active_surface_points, group.active_surface_normals = p, n
+        tracer = HeliostatRayTracer(scenario, group, blocking_active=True, world_size=world, rank=rank,
+                                    bitmap_resolution=torch.tensor(res))
+        tracer._force_one_cta_per_sample = one_cta
+        flux, ic, ot, bl = tracer.trace_rays(inc, mask, tidx)
+        (flux * wgt).sum().backward()
+        return tracer.get_sampler_indices().tolist(), flux.detach(), ic, ot, bl, p.grad, n.grad
+
+    _, full, fic, fot, fbl, gp, gn = run(1, 0)
+    parts = [run(2, r) for r in (0, 1)]
+    assert sorted(parts[0][0] + parts[1][0]) == list(range(9))
+    for rows, flux, ic, ot, bl, _, _ in parts:
+        other = [k for k in range(9) if k not in rows]
+        assert torch.equal(flux[rows], full[rows]) and flux[other].abs().max() == 0
+        assert torch.equal(ic[rows], fic[rows]) and torch.equal(ot[rows], fot[rows]) and torch.equal(bl[rows], fbl[rows])
+    for full_g, a, b in ((gp, parts[0][5], parts[1][5]), (gn, parts[0][6], parts[1][6])):
+        assert (a + b - full_g).abs().max() <= 2e-5 * full_g.abs().max()
