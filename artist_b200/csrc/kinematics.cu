@@ -4,6 +4,8 @@
 // Reference: artist/field/kinematics_rigid_body.py:194-324 (forward kinematics), :326-508 (closed
 // form inverse), :540-634 (fixed-point alignment); artist/field/actuators_linear.py:79-370;
 // artist/field/heliostat_group_rigid_body.py:217-222 (apply); artist/geometry/transforms.py:86-273.
+#include <cooperative_groups.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ab200 {
@@ -306,13 +308,12 @@ struct AlignFlags {
     int pad;
 };
 
-__global__ void kin_align_forward_kernel(const ab200_kinematics_args k, const float* __restrict__ incident,
-                                         const float* __restrict__ aim, int it, float min_eps, float* __restrict__ out,
-                                         float* __restrict__ motor_io, float* __restrict__ scratch) {
-    AlignFlags* fl = reinterpret_cast<AlignFlags*>(scratch + (size_t)4 * k.n);
-    if (fl->done) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= k.n) return;
+// forward kinematics of heliostat i at its current motor positions: orientation out, loss and desired normal to scratch;
+// returns whether the heliostat is still "open" (first iteration, or its loss moved by more than min_eps)
+__device__ __forceinline__ bool align_forward_one(const ab200_kinematics_args& k, const float* __restrict__ incident,
+                                                  const float* __restrict__ aim, int i, int it, float min_eps,
+                                                  float* __restrict__ out, float* __restrict__ motor_io,
+                                                  float* __restrict__ scratch) {
     if (it == 0) { motor_io[(size_t)i * 2] = 0.f; motor_io[(size_t)i * 2 + 1] = 0.f; }
     float th[2];
     joint_angles(k, i, motor_io, th, nullptr, nullptr, nullptr);
@@ -327,9 +328,29 @@ __global__ void kin_align_forward_kernel(const ab200_kinematics_args k, const fl
     float wn[3] = {-incident[(size_t)i * 4] + wr[0], -incident[(size_t)i * 4 + 1] + wr[1], -incident[(size_t)i * 4 + 2] + wr[2]};
     normalize3(wn, 1e-8f);
     const float loss = (fabsf(wn[0] - cn[0]) + fabsf(wn[1] - cn[1]) + fabsf(wn[2] - cn[2]) + fabsf(cn[3])) / 4.0f;
-    if (it == 0 || !(fabsf(scratch[i] - loss) <= min_eps)) fl->open[it] = 1;   // benign race: everybody writes 1
+    const bool open = it == 0 || !(fabsf(scratch[i] - loss) <= min_eps);
     scratch[i] = loss;
     scratch[(size_t)k.n + 3 * i] = wn[0]; scratch[(size_t)k.n + 3 * i + 1] = wn[1]; scratch[(size_t)k.n + 3 * i + 2] = wn[2];
+    return open;
+}
+
+__device__ __forceinline__ void align_inverse_one(const ab200_kinematics_args& k, int i, float* __restrict__ motor_io,
+                                                  const float* __restrict__ scratch) {
+    const float wn[3] = {scratch[(size_t)k.n + 3 * i], scratch[(size_t)k.n + 3 * i + 1], scratch[(size_t)k.n + 3 * i + 2]};
+    float mo[2];
+    motor_from_normal(k, i, wn, mo);
+    motor_io[(size_t)i * 2] = mo[0];
+    motor_io[(size_t)i * 2 + 1] = mo[1];
+}
+
+__global__ void kin_align_forward_kernel(const ab200_kinematics_args k, const float* __restrict__ incident,
+                                         const float* __restrict__ aim, int it, float min_eps, float* __restrict__ out,
+                                         float* __restrict__ motor_io, float* __restrict__ scratch) {
+    AlignFlags* fl = reinterpret_cast<AlignFlags*>(scratch + (size_t)4 * k.n);
+    if (fl->done) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= k.n) return;
+    if (align_forward_one(k, incident, aim, i, it, min_eps, out, motor_io, scratch)) fl->open[it] = 1;   // benign race: everybody writes 1
 }
 
 __global__ void kin_align_inverse_kernel(const ab200_kinematics_args k, int it, float* __restrict__ motor_io,
@@ -343,14 +364,38 @@ __global__ void kin_align_inverse_kernel(const ab200_kinematics_args k, int it, 
         return;
     }
     if (i >= k.n) return;
-    const float wn[3] = {scratch[(size_t)k.n + 3 * i], scratch[(size_t)k.n + 3 * i + 1], scratch[(size_t)k.n + 3 * i + 2]};
-    float mo[2];
-    motor_from_normal(k, i, wn, mo);
-    motor_io[(size_t)i * 2] = mo[0];
-    motor_io[(size_t)i * 2 + 1] = mo[1];
+    align_inverse_one(k, i, motor_io, scratch);
 }
 
-// ---- apply orientation to the surface (align) --------------------------------------------------
+// The whole loop in ONE launch for fields of up to kAlignClusterMax heliostats: one thread-block CLUSTER of 8 CTAs x 512
+// threads, one heliostat per thread through all sweeps (forward and inverse kinematics of a heliostat never need another
+// thread's data); the reference's "stop when ALL heliostats converged" (kinematics_rigid_body.py:621-625) is a
+// __syncthreads_or per CTA plus a vote over the cluster through distributed shared memory - two cluster barriers per sweep
+// instead of two kernel launches.  Same per-heliostat code as the two kernels above (bit-identical results).  (One CTA alone
+// was slower than the eight launches: the per-heliostat chain of asin / atan2 / divisions is latency-bound on one SM.)
+constexpr int kAlignClusterCtas = 8, kAlignClusterThreads = 512, kAlignClusterMax = kAlignClusterCtas * kAlignClusterThreads;
+__global__ void __cluster_dims__(kAlignClusterCtas, 1, 1) __launch_bounds__(kAlignClusterThreads)
+kin_align_cluster_kernel(const ab200_kinematics_args k, const float* __restrict__ incident, const float* __restrict__ aim,
+                         int max_iterations, float min_eps, float* __restrict__ out, float* __restrict__ motor_io,
+                         float* __restrict__ scratch) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ int open_sh;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool mine = i < k.n;
+    for (int it = 0; it < max_iterations; ++it) {
+        const bool open = mine && align_forward_one(k, incident, aim, i, it, min_eps, out, motor_io, scratch);
+        const int cta_open = __syncthreads_or(open);
+        if (threadIdx.x == 0) open_sh = cta_open;
+        cluster.sync();                                   // every CTA's vote is visible
+        int any_open = 0;
+        for (int r = 0; r < kAlignClusterCtas; ++r) any_open |= *cluster.map_shared_rank(&open_sh, r);
+        cluster.sync();                                   // ... and read, before the next sweep overwrites it
+        if (!any_open && it > 0) break;                   // uniform over the cluster
+        if (mine) align_inverse_one(k, i, motor_io, scratch);
+    }
+}
+
 __global__ void __launch_bounds__(256) align_fwd_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm,
                                                         const float* __restrict__ ori, const int* __restrict__ src_row,
                                                         int n_points, float4* __restrict__ out_p, float4* __restrict__ out_n) {
@@ -515,6 +560,13 @@ extern "C" int32_t ab200_kinematics_align_incident(const ab200_kinematics_args* 
     if (k->n == 0) return AB200_OK;
     AB200_REQUIRE(max_iterations <= 6, AB200_ELIMIT, "max_iterations > 6");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (k->n <= kAlignClusterMax && !getenv("AB200_ALIGN_MULTI_KERNEL")) {
+        kin_align_cluster_kernel<<<kAlignClusterCtas, kAlignClusterThreads, 0, st>>>(*k, incident, aim, max_iterations, min_eps,
+                                                                                  orientations, motor_positions, scratch);
+        note_launch();
+        AB200_CUDA_TRY(cudaGetLastError());
+        return AB200_OK;
+    }
     AB200_CUDA_TRY(cudaMemsetAsync(scratch + (size_t)4 * k->n, 0, sizeof(AlignFlags), st));
     const int blocks = (k->n + 63) / 64;
     for (int it = 0; it < max_iterations; ++it) {

@@ -299,3 +299,29 @@ def test_range_guarded_division_is_ieee_exact():
     qf, qi = ops.debug_div_regular(num, den)
     bad = (qf != qi).sum().item()
     assert bad == 0, f"{bad} of {n} quotients differ"
+
+
+@pytest.mark.parametrize("n", [5, 1500])
+def test_single_launch_alignment_equals_the_multi_kernel_loop(n, monkeypatch):
+    """``ab200_kinematics_align_incident``: the cluster kernel that runs all sweeps in one launch (8 CTAs, fields up to 4096 heliostats)
+    against the two-kernels-per-sweep loop (``AB200_ALIGN_MULTI_KERNEL``) - same per-heliostat code, identical bits."""
+    from artist_b200 import build_synthetic_scenario
+
+    dev = torch.device("cuda:0")
+
+    def run():
+        scenario, group = build_synthetic_scenario(n, number_of_rays=2, points_per_facet=(4, 4), device=dev)
+        mask, tidx, _ = scenario.index_mapping(group)
+        torch.manual_seed(1)
+        inc = torch.nn.functional.normalize(torch.tensor([[0.0, 0.9, -0.43, 0.0]], device=dev)
+                                            + 0.2 * torch.randn(n, 4, device=dev) * torch.tensor([1.0, 1.0, 1.0, 0.0], device=dev), dim=1)
+        group.activate_heliostats(mask)
+        aim = scenario.solar_tower.get_centers_of_target_areas(tidx)
+        ori = group.kinematics.incident_ray_directions_to_orientations(incident_ray_directions=inc, aim_points=aim)
+        return ori.clone(), group.kinematics.active_motor_positions.clone()
+
+    one = run()
+    monkeypatch.setenv("AB200_ALIGN_MULTI_KERNEL", "1")
+    multi = run()
+    assert torch.isfinite(one[0]).all() and one[1].abs().max() > 0
+    assert torch.equal(one[0], multi[0]) and torch.equal(one[1], multi[1])
