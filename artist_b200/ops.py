@@ -257,6 +257,7 @@ trace_stats: torch.Tensor | None = None  # set to a zeroed int64[20] CUDA tensor
 
 last_blocking_overflow: torch.Tensor | None = None  # int32[1]: samples whose candidate list overflowed (must stay 0)
 _overflow_pending: list = []   # (pinned host int32[1], event, max_candidates) of earlier calls, checked without a sync
+_overflow_pool: list = []      # recycled (pinned flag, event) pairs
 
 
 def check_blocking_overflow(wait: bool = False) -> None:
@@ -271,10 +272,12 @@ def check_blocking_overflow(wait: bool = False) -> None:
         if wait:
             ev.synchronize()
         if ev.query():
-            if int(host[0]) != 0:
+            value = int(host[0])
+            _overflow_pool.append((host, ev))
+            if value != 0:
                 _overflow_pending.clear()
                 raise _lib.Ab200Error(
-                    f"blocking: {int(host[0])} heliostat-sample(s) have more than {cap} candidate blockers between them and "
+                    f"blocking: {value} heliostat-sample(s) have more than {cap} candidate blockers between them and "
                     f"their target; the candidate list is limited to {cap} (kMaxBlockCandidates = 64) and the flux would "
                     "silently miss the dropped rectangles")
         else:
@@ -306,9 +309,12 @@ def _prepare_blocking(bi: BlockingInputs, opt: TraceOptions, n: int, dev):
         # capture needs have checked this geometry, and `last_blocking_overflow` stays readable after a replay
         return prims, cand_idx, cand_count
     check_blocking_overflow()                      # flags of earlier calls that have arrived by now
-    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    # (pinned flags and events come from a small pool: a pinned allocation per call is a cudaHostAlloc, which serialises
+    # with the device - measured as +1.3 ms per step in the end-to-end leg of the motor workload)
+    if len(_overflow_pending) >= 64:               # nobody collected for a long time: wait for the oldest
+        check_blocking_overflow(wait=True)
+    host, ev = _overflow_pool.pop() if _overflow_pool else (torch.empty(1, dtype=torch.int32, pin_memory=True), torch.cuda.Event())
     host.copy_(overflow, non_blocking=True)
-    ev = torch.cuda.Event()
     ev.record()
     _overflow_pending.append((host, ev, int(bi.max_candidates)))
     return prims, cand_idx, cand_count
