@@ -29,10 +29,10 @@ def test_nurbs_forward_bit_equal_points(canting, cps, ppf):
     surf = NURBSSurfaces(ft["nurbs_degrees"], ft["nurbs_control_points"].to(DEV), device=torch.device(DEV))
     gp, gn = surf.calculate_surface_points_and_normals(ev.to(DEV), None if cant is None else cant.to(DEV),
                                                        None if tr is None else tr.to(DEV))
-    # points follow the reference's op order exactly; normals go through a vector norm whose CPU
-    # accumulation is not reproducible op by op (<= 1 ulp differences)
+    # points AND normals follow the reference's op order exactly (the cross product with torch's contraction,
+    # the norm as torch's FMA chain: tests/test_oracle_kat.py::test_cpu_cross_product_rounding_the_kernels_reproduce)
     assert torch.equal(gp.cpu(), pts), f"max diff {(gp.cpu() - pts).abs().max():.3e}"
-    assert (gn.cpu() - nrm).abs().max() <= 2.4e-7
+    assert torch.equal(gn.cpu(), nrm), f"max diff {(gn.cpu() - nrm).abs().max():.3e}"
 
 
 @pytest.mark.parametrize("cps,ppf,deg,canting", [
@@ -63,7 +63,7 @@ def test_nurbs_forward_column_walk_equals_row_table_kernel(cps, ppf, deg, cantin
     assert torch.equal(res["cols"][0], res["rowtable"][0]) and torch.equal(res["cols"][1], res["rowtable"][1])
     pts, nrm = O.nurbs_points_and_normals(ft["nurbs_control_points"], deg[0], deg[1], ev, cant, tr)
     assert torch.equal(res["cols"][0], pts), f"max diff {(res['cols'][0] - pts).abs().max():.3e}"
-    assert (res["cols"][1] - nrm).abs().max() <= 2.4e-7
+    assert torch.equal(res["cols"][1], nrm), f"max diff {(res['cols'][1] - nrm).abs().max():.3e}"
 
 
 def test_nurbs_degree_2_and_shared_grid():

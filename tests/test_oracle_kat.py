@@ -106,3 +106,31 @@ def test_bitmap_loss_kats():
     for pred, gt, want in KL_KATS:
         torch.testing.assert_close(O.kl_divergence_loss(torch.tensor(pred), torch.tensor(gt)), torch.tensor(want), atol=1e-6,
                                    rtol=1e-6)
+
+
+def test_cpu_cross_product_rounding_the_kernels_reproduce():
+    """Parity note behind `cross_comp` (csrc/common.cuh): torch's CPU cross kernel rounds a1*b2 - a2*b1 as
+    fma(a1, b2, -RN(a2*b1)), and normalize() takes the norm as the FMA chain fma(z,z, fma(y,y, x*x)) with a correctly
+    rounded sqrt.  The NURBS normals (surfaces.py:615-661), the canting frame (transforms.py:321-337) and the
+    cylinder frame (geometry.py:299) of the CUDA kernels are built on exactly this sequence; if a torch build ever
+    rounds differently, the bit-exact GPU tests of those rows fail and this test says why."""
+    import numpy as np
+
+    g = torch.Generator().manual_seed(5)
+    a4, b4 = torch.randn(4, 3, 2500, 4, generator=g), torch.randn(4, 3, 2500, 4, generator=g)
+    a, b = a4[..., :3], b4[..., :3]                      # strided views, as the oracle's s10[..., :3]
+    f64 = lambda t: t.numpy().astype(np.float64)
+    f32 = lambda x: x.astype(np.float32)
+
+    def comp(i, j):   # fma(a_i, b_j, -RN(a_j * b_i)): product exact in double, one rounding to float
+        return f32(f64(a[..., i]) * f64(b[..., j]) - f64(torch.from_numpy(f32(f64(a[..., j]) * f64(b[..., i])))))
+
+    want = np.stack([comp(1, 2), comp(2, 0), comp(0, 1)], axis=-1)
+    got = torch.linalg.cross(a, b)
+    assert np.array_equal(got.numpy(), want)
+    x, y, z = (want[..., k] for k in range(3))
+    chain = f32(f64(torch.from_numpy(f32(f64(torch.from_numpy(f32(x.astype(np.float64) ** 2)))
+                                         + y.astype(np.float64) ** 2))) + z.astype(np.float64) ** 2)
+    norm = np.sqrt(chain.astype(np.float64)).astype(np.float32)
+    unit = want / np.maximum(norm, np.float32(1e-12))[..., None]
+    assert np.array_equal(torch.nn.functional.normalize(got, dim=3).numpy(), unit)
