@@ -18,10 +18,11 @@ __global__ void blocking_pack_kernel(const float* __restrict__ corners, const fl
         p.sv[q] = spans[(size_t)i * 6 + 3 + q];
         p.n[q] = normals[(size_t)i * 3 + q];
     }
-    p.uu = p.su[0] * p.su[0] + p.su[1] * p.su[1] + p.su[2] * p.su[2];
-    p.vv = p.sv[0] * p.sv[0] + p.sv[1] * p.sv[1] + p.sv[2] * p.sv[2];
-    p.uv = p.su[0] * p.sv[0] + p.su[1] * p.sv[1] + p.su[2] * p.sv[2];
-    float det = p.uu * p.vv - p.uv * p.uv;
+    // blocking.py:333-341 in its operation order (each product and sum rounded, left to right): block_tuv_strict
+    p.uu = dot3_strict(p.su[0], p.su[1], p.su[2], p.su[0], p.su[1], p.su[2]);
+    p.vv = dot3_strict(p.sv[0], p.sv[1], p.sv[2], p.sv[0], p.sv[1], p.sv[2]);
+    p.uv = dot3_strict(p.su[0], p.su[1], p.su[2], p.sv[0], p.sv[1], p.sv[2]);
+    float det = ssub(smul(p.uu, p.vv), smul(p.uv, p.uv));
     if (fabsf(det) < epsilon) det = (det > 0.f ? 1.f : (det < 0.f ? -1.f : 0.f)) * epsilon;   // torch.sign(det) * eps
     p.det = det;
     reinterpret_cast<BlockPrimPacked*>(prims)[i] = p;

@@ -85,12 +85,41 @@ __device__ __forceinline__ void block_tuv(const BlockHot& p, float eps, float o0
     v = f0 * p.Vx + f1 * p.Vy + f2 * p.Vz;
 }
 
+// The same intersection in the reference's own operation order (blocking.py:318-346: every product and sum its own
+// rounding, sums over the three components left to right, IEEE divisions) - torch's CPU evaluation reproduced bit for bit
+// (checked op by op against torch 2.11 CPU).  The soft mask multiplies the rectangle coordinates by softness (1000) and
+// the optical depth by alpha (100): one ulp of u or v is up to 1e-4 of `blocked`, so the rays that are actually
+// evaluated (block_eval / block_backward, a few per cent) take this path; culling and classification, which only
+// compare against margins, keep the short form above.
+__device__ __forceinline__ float dot3_strict(float a0, float a1, float a2, float b0, float b1, float b2) {
+    return sadd(sadd(smul(a0, b0), smul(a1, b1)), smul(a2, b2));
+}
+__device__ __forceinline__ void block_tuv_strict(const BlockPrim& p, float eps, float o0, float o1, float o2, float d0, float d1,
+                                                 float d2, float& t, float& u, float& v, float& den) {
+    den = dot3_strict(d0, d1, d2, p.n[0], p.n[1], p.n[2]);
+    if (fabsf(den) < eps) den = den >= 0.0f ? eps : -eps;
+    const float num = dot3_strict(ssub(p.c0[0], o0), ssub(p.c0[1], o1), ssub(p.c0[2], o2), p.n[0], p.n[1], p.n[2]);
+    t = sdiv(num, den);
+    const float f0 = ssub(sadd(o0, smul(t, d0)), p.c0[0]), f1 = ssub(sadd(o1, smul(t, d1)), p.c0[1]),
+                f2 = ssub(sadd(o2, smul(t, d2)), p.c0[2]);
+    const float pu = dot3_strict(f0, f1, f2, p.su[0], p.su[1], p.su[2]), pv = dot3_strict(f0, f1, f2, p.sv[0], p.sv[1], p.sv[2]);
+    u = sdiv(ssub(smul(pu, p.vv), smul(pv, p.uv)), p.det);
+    v = sdiv(ssub(smul(pv, p.uu), smul(pu, p.uv)), p.det);
+}
+
 struct BlockParams {
     float softness, alpha, offset, epsilon;
     float cull_angle;  // bound on the scatter angle used by the per-point cull (<= 0: no per-point culling)
 };
 
 __device__ __forceinline__ float sigmoidf_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// torch.sigmoid as the CPU evaluates it, 1 / (1 + exp(-x)), with the accurate expf and an IEEE division (within an ulp or
+// two of torch's vectorised exp)
+#ifdef AB200_BLOCK_SIGMOID_IEEE
+__device__ __forceinline__ float sigmoidf_ref(float x) { return sdiv(1.0f, sadd(1.0f, expf(-x))); }
+#else
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+#endif
 
 struct BlockGeom {
     float t, u, v, den;
@@ -191,15 +220,16 @@ static __device__ __noinline__ float block_eval(const BlockPrim* prims, unsigned
     while (mask) {
         const int c = __ffsll((long long)mask) - 1;
         mask &= mask - 1;
-        const BlockHot p = block_hot(base + (unsigned)c * (kPrimFloatsShared * 4));
         float t, u, v, den;
-        block_tuv(p, bp.epsilon, o0, o1, o2, d0, d1, d2, t, u, v, den);
+        block_tuv_strict(prims[c], bp.epsilon, o0, o1, o2, d0, d1, d2, t, u, v, den);
         if (!(fminf(fminf(fminf(u, 1.0f - u), fminf(v, 1.0f - v)), t - bp.offset) > -m)) continue;   // contributes < 1e-9
-        const float inside = sigmoidf_fast(k * u) * sigmoidf_fast(k * (1.0f - u)) * sigmoidf_fast(k * v) * sigmoidf_fast(k * (1.0f - v));
-        const float front = sigmoidf_fast(k * (t - bp.offset));
-        sum += fminf(fmaxf(inside * front, 0.0f), 1.0f);
+        // blocking.py:347-353 in its order: ((s(ku) s(k(1-u))) s(kv)) s(k(1-v)), times the front gate, clamped, summed over k
+        const float inside = smul(smul(smul(sigmoidf_ref(smul(k, u)), sigmoidf_ref(smul(k, ssub(1.0f, u)))), sigmoidf_ref(smul(k, v))),
+                                  sigmoidf_ref(smul(k, ssub(1.0f, v))));
+        const float front = sigmoidf_ref(smul(k, ssub(t, bp.offset)));
+        sum = sadd(sum, fminf(fmaxf(smul(inside, front), 0.0f), 1.0f));
     }
-    return 1.0f - __expf(-bp.alpha * sum);
+    return ssub(1.0f, expf(-smul(bp.alpha, sum)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -292,16 +322,16 @@ static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, 
     while (m) {
         const int c = __ffsll((long long)m) - 1;
         m &= m - 1;
-        const BlockHot p = block_hot(base + (unsigned)c * (kPrimFloatsShared * 4));
         float t, u, v, den;
-        block_tuv(p, bp.epsilon, o0, o1, o2, d0, d1, d2, t, u, v, den);
+        block_tuv_strict(prims[c], bp.epsilon, o0, o1, o2, d0, d1, d2, t, u, v, den);   // exactly block_eval's sequence
         if (!(fminf(fminf(fminf(u, 1.0f - u), fminf(v, 1.0f - v)), t - bp.offset) > -m_rel)) continue;
         relevant |= 1ull << c;
-        const float inside = sigmoidf_fast(k * u) * sigmoidf_fast(k * (1.0f - u)) * sigmoidf_fast(k * v) * sigmoidf_fast(k * (1.0f - v));
-        sum += fminf(fmaxf(inside * sigmoidf_fast(k * (t - bp.offset)), 0.0f), 1.0f);
+        const float inside = smul(smul(smul(sigmoidf_ref(smul(k, u)), sigmoidf_ref(smul(k, ssub(1.0f, u)))), sigmoidf_ref(smul(k, v))),
+                                  sigmoidf_ref(smul(k, ssub(1.0f, v))));
+        sum = sadd(sum, fminf(fmaxf(smul(inside, sigmoidf_ref(smul(k, ssub(t, bp.offset)))), 0.0f), 1.0f));
     }
-    const float transmittance = __expf(-bp.alpha * sum);
-    out.blocked = 1.0f - transmittance;
+    const float transmittance = expf(-smul(bp.alpha, sum));
+    out.blocked = ssub(1.0f, transmittance);
     out.go0 = out.go1 = out.go2 = out.gd0 = out.gd1 = out.gd2 = 0.0f;
     // dL/dsum = dL/dblocked * alpha * transmittance
     const float g_sum = g_blocked_scale * bp.alpha * transmittance;
@@ -314,7 +344,7 @@ static __device__ __noinline__ BlockBack block_backward(const BlockPrim* prims, 
         BlockGeom g;
         {   // rectangle coordinates as in the first pass (and in block_eval), plus the offset vector
             const BlockHot hp = block_hot(base + (unsigned)c * (kPrimFloatsShared * 4));
-            block_tuv(hp, bp.epsilon, o0, o1, o2, d0, d1, d2, g.t, g.u, g.v, g.den);
+            block_tuv_strict(p, bp.epsilon, o0, o1, o2, d0, d1, d2, g.t, g.u, g.v, g.den);   // the forward's values
             g.off[0] = fmaf(g.t, d0, o0 - hp.c0x); g.off[1] = fmaf(g.t, d1, o1 - hp.c0y); g.off[2] = fmaf(g.t, d2, o2 - hp.c0z);
         }
         const float su0 = sigmoidf_fast(k * g.u), su1 = sigmoidf_fast(k * (1.0f - g.u));

@@ -41,9 +41,12 @@ def test_blocked_flux_and_factors_match_oracle(res):
     ref, ric, rot, rbl = O.trace_rays(pts, nrm, inc.cpu(), du, de, tidx.cpu(), tg, res, blocking=_oracle_blocking(pts, 9))
     unblocked, *_ = O.trace_rays(pts, nrm, inc.cpu(), du, de, tidx.cpu(), tg, res)
     assert rbl.min() < 0.5 and (unblocked.sum() - ref.sum()) > 0.2 * unblocked.sum(), "scene must be strongly shadowed"
-    assert (flux.cpu() - ref).abs().max() <= 2e-4 * ref.max()
-    assert (bl.cpu() - rbl).abs().max() <= 2.5e-3        # a few rays sit on the 1e-3 threshold of the soft mask
-    assert (ic.cpu() - ric).abs().max() <= 2.5e-3 and (ot.cpu() - rot).abs().max() <= 1e-6
+    # the evaluated rays follow the reference's operation order (block_tuv_strict): no ray changes side of the 1e-3
+    # threshold, the factors are exact; measured flux error 2e-6 .. 4e-6 of peak (round 1: 2e-4 and 2.5e-3)
+    ferr = (flux.cpu() - ref).abs().max() / ref.max()
+    assert ferr <= 2e-5, f"flux {ferr:.3e}"
+    assert (bl.cpu() - rbl).abs().max() <= 1e-6, f"blocking factor {(bl.cpu() - rbl).abs().max():.3e}"
+    assert (ic.cpu() - ric).abs().max() <= 1e-6 and (ot.cpu() - rot).abs().max() <= 1e-6
     # blocking switched off gives the unshadowed flux
     plain = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor(res))
     f0, *_ = plain.trace_rays(inc, mask, tidx)
@@ -76,11 +79,11 @@ def test_blocking_gradients_match_oracle_autograd():
     for got, want, name in ((pts_leaf.grad.cpu(), p.grad, "points"), (nrm_leaf.grad.cpu(), n.grad, "normals")):
         scale = want.abs().max()
         err = (got - want).abs().max() / scale
-        assert err <= 2e-3, f"grad {name}: {err:.3e}"
+        assert err <= 5e-5, f"grad {name}: {err:.3e}"     # measured 1.5e-6 / 6.6e-6 (round 1: 2e-3)
     # the corner rows carry the blocker-geometry gradient: compare them separately (they are tiny next to the rest)
     rows = torch.tensor(HeliostatRayTracer._corner_rows(p.shape[1]))
     gc, wc = pts_leaf.grad.cpu()[:, rows], p.grad[:, rows]
-    assert (gc - wc).abs().max() <= 5e-3 * wc.abs().max()
+    assert (gc - wc).abs().max() <= 5e-5 * wc.abs().max()     # measured 1.5e-6 (round 1: 5e-3)
 
 
 def test_distant_heliostats_do_not_block():

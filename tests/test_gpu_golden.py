@@ -105,5 +105,7 @@ def test_blocking_against_reference_fixture(golden):
                                  ops.pack_distortions(g["dist_u"].to(DEV), g["dist_e"].to(DEV)), g["target_idx"].to(DEV),
                                  _targets(f), opt, trig=trig.contiguous().to(DEV), blocking=bi)
     want = g["batch100"]
-    assert (flux.cpu() - want["flux"]).abs().max() <= 2e-4 * want["flux"].max()
-    assert (bl.cpu() - want["blocking"]).abs().max() <= 2.5e-3 and torch.equal(ot.cpu(), want["on_target"])
+    ferr = (flux.cpu() - want["flux"]).abs().max() / want["flux"].max()
+    # measured against the real reference's output: flux 2.6e-7 of peak, blocking factors identical (round 1: 2e-4, 2.5e-3)
+    assert ferr <= 2e-5, f"flux {ferr:.3e}"
+    assert (bl.cpu() - want["blocking"]).abs().max() <= 1e-6 and torch.equal(ot.cpu(), want["on_target"])
