@@ -134,3 +134,96 @@ def test_cpu_cross_product_rounding_the_kernels_reproduce():
     norm = np.sqrt(chain.astype(np.float64)).astype(np.float32)
     unit = want / np.maximum(norm, np.float32(1e-12))[..., None]
     assert np.array_equal(torch.nn.functional.normalize(got, dim=3).numpy(), unit)
+
+
+def _f32(x):
+    import numpy as np
+    return np.asarray(x, dtype=np.float32)
+
+
+def _dot3_left_to_right(a, b):
+    """sum over the last axis (size 3) of separately rounded products, added left to right - torch's CPU reduction."""
+    p = _f32(a * b)
+    return _f32(_f32(p[..., 0] + p[..., 1]) + p[..., 2])
+
+
+def test_cpu_rounding_sequence_of_the_blocking_geometry():
+    """Parity note behind `block_tuv_strict` (csrc/blocking_device.cuh): the reference's ray/rectangle intersection
+    (blocking.py:318-346) on the CPU is exactly 'every product and sum its own rounding, component sums left to right,
+    IEEE divisions'.  The numpy emulation below is the kernel's instruction sequence; it must equal torch bit for bit."""
+    import numpy as np
+
+    g = torch.Generator().manual_seed(2)
+    B, R, P, K = 2, 3, 400, 5
+    origins = torch.randn(B, P, 4, generator=g) * 5
+    dirs = torch.nn.functional.normalize(torch.randn(B, R, P, 4, generator=g), dim=-1)
+    corners = torch.randn(K, 4, 4, generator=g) * 5
+    su_t, sv_t = corners[:, 1, :3] - corners[:, 0, :3], corners[:, 3, :3] - corners[:, 0, :3]
+    nn_t = torch.nn.functional.normalize(torch.linalg.cross(su_t, sv_t), dim=-1)
+    o = origins[:, None, :, None, :3]
+    d = dirs[:, :, :, None, :3]
+    c0, su, sv, nn = corners[None, None, None, :, 0, :3], su_t[None, None, None], sv_t[None, None, None], nn_t[None, None, None]
+    den = torch.sum(d * nn, dim=-1)
+    t = torch.sum((c0 - o) * nn, dim=-1) / den
+    off = (o + t[..., None] * d) - c0
+    uu, vv, uv = torch.sum(su * su, dim=-1), torch.sum(sv * sv, dim=-1), torch.sum(su * sv, dim=-1)
+    pu, pv = torch.sum(off * su, dim=-1), torch.sum(off * sv, dim=-1)
+    det = uu * vv - uv * uv
+    u = (pu * vv - pv * uv) / det
+    v = (pv * uu - pu * uv) / det
+
+    n = lambda x: x.numpy()
+    DEN = _dot3_left_to_right(n(d), n(nn))
+    T = _f32(_dot3_left_to_right(_f32(n(c0) - n(o)), n(nn)) / DEN)
+    OFF = _f32(_f32(n(o) + _f32(T[..., None] * n(d))) - n(c0))
+    UU, VV, UV = (_dot3_left_to_right(n(a), n(b)) for a, b in ((su, su), (sv, sv), (su, sv)))
+    PU, PV = _dot3_left_to_right(OFF, n(su)), _dot3_left_to_right(OFF, n(sv))
+    DET = _f32(_f32(UU * VV) - _f32(UV * UV))
+    U = _f32(_f32(_f32(PU * VV) - _f32(PV * UV)) / DET)
+    V = _f32(_f32(_f32(PV * UU) - _f32(PU * UV)) / DET)
+    for name, got, want in (("den", DEN, den), ("t", T, t), ("off", OFF, off), ("det", DET, det), ("u", U, u), ("v", V, v)):
+        assert np.array_equal(got, n(want)), name
+
+
+def test_cpu_rounding_sequence_of_the_cylinder_quadratic():
+    """Parity note behind `hit_cylinder` (csrc/trace_device.cuh): frame rows from the contracted cross product, the two
+    GEMMs as FMA chains over k, the quadratic with one rounding per product / sum (geometry.py:299-345).  Up to the
+    discriminant the emulation equals torch bit for bit; the root goes through torch's CPU sqrt, which (MKL VML) is not
+    the IEEE root for a fraction of a per cent of its arguments - the only reason the GPU's hit distance is not
+    bit-identical for every ray."""
+    import numpy as np
+
+    g = torch.Generator().manual_seed(9)
+    N, R, P = 3, 4, 300
+    nn = torch.nn.functional.normalize(torch.tensor([[0.0, 0.9063, -0.4226], [0.3, 0.8, -0.2], [-0.2, 0.9, 0.1]]), dim=-1)
+    ax = torch.nn.functional.normalize(torch.linalg.cross(nn, torch.tensor([[1.0, 0.0, 0.0]]).expand(3, -1)), dim=-1)
+    cc = torch.tensor([[0.0, -3.0, 55.0]]).expand(3, -1) + torch.randn(3, 3, generator=g)
+    o = torch.randn(N, P, 3, generator=g) * 3 + torch.tensor([10.0, 80.0, 2.0])
+    d = torch.nn.functional.normalize(cc[:, None, None, :] - o[:, None, :, :] + 0.05 * torch.randn(N, R, P, 3, generator=g), dim=-1)
+    rad = torch.tensor([4.14, 3.0, 5.5])
+    uu = torch.cross(nn, ax, dim=-1)
+    rot = torch.stack([uu, nn, ax], dim=1)
+    ol = ((o - cc[:, None, :]) @ rot.transpose(1, 2))[:, None, :, :]
+    dl = d @ rot.transpose(1, 2)[:, None, :, :]
+    ox, oy, dx, dy = ol[..., 0], ol[..., 1], dl[..., 0], dl[..., 1]
+    a = dx**2 + dy**2
+    b = 2 * (ox * dx + oy * dy)
+    c = (ox**2 + oy**2 - rad.view(-1, 1, 1) ** 2).repeat(1, R, 1)
+    disc = b**2 - 4 * a * c
+
+    n = lambda x: x.numpy()
+    f64 = lambda x: np.asarray(x, dtype=np.float64)
+    fma = lambda x, y, z: _f32(f64(x) * f64(y) + f64(z))
+    chain = lambda vec, row: fma(vec[..., 2], row[..., 2], fma(vec[..., 1], row[..., 1], _f32(vec[..., 0] * row[..., 0])))
+    q = _f32(n(o) - n(cc)[:, None, :])
+    rows = n(rot)
+    OL = np.stack([chain(q, rows[:, k, :][:, None, :]) for k in range(3)], axis=-1)[:, None]
+    DL = np.stack([chain(n(d), rows[:, k, :][:, None, None, :]) for k in range(3)], axis=-1)
+    assert np.array_equal(OL, n(ol)) and np.array_equal(DL, n(dl))
+    OX, OY, DX, DY = OL[..., 0], OL[..., 1], DL[..., 0], DL[..., 1]
+    A = _f32(_f32(DX * DX) + _f32(DY * DY))
+    Bq = _f32(np.float32(2) * _f32(_f32(OX * DX) + _f32(OY * DY)))
+    C = _f32(_f32(_f32(OX * OX) + _f32(OY * OY)) - _f32(n(rad) * n(rad))[:, None, None])
+    DISC = _f32(_f32(Bq * Bq) - _f32(_f32(np.float32(4) * A) * C))
+    assert np.array_equal(A, n(a)) and np.array_equal(Bq, n(b)) and np.array_equal(DISC, n(disc))
+    assert (n(disc) > 0).mean() > 0.5, "the case must hit the cylinder"
