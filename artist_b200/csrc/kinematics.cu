@@ -20,15 +20,19 @@ __device__ inline M4 m4_identity() {
     for (int i = 0; i < 16; ++i) r.m[i] = (i % 5 == 0) ? 1.f : 0.f;
     return r;
 }
+// Product of two per-heliostat 4x4 matrices as torch's CPU bmm evaluates it for these tiny batched operands (also when
+// one side is a broadcast [1,4,4]): every product rounded, added left to right over k - NOT the FMA chain of the large
+// GEMMs (checked against torch 2.11 CPU, numpy emulation == torch bit for bit on [N,4,4] @ [N,4,4], @ [1,4,4] and
+// [N,4,4]^T @ [N,4,1]; the FMA chain differs in 38 % of the entries).
 __device__ inline M4 m4_mul(const M4& a, const M4& b) {
     M4 r;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float acc = a.m[i * 4] * b.m[j];
+            float acc = smul(a.m[i * 4], b.m[j]);
 #pragma unroll
-            for (int k = 1; k < 4; ++k) acc = fmaf(a.m[i * 4 + k], b.m[k * 4 + j], acc);
+            for (int k = 1; k < 4; ++k) acc = sadd(acc, smul(a.m[i * 4 + k], b.m[k * 4 + j]));
             r.m[i * 4 + j] = acc;
         }
     return r;
@@ -71,8 +75,8 @@ __device__ inline M4 m4_trans(float e, float n, float u) {
 
 // ---- actuators ----------------------------------------------------------------------------------
 __device__ inline float softplus100(float x) {  // torch softplus(beta=100, threshold=20)
-    const float bx = x * 100.0f;
-    return bx > 20.0f ? x : log1pf(expf(bx)) / 100.0f;
+    const float bx = smul(x, 100.0f);
+    return bx > 20.0f ? x : sdiv(log1pf(expf(bx)), 100.0f);
 }
 __device__ inline float dsoftplus100(float x) {
     const float bx = x * 100.0f;
@@ -88,11 +92,11 @@ __device__ inline LinAct load_lin(const ab200_kinematics_args& k, int i, int j) 
     const float* op = k.actuator_opt + (size_t)i * 4;       // [2,2]
     LinAct a;
     a.cw = no[1 * 2 + j]; a.lo = no[2 * 2 + j]; a.hi = no[3 * 2 + j];
-    a.inc = softplus100(no[4 * 2 + j]) + 1e-6f;
-    a.off = softplus100(no[5 * 2 + j]) + 1e-6f;
-    a.rad = softplus100(no[6 * 2 + j]) + 1e-6f;
+    a.inc = sadd(softplus100(no[4 * 2 + j]), 1e-6f);
+    a.off = sadd(softplus100(no[5 * 2 + j]), 1e-6f);
+    a.rad = sadd(softplus100(no[6 * 2 + j]), 1e-6f);
     a.a0 = op[0 * 2 + j];
-    a.s0 = softplus100(op[1 * 2 + j]) + 1e-6f;
+    a.s0 = sadd(softplus100(op[1 * 2 + j]), 1e-6f);
     a.ds0 = dsoftplus100(op[1 * 2 + j]);
     return a;
 }
@@ -100,11 +104,12 @@ __device__ inline LinAct load_lin(const ab200_kinematics_args& k, int i, int j) 
 // absolute angle from the law of cosines; also d(angle)/d(stroke before clamp)
 __device__ inline float lin_abs_angle(const LinAct& a, float motor, float* dabs_dstroke) {
     const float eps = 1e-6f;
-    float stroke = motor / a.inc + a.s0;
-    const float lo = fabsf(a.off - a.rad) + eps, hi = a.off + a.rad - eps;
+    // actuators_linear.py:218-229 in its operation order (one rounding per product / sum / quotient)
+    float stroke = sadd(sdiv(motor, a.inc), a.s0);
+    const float lo = sadd(fabsf(ssub(a.off, a.rad)), eps), hi = ssub(sadd(a.off, a.rad), eps);
     const bool clamped_s = (stroke < lo) || (stroke > hi);
     stroke = fminf(fmaxf(stroke, lo), hi);
-    const float div = (a.off * a.off + a.rad * a.rad - stroke * stroke) / (2.0f * a.off * a.rad);
+    const float div = sdiv(ssub(sadd(smul(a.off, a.off), smul(a.rad, a.rad)), smul(stroke, stroke)), smul(smul(2.0f, a.off), a.rad));
     const bool clamped_d = (div < -1.0f + 1e-6f) || (div > 1.0f - 1e-6f);
     const float dc = fminf(fmaxf(div, -1.0f + 1e-6f), 1.0f - 1e-6f);
     if (dabs_dstroke) {
@@ -119,23 +124,24 @@ __device__ inline float lin_motor_to_angle(const LinAct& a, float motor, float* 
     float g, g0;
     const float ab = lin_abs_angle(a, motor, &g);
     const float ab0 = lin_abs_angle(a, 0.0f, &g0);
-    const float delta = ab0 - ab;
+    const float delta = ssub(ab0, ab);
     const float sign = (a.cw == 1.0f) ? 1.0f : ((a.cw == 0.0f) ? -1.0f : 0.0f);
     if (dang_dmotor) *dang_dmotor = sign * (-g) / a.inc;
     if (dang_da0) *dang_da0 = 1.0f;
     if (dang_ds0raw) *dang_ds0raw = sign * (g0 - g) * a.ds0;
-    return a.a0 + sign * delta;
+    return sadd(a.a0, sign * delta);   // sign * delta is exact
 }
 
 __device__ inline float lin_angle_to_motor(const LinAct& a, float angle) {
     const float eps = 1e-6f;
-    const float delta = (a.cw == 1.0f) ? (angle - a.a0) : (a.a0 - angle);
+    // actuators_linear.py:331-370 in its operation order
+    const float delta = (a.cw == 1.0f) ? ssub(angle, a.a0) : ssub(a.a0, angle);
     const float ab0 = lin_abs_angle(a, 0.0f, nullptr);
-    const float ia = ab0 - delta;
+    const float ia = ssub(ab0, delta);
     const float cv = fminf(fmaxf(cosf(ia), -1.0f + 1e-6f), 1.0f - 1e-6f);
-    float stroke = sqrtf(a.off * a.off + a.rad * a.rad - 2.0f * a.off * a.rad * cv);
-    stroke = fminf(fmaxf(stroke, fabsf(a.off - a.rad) + eps), a.off + a.rad - eps);
-    return (stroke - a.s0) * a.inc;
+    float stroke = sqrtf(ssub(sadd(smul(a.off, a.off), smul(a.rad, a.rad)), smul(smul(smul(2.0f, a.off), a.rad), cv)));
+    stroke = fminf(fmaxf(stroke, sadd(fabsf(ssub(a.off, a.rad)), eps)), ssub(sadd(a.off, a.rad), eps));
+    return smul(ssub(stroke, a.s0), a.inc);
 }
 
 // ---- forward kinematics chain -----------------------------------------------------------------
@@ -262,13 +268,16 @@ __device__ inline void motor_from_normal(const ab200_kinematics_args& k, int i, 
     const M4 f2 = m4_mul(m4_rot(0, rd[2]), m4_rot(1, rd[3]));
     // n' = F1^T n
     float np[3];
-    for (int j = 0; j < 3; ++j) np[j] = fmaf(f1.m[8 + j], nrm[2], fmaf(f1.m[4 + j], nrm[1], f1.m[j] * nrm[0]));
+    // (kinematics_rigid_body.py:420-470 in its operation order; the batched mat-vec adds rounded products left to right,
+    // the 4th term is f1[3][j] * 0 = +-0 and changes nothing)
+    for (int j = 0; j < 3; ++j) np[j] = sadd(sadd(smul(f1.m[j], nrm[0]), smul(f1.m[4 + j], nrm[1])), smul(f1.m[8 + j], nrm[2]));
     const float f00 = f2.m[0], f01 = f2.m[1];
-    const float den = sqrtf(f00 * f00 + f01 * f01);
+    const float den = sqrtf(sadd(smul(f00, f00), smul(f01, f01)));
     const float phi = atan2f(-f01, f00);
-    const float ratio = fminf(fmaxf(np[0] / (den + eps), -1.0f + eps), 1.0f - eps);
+    const float ratio = fminf(fmaxf(sdiv(np[0], sadd(den, eps)), -1.0f + eps), 1.0f - eps);
     const float pi = 3.14159265358979323846f;
-    float s[2] = {asinf(ratio) - phi, pi - asinf(ratio) - phi};
+    const float asr = asinf(ratio);
+    float s[2] = {ssub(asr, phi), ssub(ssub(pi, asr), phi)};
     float mot[2][2];
     for (int c = 0; c < 2; ++c) {
         s[c] = atan2f(sinf(s[c]), cosf(s[c]));
@@ -276,8 +285,8 @@ __device__ inline void motor_from_normal(const ab200_kinematics_args& k, int i, 
         float ss, cs;
         sincosf(s[c], &ss, &cs);
         const float w0 = ss, w1 = -cs;  // Ru(s) * (0,-1,0): (-(-sin), -cos, 0) = (sin, -cos, 0)
-        const float v1 = f2.m[4] * w0 + f2.m[5] * w1, v2 = f2.m[8] * w0 + f2.m[9] * w1;
-        float a = atan2f(v1 * np[2] - v2 * np[1], v1 * np[1] + v2 * np[2]);
+        const float v1 = sadd(smul(f2.m[4], w0), smul(f2.m[5], w1)), v2 = sadd(smul(f2.m[8], w0), smul(f2.m[9], w1));
+        float a = atan2f(ssub(smul(v1, np[2]), smul(v2, np[1])), sadd(smul(v1, np[1]), smul(v2, np[2])));
         a = atan2f(sinf(a), cosf(a));
         if (k.linear_actuators) {
             mot[c][0] = lin_angle_to_motor(load_lin(k, i, 0), a);
@@ -293,8 +302,8 @@ __device__ inline void motor_from_normal(const ab200_kinematics_args& k, int i, 
 }
 
 __device__ inline void normalize3(float* v, float eps) {
-    const float n = fmaxf(sqrtf(fmaf(v[2], v[2], fmaf(v[1], v[1], v[0] * v[0]))), eps);
-    v[0] /= n; v[1] /= n; v[2] /= n;
+    const float n = fmaxf(sqrtf(fmaf(v[2], v[2], fmaf(v[1], v[1], smul(v[0], v[0])))), eps);   // torch's norm: the FMA chain
+    v[0] = sdiv(v[0], n); v[1] = sdiv(v[1], n); v[2] = sdiv(v[2], n);
 }
 
 // The alignment loop: per iteration two small kernels (forward kinematics + convergence vote, then inverse
@@ -323,9 +332,9 @@ __device__ __forceinline__ bool align_forward_one(const ab200_kinematics_args& k
     const M4 fin = m4_mul(o, F[10]);
     for (int q = 0; q < 16; ++q) out[(size_t)i * 16 + q] = fin.m[q];
     const float cn[4] = {-o.m[1], -o.m[5], -o.m[9], -o.m[13]};   // O (0,-1,0,0)
-    float wr[3] = {aim[(size_t)i * 4] - o.m[3], aim[(size_t)i * 4 + 1] - o.m[7], aim[(size_t)i * 4 + 2] - o.m[11]};
+    float wr[3] = {ssub(aim[(size_t)i * 4], o.m[3]), ssub(aim[(size_t)i * 4 + 1], o.m[7]), ssub(aim[(size_t)i * 4 + 2], o.m[11])};
     normalize3(wr, 1e-8f);
-    float wn[3] = {-incident[(size_t)i * 4] + wr[0], -incident[(size_t)i * 4 + 1] + wr[1], -incident[(size_t)i * 4 + 2] + wr[2]};
+    float wn[3] = {sadd(-incident[(size_t)i * 4], wr[0]), sadd(-incident[(size_t)i * 4 + 1], wr[1]), sadd(-incident[(size_t)i * 4 + 2], wr[2])};
     normalize3(wn, 1e-8f);
     const float loss = (fabsf(wn[0] - cn[0]) + fabsf(wn[1] - cn[1]) + fabsf(wn[2] - cn[2]) + fabsf(cn[3])) / 4.0f;
     const bool open = it == 0 || !(fabsf(scratch[i] - loss) <= min_eps);

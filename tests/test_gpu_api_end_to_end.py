@@ -69,8 +69,13 @@ def test_surface_reconstruction_step_gradients():
     group.align_surfaces_with_incident_ray_directions(scenario.solar_tower.get_centers_of_target_areas(tidx), inc, mask)
     tracer = HeliostatRayTracer(scenario, group, blocking_active=False, bitmap_resolution=torch.tensor(res))
     flux, *_ = tracer.trace_rays(inc, mask, tidx)
-    torch.manual_seed(1)
-    wgt = torch.rand(n, res[1], res[0])
+    # A SMOOTH functional of the flux: the orientation of the device alignment differs from the CPU one in the last bit
+    # for some heliostats (transcendental functions), a handful of rays then land in the neighbouring pixel, and with
+    # independent random weights per pixel ONE such flip moves a control point's gradient by several per cent
+    # (measured: 4.7e-2 with torch.rand weights vs 2.2e-4 with these, same kernels, tools/diag note in DESIGN §2) - the
+    # trace-level tests compare gradients under random weights on identical aligned inputs instead.
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, res[1]), torch.linspace(-1, 1, res[0]), indexing="ij")
+    wgt = (torch.exp(-((xx - 0.2) ** 2 + (yy + 0.1) ** 2) / 0.3) + 0.3 * xx)[None].expand(n, -1, -1).contiguous()
     (flux * wgt.to(DEV)).sum().backward()
     # oracle: same chain with autograd on the CPU, same distortions
     cpo = ft["nurbs_control_points"].clone().requires_grad_(True)
@@ -86,7 +91,7 @@ def test_surface_reconstruction_step_gradients():
     (ref * wgt).sum().backward()
     scale = cpo.grad.abs().max()
     err = (cp.grad.cpu() - cpo.grad).abs().max() / scale
-    assert err <= 5e-3, f"control-point gradient error {err:.3e}"
+    assert err <= 1e-3, f"control-point gradient error {err:.3e}"     # measured 2.2e-4 (round 1 accepted 5e-3)
 
 
 def test_motor_position_gradients_and_mask_assertion():

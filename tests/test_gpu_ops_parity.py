@@ -185,7 +185,11 @@ def test_kinematics_forward_and_backward(linear):
     mc = motor.to(DEV).requires_grad_(True)
     rot, trans, opt = (d[k].detach().requires_grad_(True) for k in ("rot", "trans", "opt"))
     out = ops.kinematics_orientations(mc, rot, trans, opt if linear else None, d["positions"], d["non_opt"], off, linear)
-    assert (out.detach().cpu() - ref.detach()).abs().max() <= 2e-5
+    # the kernels follow torch-CPU's rounding sequence (unfused left-to-right 4x4 products, strict actuator formulas); what
+    # is left are last-bit differences of sin / cos / acos / exp (tools/diag_kinematics_parity.py: 256 heliostats, ideal
+    # actuators 56 % of the orientations bit-identical, linear 22 %; rotation part within 2e-7, translation within 2e-6)
+    diff = (out.detach().cpu() - ref.detach()).abs()
+    assert diff[:, :3, :3].max() <= 6e-7 and diff.max() <= 8e-6, f"{diff[:, :3, :3].max():.2e} {diff.max():.2e}"
     (out * wgt.to(DEV)).sum().backward()
     for got, want, name in ((mc.grad, m.grad, "motor"), (rot.grad, kin.rotation_deviations.grad, "rotation dev"),
                             (trans.grad, kin.translation_deviations.grad, "translation dev")):
@@ -213,8 +217,9 @@ def test_alignment_to_incident_rays(linear):
     off = O.initial_orientation_offset().reshape(4, 4).to(DEV)
     got, gm = ops.kinematics_align_incident(case["incident"].to(DEV), case["aim"].to(DEV), d["rot"], d["trans"],
                                             d["opt"] if linear else None, d["positions"], d["non_opt"], off, linear)
-    assert (got.cpu() - ori).abs().max() <= 5e-5
-    assert ((gm.cpu() - motor).abs() / motor.abs().clamp_min(1.0)).max() <= 2e-4
+    diff = (got.cpu() - ori).abs()
+    assert diff[:, :3, :3].max() <= 1e-6 and diff.max() <= 1.6e-5, f"{diff[:, :3, :3].max():.2e} {diff.max():.2e}"
+    assert ((gm.cpu() - motor).abs() / motor.abs().clamp_min(1.0)).max() <= 1e-6       # measured 3e-7 (round 1: 2e-4)
 
 
 def test_align_apply_forward_backward():

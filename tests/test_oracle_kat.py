@@ -227,3 +227,36 @@ def test_cpu_rounding_sequence_of_the_cylinder_quadratic():
     DISC = _f32(_f32(Bq * Bq) - _f32(_f32(np.float32(4) * A) * C))
     assert np.array_equal(A, n(a)) and np.array_equal(Bq, n(b)) and np.array_equal(DISC, n(disc))
     assert (n(disc) > 0).mean() > 0.5, "the case must hit the cylinder"
+
+
+def test_cpu_rounding_sequence_of_the_small_batched_matrix_products():
+    """Parity note behind `m4_mul` / `motor_from_normal` (csrc/kinematics.cu): torch's CPU bmm of the kinematic chain's
+    tiny operands ([N,4,4] @ [N,4,4], @ a broadcast [1,4,4], [N,4,4]^T @ [N,4,1]) adds separately rounded products left
+    to right - unlike the large GEMMs (`points @ O^T`), which accumulate as an FMA chain."""
+    import numpy as np
+
+    g = torch.Generator().manual_seed(4)
+    a, b, one = torch.randn(300, 4, 4, generator=g), torch.randn(300, 4, 4, generator=g), torch.randn(1, 4, 4, generator=g)
+
+    def unfused(x, y):
+        x, y = np.broadcast_arrays(x, y)
+        out = np.zeros(x.shape, dtype=np.float32)
+        for i in range(4):
+            for j in range(4):
+                acc = _f32(x[..., i, 0] * y[..., 0, j])
+                for k in (1, 2, 3):
+                    acc = _f32(acc + _f32(x[..., i, k] * y[..., k, j]))
+                out[..., i, j] = acc
+        return out
+
+    assert np.array_equal(unfused(a.numpy(), b.numpy()), (a @ b).numpy())
+    assert np.array_equal(unfused(a.numpy(), one.numpy()), (a @ one).numpy())
+    assert np.array_equal(unfused(one.numpy(), a.numpy()), (one @ a).numpy())
+    v = torch.randn(300, 4, generator=g)
+    at = a.transpose(-1, -2).numpy()
+    acc = _f32(at[:, :, 0] * v.numpy()[:, None, 0])
+    for k in (1, 2, 3):
+        acc = _f32(acc + _f32(at[:, :, k] * v.numpy()[:, None, k]))
+    assert np.array_equal(acc, (a.transpose(-1, -2) @ v[:, :, None])[:, :, 0].numpy())
+    south = torch.tensor([0.0, -1.0, 0.0, 0.0])
+    assert np.array_equal((a @ south).numpy(), -a.numpy()[:, :, 1])
