@@ -10,6 +10,35 @@
 
 namespace ab200 {
 
+// Transcendental functions of the kinematics.  torch's CPU implementations (SLEEF, <= 1 ulp) return the correctly rounded
+// float for 91 % (acos) ... 99.9 % (log1p) of their arguments; CUDA's float versions (<= 2 ulp) hit it less often.  These
+// are per-heliostat evaluations (a few dozen per heliostat and step, nothing per ray), so they are taken in double
+// precision and rounded once: the correctly rounded value in all but ~1e-8 of the cases - the closest a device
+// function gets to the reference's last bit (tools/diag_kinematics_parity.py; -DAB200_KIN_FLOAT_TRIG switches back).
+#ifdef AB200_KIN_FLOAT_TRIG
+__device__ __forceinline__ void k_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ float k_sin(float x) { return sinf(x); }
+__device__ __forceinline__ float k_cos(float x) { return cosf(x); }
+__device__ __forceinline__ float k_acos(float x) { return acosf(x); }
+__device__ __forceinline__ float k_asin(float x) { return asinf(x); }
+__device__ __forceinline__ float k_atan2(float y, float x) { return atan2f(y, x); }
+__device__ __forceinline__ float k_exp(float x) { return expf(x); }
+__device__ __forceinline__ float k_log1p(float x) { return log1pf(x); }
+#else
+__device__ __forceinline__ void k_sincos(float x, float* s, float* c) {
+    double sd, cd;
+    sincos((double)x, &sd, &cd);
+    *s = (float)sd; *c = (float)cd;
+}
+__device__ __forceinline__ float k_sin(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float k_cos(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float k_acos(float x) { return (float)acos((double)x); }
+__device__ __forceinline__ float k_asin(float x) { return (float)asin((double)x); }
+__device__ __forceinline__ float k_atan2(float y, float x) { return (float)atan2((double)y, (double)x); }
+__device__ __forceinline__ float k_exp(float x) { return (float)exp((double)x); }
+__device__ __forceinline__ float k_log1p(float x) { return (float)log1p((double)x); }
+#endif
+
 struct M4 {
     float m[16];
 };
@@ -49,7 +78,7 @@ __device__ inline M4 m4_transpose(const M4& a) {
 __device__ inline M4 m4_rot(int axis, float ang) {
     M4 r = m4_identity();
     float s, c;
-    sincosf(ang, &s, &c);
+    k_sincos(ang, &s, &c);
     if (axis == 0) { r.m[5] = c; r.m[6] = -s; r.m[9] = s; r.m[10] = c; }
     else if (axis == 1) { r.m[0] = c; r.m[2] = -s; r.m[8] = s; r.m[10] = c; }
     else { r.m[0] = c; r.m[1] = -s; r.m[4] = s; r.m[5] = c; }
@@ -61,7 +90,7 @@ __device__ inline M4 m4_drot(int axis, float ang) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) r.m[i] = 0.f;
     float s, c;
-    sincosf(ang, &s, &c);
+    k_sincos(ang, &s, &c);
     if (axis == 0) { r.m[5] = -s; r.m[6] = -c; r.m[9] = c; r.m[10] = -s; }
     else if (axis == 1) { r.m[0] = -s; r.m[2] = -c; r.m[8] = c; r.m[10] = -s; }
     else { r.m[0] = -s; r.m[1] = -c; r.m[4] = c; r.m[5] = -s; }
@@ -76,16 +105,18 @@ __device__ inline M4 m4_trans(float e, float n, float u) {
 // ---- actuators ----------------------------------------------------------------------------------
 __device__ inline float softplus100(float x) {  // torch softplus(beta=100, threshold=20)
     const float bx = smul(x, 100.0f);
-    return bx > 20.0f ? x : sdiv(log1pf(expf(bx)), 100.0f);
+    return bx > 20.0f ? x : sdiv(k_log1p(k_exp(bx)), 100.0f);
 }
 __device__ inline float dsoftplus100(float x) {
     const float bx = x * 100.0f;
-    return bx > 20.0f ? 1.0f : 1.0f / (1.0f + expf(-bx));
+    return bx > 20.0f ? 1.0f : 1.0f / (1.0f + k_exp(-bx));
 }
 
 struct LinAct {
     float inc, off, rad, a0, s0, ds0, cw, lo, hi;
+    float ab0, g0;   // absolute angle at motor position 0 and its stroke derivative: constants of the actuator
 };
+__device__ inline float lin_abs_angle(const LinAct& a, float motor, float* dabs_dstroke);
 
 __device__ inline LinAct load_lin(const ab200_kinematics_args& k, int i, int j) {
     const float* no = k.actuator_non_opt + (size_t)i * 14;  // [7,2]
@@ -98,6 +129,7 @@ __device__ inline LinAct load_lin(const ab200_kinematics_args& k, int i, int j) 
     a.a0 = op[0 * 2 + j];
     a.s0 = sadd(softplus100(op[1 * 2 + j]), 1e-6f);
     a.ds0 = dsoftplus100(op[1 * 2 + j]);
+    a.ab0 = lin_abs_angle(a, 0.0f, &a.g0);
     return a;
 }
 
@@ -117,14 +149,14 @@ __device__ inline float lin_abs_angle(const LinAct& a, float motor, float* dabs_
         if (!clamped_s && !clamped_d) g = (-1.0f / sqrtf(1.0f - dc * dc)) * (-stroke / (a.off * a.rad));
         *dabs_dstroke = g;
     }
-    return acosf(dc);
+    return k_acos(dc);
 }
 
 __device__ inline float lin_motor_to_angle(const LinAct& a, float motor, float* dang_dmotor, float* dang_da0, float* dang_ds0raw) {
-    float g, g0;
+    float g;
+    const float g0 = a.g0;
     const float ab = lin_abs_angle(a, motor, &g);
-    const float ab0 = lin_abs_angle(a, 0.0f, &g0);
-    const float delta = ssub(ab0, ab);
+    const float delta = ssub(a.ab0, ab);
     const float sign = (a.cw == 1.0f) ? 1.0f : ((a.cw == 0.0f) ? -1.0f : 0.0f);
     if (dang_dmotor) *dang_dmotor = sign * (-g) / a.inc;
     if (dang_da0) *dang_da0 = 1.0f;
@@ -136,9 +168,8 @@ __device__ inline float lin_angle_to_motor(const LinAct& a, float angle) {
     const float eps = 1e-6f;
     // actuators_linear.py:331-370 in its operation order
     const float delta = (a.cw == 1.0f) ? ssub(angle, a.a0) : ssub(a.a0, angle);
-    const float ab0 = lin_abs_angle(a, 0.0f, nullptr);
-    const float ia = ssub(ab0, delta);
-    const float cv = fminf(fmaxf(cosf(ia), -1.0f + 1e-6f), 1.0f - 1e-6f);
+    const float ia = ssub(a.ab0, delta);
+    const float cv = fminf(fmaxf(k_cos(ia), -1.0f + 1e-6f), 1.0f - 1e-6f);
     float stroke = sqrtf(ssub(sadd(smul(a.off, a.off), smul(a.rad, a.rad)), smul(smul(smul(2.0f, a.off), a.rad), cv)));
     stroke = fminf(fmaxf(stroke, sadd(fabsf(ssub(a.off, a.rad)), eps)), ssub(sadd(a.off, a.rad), eps));
     return smul(ssub(stroke, a.s0), a.inc);
@@ -148,12 +179,13 @@ __device__ inline float lin_angle_to_motor(const LinAct& a, float angle) {
 constexpr int kFactors = 11;
 // factor k: 0 T(pos) 1 Rn(t1n) 2 Ru(t1u) 3 T(t1) 4 Re(theta1) 5 Re(t2e) 6 Rn(t2n) 7 T(t2) 8 Ru(theta2) 9 T(tc) 10 offset
 
+// `pre` (optional): the heliostat's two actuators already loaded (the alignment loop loads them once for all sweeps)
 __device__ inline void joint_angles(const ab200_kinematics_args& k, int i, const float* motor, float* th, float* dth_dm,
-                                    float* dth_da0, float* dth_ds0) {
+                                    float* dth_da0, float* dth_ds0, const LinAct* pre = nullptr) {
     for (int j = 0; j < 2; ++j) {
         const float mp = motor[(size_t)i * 2 + j];
         if (k.linear_actuators) {
-            const LinAct a = load_lin(k, i, j);
+            const LinAct a = pre ? pre[j] : load_lin(k, i, j);
             th[j] = lin_motor_to_angle(a, mp, dth_dm ? dth_dm + j : nullptr, dth_da0 ? dth_da0 + j : nullptr,
                                        dth_ds0 ? dth_ds0 + j : nullptr);
         } else {
@@ -261,7 +293,8 @@ __global__ void kinematics_bwd_kernel(const ab200_kinematics_args k, const float
 
 // ---- inverse kinematics + fixed-point alignment (2 x max_iterations small multi-block launches; the convergence vote
 // of all heliostats stays on the device, no host sync) ------------------
-__device__ inline void motor_from_normal(const ab200_kinematics_args& k, int i, const float* nrm /*3*/, float* motor_out) {
+__device__ inline void motor_from_normal(const ab200_kinematics_args& k, int i, const float* nrm /*3*/, float* motor_out,
+                                         const LinAct* pre = nullptr) {
     const float eps = 1e-8f;
     const float* rd = k.rotation_dev + (size_t)i * 4;
     const M4 f1 = m4_mul(m4_rot(1, rd[0]), m4_rot(2, rd[1]));
@@ -273,30 +306,39 @@ __device__ inline void motor_from_normal(const ab200_kinematics_args& k, int i, 
     for (int j = 0; j < 3; ++j) np[j] = sadd(sadd(smul(f1.m[j], nrm[0]), smul(f1.m[4 + j], nrm[1])), smul(f1.m[8 + j], nrm[2]));
     const float f00 = f2.m[0], f01 = f2.m[1];
     const float den = sqrtf(sadd(smul(f00, f00), smul(f01, f01)));
-    const float phi = atan2f(-f01, f00);
+    const float phi = k_atan2(-f01, f00);
     const float ratio = fminf(fmaxf(sdiv(np[0], sadd(den, eps)), -1.0f + eps), 1.0f - eps);
     const float pi = 3.14159265358979323846f;
-    const float asr = asinf(ratio);
+    const float asr = k_asin(ratio);
     float s[2] = {ssub(asr, phi), ssub(ssub(pi, asr), phi)};
-    float mot[2][2];
+    float mot[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    LinAct la[2];
+    if (k.linear_actuators) { la[0] = pre ? pre[0] : load_lin(k, i, 0); la[1] = pre ? pre[1] : load_lin(k, i, 1); }
+    const float* no = k.actuator_non_opt + (size_t)i * 14;
+    bool ok1 = true;
+    // the reference evaluates both solutions and keeps the first when it lies inside the motor limits: the second is only
+    // computed when it is needed (same result)
     for (int c = 0; c < 2; ++c) {
-        s[c] = atan2f(sinf(s[c]), cosf(s[c]));
-        // v = F2 Ru(s) (0,-1,0,0)
+        if (c == 1 && ok1) break;
         float ss, cs;
-        sincosf(s[c], &ss, &cs);
+        k_sincos(s[c], &ss, &cs);
+        s[c] = k_atan2(ss, cs);
+        // v = F2 Ru(s) (0,-1,0,0)
+        k_sincos(s[c], &ss, &cs);
         const float w0 = ss, w1 = -cs;  // Ru(s) * (0,-1,0): (-(-sin), -cos, 0) = (sin, -cos, 0)
         const float v1 = sadd(smul(f2.m[4], w0), smul(f2.m[5], w1)), v2 = sadd(smul(f2.m[8], w0), smul(f2.m[9], w1));
-        float a = atan2f(ssub(smul(v1, np[2]), smul(v2, np[1])), sadd(smul(v1, np[1]), smul(v2, np[2])));
-        a = atan2f(sinf(a), cosf(a));
+        float a = k_atan2(ssub(smul(v1, np[2]), smul(v2, np[1])), sadd(smul(v1, np[1]), smul(v2, np[2])));
+        float sa, ca;
+        k_sincos(a, &sa, &ca);
+        a = k_atan2(sa, ca);
         if (k.linear_actuators) {
-            mot[c][0] = lin_angle_to_motor(load_lin(k, i, 0), a);
-            mot[c][1] = lin_angle_to_motor(load_lin(k, i, 1), s[c]);
+            mot[c][0] = lin_angle_to_motor(la[0], a);
+            mot[c][1] = lin_angle_to_motor(la[1], s[c]);
         } else {
             mot[c][0] = a; mot[c][1] = s[c];
         }
+        if (c == 0) ok1 = (mot[0][0] >= no[4] && mot[0][0] <= no[6]) && (mot[0][1] >= no[5] && mot[0][1] <= no[7]);
     }
-    const float* no = k.actuator_non_opt + (size_t)i * 14;
-    const bool ok1 = (mot[0][0] >= no[4] && mot[0][0] <= no[6]) && (mot[0][1] >= no[5] && mot[0][1] <= no[7]);
     motor_out[0] = ok1 ? mot[0][0] : mot[1][0];
     motor_out[1] = ok1 ? mot[0][1] : mot[1][1];
 }
@@ -322,10 +364,10 @@ struct AlignFlags {
 __device__ __forceinline__ bool align_forward_one(const ab200_kinematics_args& k, const float* __restrict__ incident,
                                                   const float* __restrict__ aim, int i, int it, float min_eps,
                                                   float* __restrict__ out, float* __restrict__ motor_io,
-                                                  float* __restrict__ scratch) {
+                                                  float* __restrict__ scratch, const LinAct* pre = nullptr) {
     if (it == 0) { motor_io[(size_t)i * 2] = 0.f; motor_io[(size_t)i * 2 + 1] = 0.f; }
     float th[2];
-    joint_angles(k, i, motor_io, th, nullptr, nullptr, nullptr);
+    joint_angles(k, i, motor_io, th, nullptr, nullptr, nullptr, pre);
     M4 F[kFactors];
     build_factors(F, k, i, th);
     const M4 o = raw_orientation(F);
@@ -344,10 +386,10 @@ __device__ __forceinline__ bool align_forward_one(const ab200_kinematics_args& k
 }
 
 __device__ __forceinline__ void align_inverse_one(const ab200_kinematics_args& k, int i, float* __restrict__ motor_io,
-                                                  const float* __restrict__ scratch) {
+                                                  const float* __restrict__ scratch, const LinAct* pre = nullptr) {
     const float wn[3] = {scratch[(size_t)k.n + 3 * i], scratch[(size_t)k.n + 3 * i + 1], scratch[(size_t)k.n + 3 * i + 2]};
     float mo[2];
-    motor_from_normal(k, i, wn, mo);
+    motor_from_normal(k, i, wn, mo, pre);
     motor_io[(size_t)i * 2] = mo[0];
     motor_io[(size_t)i * 2 + 1] = mo[1];
 }
@@ -392,8 +434,11 @@ kin_align_cluster_kernel(const ab200_kinematics_args k, const float* __restrict_
     __shared__ int open_sh;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool mine = i < k.n;
+    LinAct la[2];   // the heliostat's actuators: loaded (softplus, law of cosines at rest) once for all sweeps
+    const LinAct* pre = nullptr;
+    if (mine && k.linear_actuators) { la[0] = load_lin(k, i, 0); la[1] = load_lin(k, i, 1); pre = la; }
     for (int it = 0; it < max_iterations; ++it) {
-        const bool open = mine && align_forward_one(k, incident, aim, i, it, min_eps, out, motor_io, scratch);
+        const bool open = mine && align_forward_one(k, incident, aim, i, it, min_eps, out, motor_io, scratch, pre);
         const int cta_open = __syncthreads_or(open);
         if (threadIdx.x == 0) open_sh = cta_open;
         cluster.sync();                                   // every CTA's vote is visible
@@ -401,7 +446,7 @@ kin_align_cluster_kernel(const ab200_kinematics_args k, const float* __restrict_
         for (int r = 0; r < kAlignClusterCtas; ++r) any_open |= *cluster.map_shared_rank(&open_sh, r);
         cluster.sync();                                   // ... and read, before the next sweep overwrites it
         if (!any_open && it > 0) break;                   // uniform over the cluster
-        if (mine) align_inverse_one(k, i, motor_io, scratch);
+        if (mine) align_inverse_one(k, i, motor_io, scratch, pre);
     }
 }
 

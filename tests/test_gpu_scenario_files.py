@@ -52,7 +52,7 @@ def _reference_distortions(tracer, scenario, n, p, check):
     tracer._packed = ops.pack_distortions(tracer.distortions_dataset.distortions_u, tracer.distortions_dataset.distortions_e)
 
 
-def _check_trace(scenario, group, t):
+def _check_trace(scenario, group, t, flux_bar=2.5e-4):
     from artist_b200 import HeliostatRayTracer
 
     inc, mask, tidx = t["incident"].to(DEV), t["mask"].to(DEV), t["target_idx"].to(DEV)
@@ -67,27 +67,30 @@ def _check_trace(scenario, group, t):
     _reference_distortions(tracer, scenario, n, p, t["distortions"])
     flux, ic, ot, bl = tracer.trace_rays(incident_ray_directions=inc, active_heliostats_mask=mask, target_area_indices=tidx,
                                          device=DEV)
-    # motor positions and the aligned surface (fp32 kinematics: relative 2e-4 / absolute 2e-4 m like the other API tests)
+    # motor positions and the aligned surface against the real reference: the kinematics kernels follow torch-CPU's
+    # rounding sequence and take their transcendental functions correctly rounded, so what is left is the last bit where
+    # SLEEF is not correctly rounded (measured: motors <= 2e-7 relative, points <= 4e-6 m at ~100 m, normals <= 3e-7)
     motor = group.kinematics.active_motor_positions.cpu()
-    assert ((motor - t["motor_positions"]).abs() / t["motor_positions"].abs().clamp_min(1)).max() < 2e-4
-    assert (group.active_surface_points[:, ::SAMPLE].cpu() - t["aligned_points_sample"]).abs().max() <= 2e-4
-    assert (group.active_surface_normals[:, ::SAMPLE].cpu() - t["aligned_normals_sample"]).abs().max() <= 2e-5
+    assert ((motor - t["motor_positions"]).abs() / t["motor_positions"].abs().clamp_min(1)).max() < 1e-6
+    assert (group.active_surface_points[:, ::SAMPLE].cpu() - t["aligned_points_sample"]).abs().max() <= 1.6e-5
+    assert (group.active_surface_normals[:, ::SAMPLE].cpu() - t["aligned_normals_sample"]).abs().max() <= 6e-7
     print(f"   {t['name']}: motor rel diff {float(((motor - t['motor_positions']).abs() / t['motor_positions'].abs().clamp_min(1)).max()):.2e}, "
           f"aligned points max diff {float((group.active_surface_points[:, ::SAMPLE].cpu() - t['aligned_points_sample']).abs().max()):.2e} m, "
           f"normals {float((group.active_surface_normals[:, ::SAMPLE].cpu() - t['aligned_normals_sample']).abs().max()):.2e}")
     ref = _dense(t["flux"])
     assert flux.shape == ref.shape
     peak = ref.max()
-    # end to end INCLUDING the fp32 kinematics (device asin/atan2/sincos in the alignment differ from torch-CPU's in the
-    # last bits, so the aligned surfaces are not bit-identical): measured 5e-6 .. 2.4e-4 of the peak pixel on B200; with
-    # identical aligned inputs the trace alone is within 1e-5 (tests/test_gpu_golden.py)
-    assert (flux.cpu() - ref).abs().max() <= 5e-4 * peak, f"{t['name']}: {(flux.cpu() - ref).abs().max() / peak:.2e}"
+    # end to end INCLUDING the kinematics: where the alignment reproduces the reference's orientation bit for bit the
+    # bitmaps agree to 3e-6 .. 6e-6 of the peak pixel (all four sun directions of config 1; with identical aligned
+    # inputs the trace alone is within 1e-5, tests/test_gpu_golden.py); one ulp in an aligned normal moves the focal spot
+    # by ~1e-3 px = 1e-4 of the peak (config 2: 6e-6, 1e-5, 4e-5 and 1.7e-4).  Round 1: up to 2.4e-4 everywhere, bar 5e-4.
+    assert (flux.cpu() - ref).abs().max() <= flux_bar * peak, f"{t['name']}: {(flux.cpu() - ref).abs().max() / peak:.2e}"
     assert abs(float(flux.sum()) - float(ref.sum())) <= 1e-4 * float(ref.sum())
     assert (ic.cpu() - t["intercept"]).abs().max() <= 1e-3 and (ot.cpu() - t["on_target"]).abs().max() <= 1e-3
     assert torch.equal(bl.cpu(), t["blocking"])
     per_target = tracer.get_bitmaps_per_target(flux, tidx)
     ref_pt = _dense(t["per_target"])
-    assert per_target.shape == ref_pt.shape and (per_target.cpu() - ref_pt).abs().max() <= 5e-4 * ref_pt.max()
+    assert per_target.shape == ref_pt.shape and (per_target.cpu() - ref_pt).abs().max() <= flux_bar * ref_pt.max()
     return float((flux.cpu() - ref).abs().max() / peak)
 
 
@@ -97,10 +100,10 @@ def test_config1_tutorial_single_heliostat(golden, tmp_path):
     group = scenario.heliostat_field.heliostat_groups[0]
     r = ref["groups"][0]
     assert group.names == r["names"] and scenario.solar_tower.target_name_to_index == ref["tower"]["target_name_to_index"]
-    # surfaces evaluated from the file's control points: bit-exact points, normals within an ulp
+    # surfaces evaluated from the file's control points: points and normals bit-exact
     assert torch.equal(group.surface_points[:, ::SAMPLE].cpu(), r["surface_points_sample"])
-    assert (group.surface_normals[:, ::SAMPLE].cpu() - r["surface_normals_sample"]).abs().max() <= 2e-7
-    errs = [_check_trace(scenario, group, t) for t in ref["traces"]]
+    assert torch.equal(group.surface_normals[:, ::SAMPLE].cpu(), r["surface_normals_sample"])
+    errs = [_check_trace(scenario, group, t, flux_bar=2e-5) for t in ref["traces"]]   # measured 3e-6 .. 6e-6
     print("config 1 flux max rel err per direction:", errs)
 
 
@@ -112,6 +115,6 @@ def test_config2_four_heliostats_two_groups(golden, tmp_path):
     assert [type(g.kinematics.actuators).__name__ for g in groups] == [r["actuator_class"] for r in ref["groups"]]
     for g, r in zip(groups, ref["groups"]):
         assert torch.equal(g.surface_points[:, ::SAMPLE].cpu(), r["surface_points_sample"])
-        assert (g.surface_normals[:, ::SAMPLE].cpu() - r["surface_normals_sample"]).abs().max() <= 2e-7
+        assert torch.equal(g.surface_normals[:, ::SAMPLE].cpu(), r["surface_normals_sample"])
     errs = [_check_trace(scenario, groups[t["group"]], t) for t in ref["traces"]]
     print("config 2 flux max rel err per trace:", errs)
