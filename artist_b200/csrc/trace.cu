@@ -359,7 +359,7 @@ __device__ __forceinline__ void fwd_rays(const TraceParams& prm, const TargetCtx
             ray_trig<TRIG>(d.x, d.y, trig, (size_t)r * P + p, s.cu, s.su, s.ce, s.se);
             scatter(s, pc);
             Hit hit;
-            if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
+            if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV, TRIG == AB200_TRIG_TABLE>(hit, T, pc, s, mag);
             if (ONLY_IRREGULAR && point_regular(pc) && angles_regular<TRIG>(d.x, d.y) && cosine_regular(hit.a)) continue;
             float blocked = 0.0f;
             if (BLK) {
@@ -1528,7 +1528,7 @@ __device__ __forceinline__ void bwd_rays(const TraceParams& prm, const TargetCtx
                 if (bcls == 1) continue;
             }
             Hit hit;
-            if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV>(hit, T, pc, s, mag);
+            if (PLANAR) hit_planar<FASTDIV>(hit, T, pc, s, mag); else hit_cylinder<FASTDIV, TRIG == AB200_TRIG_TABLE>(hit, T, pc, s, mag);
             if (ONLY_IRREGULAR && point_regular(pc) && angles_regular<TRIG>(d.x, d.y) && cosine_regular(hit.a)) continue;
             if (!hit.valid) continue;
             Splat sp;

@@ -84,7 +84,7 @@ __device__ inline void load_target(TargetCtx& T, const ab200_targets& tg, int ti
         T.opn = tg.cyl_opening[k];
         T.w = T.opn;  // "width" of the unwrapped sector is the opening angle
         T.half_w = 0.f;
-        T.ang0 = ssub(atan2f(T.n1, T.n0), sdiv(T.opn, 2.0f));
+        T.ang0 = ssub((float)atan2((double)T.n1, (double)T.n0), sdiv(T.opn, 2.0f));   // once per CTA: correctly rounded
         T.px_per_m_e = T.em1 / fmaxf(rad * T.opn, 1e-6f);
         T.px_per_m_u = T.um1 / T.h;
         T.rw = __frcp_rn(T.opn);
@@ -241,7 +241,10 @@ __device__ __forceinline__ bool centre_planar(const TargetCtx& T, const PointCtx
     return true;
 }
 
-template <bool FASTDIV>
+// CRATAN: the sector angle through a double-precision atan2 rounded once (the correctly rounded float, which torch's CPU
+// atan2 returns for 97.7 % of its arguments; atan2f agrees with it for about half).  Per-ray double arithmetic: the strict
+// parity mode (AB200_TRIG_TABLE) pays it, the device-trig modes keep atan2f.
+template <bool FASTDIV, bool CRATAN = false>
 __device__ __forceinline__ void hit_cylinder(Hit& h, const TargetCtx& T, const PointCtx& pc, const Scatter& s, float mag) {
     // directions @ rot^T (FMA chain over k, as the CPU GEMM does)
     const float dlx = fmaf(s.dz, T.uz, fmaf(s.dy, T.uy, smul(s.dx, T.ux)));
@@ -270,7 +273,7 @@ __device__ __forceinline__ void hit_cylinder(Hit& h, const TargetCtx& T, const P
     float lam = sadd(smul(-dlx, nlx), smul(-dly, nly));
     lam = fmaxf(lam, 0.0f);
     z = sadd(z, T.half_h);
-    const float ang = ssub(atan2f(y, x), T.ang0);
+    const float ang = ssub(CRATAN ? (float)atan2((double)y, (double)x) : atan2f(y, x), T.ang0);
     const bool on = (z >= 0.0f) && (z <= T.h) && (ang >= 0.0f) && (ang <= T.opn);
     const bool valid = on && vd;
     h.valid = valid;

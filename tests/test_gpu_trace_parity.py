@@ -81,8 +81,8 @@ def test_cylindrical_and_mixed_targets():
     """Cylinder hits follow the reference's operation order (frame rows from torch's contracted cross product, GEMM FMA
     chains, one rounding per product / sum of the quadratic, IEEE sqrt and divisions): the hit distance and the height
     coordinate are bit-identical except where torch's CPU sqrt (MKL VML, not correctly rounded for ~0.7 % of its
-    arguments) differs from IEEE in the last bit; the angular coordinate goes through atan2 (device vs SLEEF: 1 ulp,
-    3e-5 rad-pixels).  Measured on B200: t / bu identical for 99.99 % of the rays, be within 3e-4 px, flux 5e-5 of
+    arguments) differs from IEEE in the last bit; the angular coordinate goes through atan2 (strict mode: in double
+    precision, rounded once - torch's SLEEF atan2 returns that value for most arguments: 84 % of `be` bit-identical).  Measured on B200: t / bu identical for 99.99 % of the rays, be within 3e-4 px, flux 5e-5 of
     peak (tools/diag_cylinder_parity.py)."""
     case = cases.make_case(n=6, points_per_facet=(16, 16), rays=6, target_pattern=(1, 0, 1))
     res = (256, 256)
@@ -95,6 +95,7 @@ def test_cylindrical_and_mixed_targets():
     both = (lam > 0) & cyl[:, None, None]
     assert (dt.cpu() == t)[both].float().mean() >= 0.999 and (dbu.cpu() == bu)[both].float().mean() >= 0.999
     assert ((dt.cpu() - t).abs() / t.clamp_min(1.0))[both].max() <= 2.5e-7           # the rest: one ulp of the root
+    assert (dbe.cpu() == be)[both].float().mean() >= 0.75
     assert (dbe.cpu() - be)[both].abs().max() < 1e-3 and (dbu.cpu() - bu)[both].abs().max() < 1e-3
     assert ((dlam.cpu() - lam).abs() / lam.clamp_min(1e-3))[both].max() <= 2e-6
     ref, ric, rot, _ = O.trace_rays(case["points"], case["normals"], case["incident"], case["dist_u"], case["dist_e"],
