@@ -194,10 +194,10 @@ def test_kinematics_forward_and_backward(linear):
     for got, want, name in ((mc.grad, m.grad, "motor"), (rot.grad, kin.rotation_deviations.grad, "rotation dev"),
                             (trans.grad, kin.translation_deviations.grad, "translation dev")):
         scale = want.abs().max().clamp_min(1e-12)
-        assert (got.cpu() - want).abs().max() <= 2e-3 * scale, name
+        assert (got.cpu() - want).abs().max() <= 5e-6 * scale, name      # measured 6e-8 .. 2e-7 (round 1 bar: 2e-3)
     if linear:
         want = kin.actuator_optimizable.grad
-        assert (opt.grad.cpu() - want).abs().max() <= 2e-3 * want.abs().max()
+        assert (opt.grad.cpu() - want).abs().max() <= 5e-6 * want.abs().max()      # measured 7e-7
 
 
 @pytest.mark.parametrize("linear", [True, False])
