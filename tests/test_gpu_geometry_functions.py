@@ -82,11 +82,13 @@ def test_line_cylinder_intersections_match_the_oracle():
     got = line_cylinder_intersections(rays, case["points"].to(DEV), _Cyl(tg), tidx.to(DEV), res)
     hit = want[3] > 0
     assert hit.any() and torch.equal(got[3].cpu() > 0, hit)
-    # the quadratic cancels ~3 digits in fp32 (origins ~80 m from a 4 m cylinder): coordinates within 0.05 px
+    # the reference's operation order (tests/test_gpu_trace_parity.py::test_cylindrical_and_mixed_targets): hit distance
+    # and height coordinate identical up to torch's MKL sqrt, the angle up to an ulp of atan2 (round 1: 0.05 px)
     for g, w in zip(got[:2], want[:2]):
-        assert (g.cpu() - w)[hit].abs().max() < 0.05
-    assert ((got[2].cpu() - want[2])[hit].abs() / want[2][hit]).max() < 1e-5
-    assert ((got[3].cpu() - want[3])[hit].abs() / want[3][hit]).max() < 1e-3
+        assert (g.cpu() - w)[hit].abs().max() < 1e-3
+    assert (got[2].cpu() == want[2])[hit].float().mean() >= 0.999
+    assert ((got[2].cpu() - want[2])[hit].abs() / want[2][hit]).max() < 2.5e-7
+    assert ((got[3].cpu() - want[3])[hit].abs() / want[3][hit]).max() < 2e-6
 
 
 def test_bilinear_splatting_method_and_edge_rows():

@@ -67,14 +67,14 @@ def test_large_mode_mixed_planar_and_cylindrical_targets_vs_oracle():
     planar = case["target_idx"] == 0
     assert (flux.cpu()[planar] - ref[planar]).abs().max() <= 1e-5 * ref[planar].max()
     assert torch.equal(ic.cpu()[planar], ric[planar]) and torch.equal(ot.cpu()[planar], rot[planar])
-    # cylinder rows: fp32 conditioning of the quadratic (see test_cylindrical_and_mixed_targets) - hits move by ~0.01 px and
-    # a handful of the 260 000 rays fall on the other side of the opening-angle / height window, each worth one ray weight
-    # in bitmaps whose peak is only ~3 ray weights: the power per heliostat and all but a few pixels agree
+    # cylinder rows: hit distance / height follow the reference bit for bit for 99.99 % of the 260 000 rays; the angular
+    # coordinate differs in the last bit for 16 % of them (atan2), i.e. tap weights move by <= 3e-4 px in bitmaps whose
+    # peak is only ~3 ray weights.  Measured: flux 1.2e-4 of that peak, power per heliostat 2e-7, factors identical
+    # (round 1: "all but a few pixels within 5e-3", power 2e-3)
     fc, rc = flux.cpu()[~planar], ref[~planar]
-    assert ((fc.sum((1, 2)) - rc.sum((1, 2))).abs() / rc.sum((1, 2))).max() <= 2e-3
-    bad = ((fc - rc).abs() > 5e-3 * rc.max()).sum().item()
-    assert bad <= 1e-5 * fc.numel(), f"{bad} cylinder pixels differ by more than 5e-3 of the peak"
-    assert (ic.cpu() - ric).abs().max() < 2e-3
+    assert (fc - rc).abs().max() <= 5e-4 * rc.max()
+    assert ((fc.sum((1, 2)) - rc.sum((1, 2))).abs() / rc.sum((1, 2))).max() <= 2e-6
+    assert (ic.cpu() - ric).abs().max() <= 1e-6
 
 
 @pytest.mark.parametrize("trig_mode", [1, 2])

@@ -160,6 +160,10 @@ def test_backward_matches_oracle_autograd(pattern):
             ref_err = (g32[~planar].double() - g64[~planar]).abs().max() / scale64
             err = (got[~planar].double() - g64[~planar]).abs().max() / scale64
             assert err <= max(2 * ref_err, 1e-3), f"cylinder grad {name}: {err:.3e} (fp32 oracle itself {ref_err:.3e})"
+            # ... and, now that the hits follow the reference bit for bit, the reference's OWN fp32 gradient (which is
+            # 24-33 % away from the float64 value through b^2 - 4ac) is reproduced like the planar one: measured 1.2e-5 / 1.5e-5
+            err32 = (got[~planar] - g32[~planar]).abs().max() / g32[~planar].abs().max()
+            assert err32 <= 2e-4, f"cylinder grad {name} vs the fp32 oracle: {err32:.3e}"
 
 
 def test_irregular_rays_take_the_generic_path():
