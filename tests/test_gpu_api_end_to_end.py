@@ -186,11 +186,13 @@ def test_motor_position_and_deviation_gradients_vs_oracle_autograd(n):
     # (two fp32 evaluations of this chain scatter around the exact result: measured with tools/diag_parity.py, the CPU
     # oracle's and the kernels' distances to float64 are 1e-4 ... 8e-4 of the peak pixel depending on the heliostats; the
     # trace itself, fed the oracle's orientations, reproduces the oracle to 2e-6)
-    caps = (1.5e-3, 5e-3, 5e-3)
+    caps = (1.5e-3, 5e-4, 5e-4)
     for name, o, r32, cap in zip(("flux", "motor-position gradient", "rotation-deviation gradient"), own, ref32, caps):
         assert o <= max(10.0 * r32, 2e-4) and o <= cap, f"{name}: error vs float64 {o:.2e}, the fp32 oracle's own {r32:.2e}"
     # and, in absolute terms, close to the fp32 oracle as well
-    assert rel(total.detach(), t32.double()) <= 3e-3 and rel(motor.grad, gm32) <= 5e-3 and rel(rot.grad, gr32) <= 5e-3
+    # (measured, the two parametrisations: flux 8e-5 / 7.8e-4 of peak, gradients 2.5e-6 / 1.7e-4 - the second one has a
+    # heliostat whose orientation differs from torch-CPU's in the last bit; round 1 bars: 3e-3 and 5e-3)
+    assert rel(total.detach(), t32.double()) <= 1.5e-3 and rel(motor.grad, gm32) <= 5e-4 and rel(rot.grad, gr32) <= 5e-4
 
 
 def test_lazy_alignment_fused_and_materialised_paths_agree():
