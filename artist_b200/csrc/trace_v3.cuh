@@ -98,7 +98,12 @@ struct RowTrig {
 __device__ __forceinline__ void sincos_tiny_p(P2 x, P2& s, P2& c, const PK& K) {   // = sincos_tiny2
     const P2 z = K.mul(x, x);
     s = fma2(K.mul(x, z), pb(-1.6666667163e-1f), x);
+#ifndef AB200_COS_CORRECTLY_ROUNDED
+    const P2 ax = x & 0x7fffffff7fffffffull;   // |x| in both lanes
+    c = fma2(pb(-1.0f), fma2(pb(kCosBiasB), ax, fma2(pb(0.5f), z, pb(-kCosBiasA))), pb(1.0f));
+#else
     c = fma2(pb(-0.5f), z, pb(1.0f));
+#endif
 }
 __device__ __forceinline__ void sincos_poly_p(P2 x, P2& s, P2& c, const PK& K) {   // = sincos_poly_core2
     const P2 z = K.mul(x, x);

@@ -62,6 +62,9 @@ def test_planar_device_trig_index_flip_rate(trig_mode):
     (flux, *_), (dbe, dbu, _, _) = _run_cuda(case, res, trig_mode=trig_mode, debug=True)
     flips = ((dbe.cpu().long() != be.long()) | (dbu.cpu().long() != bu.long())).sum().item()
     assert flips <= 1e-4 * be.numel(), f"{flips} index flips of {be.numel()} rays"
+    if trig_mode == 2:   # the polynomial reproduces torch's CPU cos incl. its rounding bias (common.cuh): measured 0 flips of
+        neq = ((dbe.cpu() != be) | (dbu.cpu() != bu)).float().mean().item()      # 1.6e6 rays, 0.09 % of coordinates differ
+        assert flips <= 4e-6 * be.numel() and neq <= 5e-3, f"{flips} flips, {neq:.2e} of the coordinates differ in some bit"
     assert (dbe.cpu() - be).abs().max() < 1e-3 and (dbu.cpu() - bu).abs().max() < 1e-3
     ref, *_ = O.trace_rays(case["points"], case["normals"], case["incident"], case["dist_u"], case["dist_e"],
                            case["target_idx"], case["targets"], res)
