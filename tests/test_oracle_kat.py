@@ -260,3 +260,25 @@ def test_cpu_rounding_sequence_of_the_small_batched_matrix_products():
     assert np.array_equal(acc, (a.transpose(-1, -2) @ v[:, :, None])[:, :, 0].numpy())
     south = torch.tensor([0.0, -1.0, 0.0, 0.0])
     assert np.array_equal((a @ south).numpy(), -a.numpy()[:, :, 1])
+
+
+def test_cpu_cosine_rounding_bias_the_production_polynomial_reproduces():
+    """Parity note behind `sincos_tiny` (csrc/common.cuh): for sun-shape angles torch's CPU cos is the correctly rounded
+    float for only ~91 % of the arguments; it rounds 1 - x^2/2 up once the fraction of the last ulp exceeds 0.40 + 6|x|.
+    The kernel's c = RN(1 - (x^2/2 - (0.1 - 6|x|) 2^-24)) - emulated here in float32 - is torch's value for > 99.9 %."""
+    import numpy as np
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1 << 18, generator=g) * (4.3681e-06 ** 0.5)
+    want = torch.cos(x).numpy()
+    xn = x.numpy()
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    fma = lambda a, b, c: _f32(f64(a) * f64(b) + f64(c))
+    z = _f32(xn * xn)
+    a, b = np.float32(5.9604645e-09), np.float32(3.5762787e-07)
+    model = fma(np.float32(-1.0), fma(b, np.abs(xn), fma(np.float32(0.5), z, -a)), np.float32(1.0))
+    correctly_rounded = _f32(np.cos(f64(xn)))
+    assert (model != want).mean() < 1e-3, f"{(model != want).mean():.2e}"
+    assert (correctly_rounded != want).mean() > 0.05      # why the correctly rounded cosine was not good enough
+    sin_model = fma(_f32(xn * z), np.float32(-1.6666667163e-1), xn)
+    assert (sin_model != torch.sin(x).numpy()).mean() < 1e-4
