@@ -10,6 +10,9 @@
 
 namespace ab200 {
 
+// atan2 in double precision, rounded once to float (the correctly rounded value)
+__device__ __forceinline__ float atan2_rounded_once(float y, float x) { return (float)atan2((double)y, (double)x); }
+
 // Per-CTA target constants (one heliostat-sample aims at one target area).
 struct TargetCtx {
     int planar;
@@ -84,7 +87,7 @@ __device__ inline void load_target(TargetCtx& T, const ab200_targets& tg, int ti
         T.opn = tg.cyl_opening[k];
         T.w = T.opn;  // "width" of the unwrapped sector is the opening angle
         T.half_w = 0.f;
-        T.ang0 = ssub((float)atan2((double)T.n1, (double)T.n0), sdiv(T.opn, 2.0f));   // once per CTA: correctly rounded
+        T.ang0 = ssub(atan2_rounded_once(T.n1, T.n0), sdiv(T.opn, 2.0f));   // once per CTA: correctly rounded
         T.px_per_m_e = T.em1 / fmaxf(rad * T.opn, 1e-6f);
         T.px_per_m_u = T.um1 / T.h;
         T.rw = __frcp_rn(T.opn);
@@ -273,7 +276,7 @@ __device__ __forceinline__ void hit_cylinder(Hit& h, const TargetCtx& T, const P
     float lam = sadd(smul(-dlx, nlx), smul(-dly, nly));
     lam = fmaxf(lam, 0.0f);
     z = sadd(z, T.half_h);
-    const float ang = ssub(CRATAN ? (float)atan2((double)y, (double)x) : atan2f(y, x), T.ang0);
+    const float ang = ssub(CRATAN ? atan2_rounded_once(y, x) : atan2f(y, x), T.ang0);
     const bool on = (z >= 0.0f) && (z <= T.h) && (ang >= 0.0f) && (ang <= T.opn);
     const bool valid = on && vd;
     h.valid = valid;
