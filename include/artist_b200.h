@@ -35,7 +35,9 @@ extern "C" {
 /* trig source for the per-ray scatter rotation (artist/geometry/transforms.py:52-55) */
 #define AB200_TRIG_SINCOSF 0 /* libdevice sincosf (default) */
 #define AB200_TRIG_TABLE 1   /* strict parity: consume caller-computed cos/sin (args->trig) */
-#define AB200_TRIG_POLY 2    /* small-angle polynomial (<= 1 ulp for |x| <= pi/4), sincosf otherwise */
+#define AB200_TRIG_POLY 2    /* small-angle polynomial (<= 1 ulp for |x| <= pi/4), sincosf otherwise; for |x| <= 0.01 (any physical
+                              * sun shape) the cosine is torch's CPU cos incl. its rounding bias, so that no ray changes pixel
+                              * against the reference (csrc/common.cuh; -DAB200_COS_CORRECTLY_ROUNDED: the correctly rounded one) */
 
 /* flags */
 #define AB200_FLAG_FP32_ACCUM 1 /* accumulate the bitmap with fp32 shared-memory atomics instead of the
